@@ -1,0 +1,67 @@
+"""Class-attribute configs with the reference's semantics (src/config.py:45-160): a ``Config`` nested class lists the
+fields, ``Configurable.__init__`` copies them onto ``self``; nested configs and ``update(dict)`` are supported so the
+reference's JSON files and ``-s a.b value`` overrides keep working."""
+import copy
+
+SIMPLE_TYPES = (bool, int, float, str)
+
+
+class Optional:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+
+class BaseConfig:
+    def vars(self):
+        out = {}
+        for key in dir(self):
+            if key.startswith("_"):
+                continue
+            val = getattr(self, key)
+            if callable(val):
+                continue
+            out[key] = val
+        return out
+
+    def __init__(self, **kwargs):
+        v = self.vars()
+        v.update(kwargs)
+        for key, val in v.items():
+            setattr(self, key, copy.deepcopy(val) if isinstance(val, BaseConfig) else val)
+
+    def update(self, d):
+        for key, val in d.items():
+            assert hasattr(self, key), f"Cannot set non-existent key {key} in {type(self).__name__}"
+            cur = getattr(self, key)
+            if isinstance(val, dict) and isinstance(cur, BaseConfig):
+                cur.update(val)
+            else:
+                if isinstance(cur, float) and isinstance(val, int) and not isinstance(val, bool):
+                    val = float(val)
+                setattr(self, key, val)
+        return self
+
+    def nested_set(self, path, value):
+        obj = self
+        for p in path[:-1]:
+            obj = getattr(obj, p)
+        assert hasattr(obj, path[-1]), f"Cannot override non-existent key {'.'.join(path)}"
+        setattr(obj, path[-1], value)
+
+    def verify(self):
+        for key, val in self.vars().items():
+            if isinstance(val, BaseConfig):
+                val.verify()
+            elif isinstance(val, Optional):
+                setattr(self, key, None)
+
+
+class Configurable:
+    """Subclasses define a nested ``Config``; its fields become attributes of the instance."""
+
+    def __init__(self, config):
+        assert type(config) is self.__class__.Config, f"expected {self.__class__.Config}, got {type(config)}"
+        self.config = copy.deepcopy(config)
+        self.config.verify()
+        for key, val in self.config.vars().items():
+            setattr(self, key, val)

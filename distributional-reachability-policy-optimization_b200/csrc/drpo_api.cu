@@ -1,0 +1,303 @@
+// extern "C" entry points of libdrpo_sm100.so (see include/drpo_b200.h for the contract of each).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "critic.cuh"
+#include "nets.cuh"
+#include "rollout.cuh"
+#include "umma_api.h"
+
+namespace drpo {
+static thread_local char g_err[1024] = "";
+int64_t g_launch_count = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+__global__ void philox_fill_kernel(float* out, int64_t n, int cols, const int32_t* row_ids, uint64_t seed, uint32_t tag, uint32_t step) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * cols; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols; const int c = (int)(i % cols);
+    out[i] = philox_normal1(seed, (uint32_t)(row_ids ? row_ids[r] : r), (uint32_t)c, tag, step);
+  }
+}
+}  // namespace drpo
+
+using namespace drpo;
+
+extern "C" {
+
+const char* drpo_last_error(void) { return g_err; }
+int drpo_abi_version(void) { return DRPO_ABI_VERSION; }
+int64_t drpo_launch_count(void) { return g_launch_count; }
+
+int drpo_philox_normal(float* out, int64_t n, int32_t cols, const int32_t* row_ids, uint64_t seed, uint32_t stream_tag,
+                       uint32_t step, void* stream) {
+  DRPO_CHECK_ARG(out && n >= 0 && cols > 0, "drpo_philox_normal: bad arguments");
+  if (n == 0) return DRPO_OK;
+  DRPO_LAUNCH(philox_fill_kernel, grid_for(n * cols), 256, 0, stream, out, n, cols, row_ids, seed, stream_tag, step);
+  return DRPO_OK;
+}
+
+static int check_env(const drpo_env_params* e) {
+  DRPO_CHECK_ARG(e, "env params are NULL");
+  DRPO_CHECK_ARG(e->kind >= DRPO_ENV_POINT_ROBOT && e->kind <= DRPO_ENV_TRACKING, "unknown env kind %d", e->kind);
+  DRPO_CHECK_ARG(e->state_dim > 0 && e->con_dim > 0 && e->con_dim <= DRPO_MAX_CON, "bad env dims S=%d C=%d", e->state_dim, e->con_dim);
+  if (e->kind == DRPO_ENV_POINT_ROBOT)
+    DRPO_CHECK_ARG(e->state_dim >= 2 && e->con_dim == 1 && e->n_hazards >= 1 && e->n_hazards <= DRPO_MAX_HAZARDS, "bad point-robot params");
+  if (e->kind == DRPO_ENV_BOUNDED) {
+    DRPO_CHECK_ARG(e->n_active >= 1 && e->n_active <= DRPO_MAX_ACTIVE && e->con_dim == 2 * e->n_active, "bounded env: con_dim must be 2*n_active");
+    for (int i = 0; i < e->n_active; ++i) DRPO_CHECK_ARG(e->active_dims[i] >= 0 && e->active_dims[i] < e->state_dim, "active dim out of range");
+    DRPO_CHECK_ARG(e->n_done_dims >= 0 && e->n_done_dims <= DRPO_MAX_DONE_DIMS, "bad n_done_dims");
+    for (int i = 0; i < e->n_done_dims; ++i) DRPO_CHECK_ARG(e->done_dims[i] >= 0 && e->done_dims[i] < e->state_dim, "done dim out of range");
+  }
+  if (e->kind == DRPO_ENV_TRACKING)
+    DRPO_CHECK_ARG(e->con_dim == 1 && e->surr_veh_num >= 1 && e->surr_start >= 7 && e->surr_start + 4 * e->surr_veh_num <= e->state_dim,
+                   "bad tracking params");
+  return DRPO_OK;
+}
+
+int drpo_hooks_eval(const drpo_env_params* env, const float* states, int64_t n, uint8_t* done, uint8_t* violation,
+                    float* constraint_values, void* stream) {
+  int rc = check_env(env); if (rc) return rc;
+  DRPO_CHECK_ARG(n >= 0 && (n == 0 || states), "drpo_hooks_eval: bad arguments");
+  if (n == 0) return DRPO_OK;
+  DRPO_LAUNCH(hooks_kernel, grid_for(n), 256, 0, stream, *env, states, n, done, violation, constraint_values, (const int*)nullptr);
+  return DRPO_OK;
+}
+
+static int check_ens(const drpo_ensemble* e) {
+  DRPO_CHECK_ARG(e && e->state_dim > 0 && e->action_dim > 0 && e->ensemble_size > 0 && e->hidden > 0, "bad ensemble dims");
+  DRPO_CHECK_ARG(e->norm_mean && e->norm_std && e->min_log_var && e->max_log_var && e->trunk0_w && e->trunk0_b && e->trunk1_w &&
+                 e->trunk1_b && e->diff0_w && e->diff0_b && e->diff1_w && e->diff1_b && e->lvar0_w && e->lvar0_b && e->lvar1_w && e->lvar1_b,
+                 "ensemble weight pointer is NULL");
+  return DRPO_OK;
+}
+
+int64_t drpo_ensemble_workspace_bytes(const drpo_ensemble* ens, int64_t batch) {
+  if (!ens || batch < 0) return -1;
+  return ens_scratch_floats(*ens, batch) * 4 + 16 * 256;
+}
+
+int drpo_ensemble_forward(const drpo_ensemble* ens, int32_t member, int32_t per_member_inputs, const float* states,
+                          const float* actions, int64_t batch, float* means, float* log_vars, int32_t precision, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  int rc = check_ens(ens); if (rc) return rc;
+  DRPO_CHECK_ARG(member >= -1 && member < ens->ensemble_size, "member %d out of range", member);
+  DRPO_CHECK_ARG(batch >= 0 && states && actions && means && log_vars, "drpo_ensemble_forward: bad arguments");
+  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_ensemble_forward: only DRPO_PREC_FP32 here (the bf16 path is fused into drpo_rollout)");
+  if (batch == 0) return DRPO_OK;
+  Arena ar(workspace, workspace_bytes);
+  EnsScratch w = ens_scratch(ar, *ens, batch);
+  if (!ar.ok()) { set_error("drpo_ensemble_forward: workspace too small"); return DRPO_ERR_WORKSPACE; }
+  const int S = ens->state_dim, A = ens->action_dim, O = S + 1;
+  const int m0 = member < 0 ? 0 : member, m1 = member < 0 ? ens->ensemble_size : member + 1;
+  for (int m = m0; m < m1; ++m) {
+    const int64_t slot = member < 0 ? m : 0;
+    const float* s = states + (per_member_inputs && member < 0 ? slot * batch * S : 0);
+    const float* a = actions + (per_member_inputs && member < 0 ? slot * batch * A : 0);
+    if ((rc = ens_member_raw(*ens, m, s, a, (int)batch, w, nullptr, stream))) return rc;
+    DRPO_LAUNCH(ens_head_kernel, grid_for(batch * O), 256, 0, stream, w.dd, w.lr, s, ens->min_log_var, ens->max_log_var,
+                means + slot * batch * O, log_vars + slot * batch * O, batch, S);
+  }
+  return DRPO_OK;
+}
+
+int drpo_ensemble_sample(const drpo_ensemble* ens, int32_t member, const float* states, const float* actions, int64_t batch,
+                         const drpo_noise* noise, float* next_states, float* rewards, int32_t precision, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  int rc = check_ens(ens); if (rc) return rc;
+  DRPO_CHECK_ARG(member >= 0 && member < ens->ensemble_size, "member %d out of range", member);
+  DRPO_CHECK_ARG(batch >= 0 && states && actions && noise && next_states && rewards, "drpo_ensemble_sample: bad arguments");
+  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_ensemble_sample: only DRPO_PREC_FP32 here");
+  if (batch == 0) return DRPO_OK;
+  Arena ar(workspace, workspace_bytes);
+  EnsScratch w = ens_scratch(ar, *ens, batch);
+  if (!ar.ok()) { set_error("drpo_ensemble_sample: workspace too small"); return DRPO_ERR_WORKSPACE; }
+  const int S = ens->state_dim;
+  if ((rc = ens_member_raw(*ens, member, states, actions, (int)batch, w, nullptr, stream))) return rc;
+  NoiseView nv = make_noise(noise->eps, noise->row_stride, noise->seed, noise->stream_tag, noise->step);
+  DRPO_LAUNCH(ens_sample_kernel, grid_for(batch * (S + 1)), 256, 0, stream, w.dd, w.lr, states, ens->min_log_var, ens->max_log_var, nv,
+              (const int32_t*)nullptr, next_states, rewards, batch, S, (const int*)nullptr);
+  return DRPO_OK;
+}
+
+static int check_mlp3(const drpo_mlp3* m, const char* what) {
+  DRPO_CHECK_ARG(m && m->l0.w && m->l0.b && m->l1.w && m->l1.b && m->l2.w && m->l2.b, "%s: weight pointer is NULL", what);
+  DRPO_CHECK_ARG(m->l0.out_dim == m->l1.in_dim && m->l1.out_dim == m->l2.in_dim && m->l0.in_dim > 0 && m->l2.out_dim > 0,
+                 "%s: inconsistent layer dims", what);
+  return DRPO_OK;
+}
+static int check_qc(const drpo_qc* q, const char* what) {
+  DRPO_CHECK_ARG(q && q->trunk0.w && q->trunk1.w && q->mean0.w && q->mean1.w && q->lstd0.w && q->lstd1.w && q->trunk0.b && q->trunk1.b &&
+                 q->mean0.b && q->mean1.b && q->lstd0.b && q->lstd1.b, "%s: weight pointer is NULL", what);
+  return DRPO_OK;
+}
+
+int64_t drpo_policy_workspace_bytes(const drpo_mlp3* actor, int64_t batch) {
+  if (!actor || batch < 0) return -1;
+  return pol_scratch_floats(*actor, batch) * 4 + 8 * 256;
+}
+
+int drpo_policy_act(const drpo_mlp3* actor, const float* states, int64_t batch, int32_t eval_mode, const drpo_noise* noise,
+                    float* actions, float* log_prob, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_mlp3(actor, "drpo_policy_act"); if (rc) return rc;
+  DRPO_CHECK_ARG(batch >= 0 && states && actions && (eval_mode || noise), "drpo_policy_act: bad arguments");
+  DRPO_CHECK_ARG(actor->l2.out_dim % 2 == 0, "actor output dim must be 2*action_dim");
+  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_policy_act: only DRPO_PREC_FP32 here");
+  if (batch == 0) return DRPO_OK;
+  Arena ar(workspace, workspace_bytes);
+  PolScratch w = pol_scratch(ar, *actor, batch);
+  if (!ar.ok()) { set_error("drpo_policy_act: workspace too small"); return DRPO_ERR_WORKSPACE; }
+  if ((rc = mlp3_fwd(*actor, states, actor->l0.in_dim, (int)batch, ACT_RELU, w.hA, w.hB, w.out, nullptr, stream))) return rc;
+  NoiseView nv = noise ? make_noise(noise->eps, noise->row_stride, noise->seed, noise->stream_tag, noise->step) : make_noise(nullptr, 0, 0, 0, 0);
+  DRPO_LAUNCH(policy_head_kernel, grid_for(batch), 256, 0, stream, w.out, nv, (const int32_t*)nullptr, eval_mode, actions, log_prob, batch,
+              actor->l2.out_dim / 2, (const int*)nullptr);
+  return DRPO_OK;
+}
+
+int64_t drpo_qc_workspace_bytes(int64_t batch, int32_t hidden) {
+  return (batch * (4LL * hidden + 2 * DRPO_MAX_CON + 64)) * 4 + 16 * 256;
+}
+
+int drpo_qc_forward(const drpo_qc* qc, const float* states, const float* actions, int64_t batch, int32_t state_dim, int32_t action_dim,
+                    int32_t con_dim, int32_t mode, float std_ratio, const drpo_noise* noise, float* out_mean, float* out_std,
+                    float* out_sample, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_qc(qc, "drpo_qc_forward"); if (rc) return rc;
+  DRPO_CHECK_ARG(batch >= 0 && states && actions && mode >= 0 && mode <= 2, "drpo_qc_forward: bad arguments");
+  DRPO_CHECK_ARG(qc->trunk0.in_dim == state_dim + action_dim && qc->mean1.out_dim == con_dim, "drpo_qc_forward: dims do not match the network");
+  DRPO_CHECK_ARG(mode == 0 ? out_mean != nullptr : out_sample != nullptr, "drpo_qc_forward: output pointer is NULL");
+  DRPO_CHECK_ARG(mode != 2 || noise, "drpo_qc_forward: sample mode needs noise");
+  if (batch == 0) return DRPO_OK;
+  const int H = qc->trunk0.out_dim, D = state_dim + action_dim, C = con_dim;
+  Arena ar(workspace, workspace_bytes);
+  float* sa = ar.take<float>(batch * D);
+  QcActs a; a.t1 = ar.take<float>(batch * H); a.t2 = ar.take<float>(batch * H); a.m1 = ar.take<float>(batch * H); a.l1 = a.m1;
+  a.mean_raw = ar.take<float>(batch * C); a.ls_raw = ar.take<float>(batch * C);
+  if (!ar.ok()) { set_error("drpo_qc_forward: workspace too small"); return DRPO_ERR_WORKSPACE; }
+  DRPO_LAUNCH(cat2_kernel, grid_for(batch * D), 256, 0, stream, states, actions, sa, batch, state_dim, action_dim);
+  // the two heads share scratch (l1 aliases m1): run them one after the other
+  if ((rc = linear_fwd(sa, D, qc->trunk0, a.t1, H, (int)batch, ACT_RELU, nullptr, stream))) return rc;
+  if ((rc = linear_fwd(a.t1, H, qc->trunk1, a.t2, H, (int)batch, ACT_RELU, nullptr, stream))) return rc;
+  if ((rc = linear_fwd(a.t2, H, qc->mean0, a.m1, H, (int)batch, ACT_RELU, nullptr, stream))) return rc;
+  if ((rc = linear_fwd(a.m1, H, qc->mean1, a.mean_raw, C, (int)batch, ACT_NONE, nullptr, stream))) return rc;
+  if (mode != 0) {
+    if ((rc = linear_fwd(a.t2, H, qc->lstd0, a.l1, H, (int)batch, ACT_RELU, nullptr, stream))) return rc;
+    if ((rc = linear_fwd(a.l1, H, qc->lstd1, a.ls_raw, C, (int)batch, ACT_NONE, nullptr, stream))) return rc;
+  }
+  NoiseView nv = noise ? make_noise(noise->eps, noise->row_stride, noise->seed, noise->stream_tag, noise->step) : make_noise(nullptr, 0, 0, 0, 0);
+  DRPO_LAUNCH(qc_head_kernel, grid_for(batch * C), 256, 0, stream, a.mean_raw, a.ls_raw, mode, std_ratio, nv, (int64_t)0, out_mean, out_std,
+              out_sample, batch, C);
+  return DRPO_OK;
+}
+
+static int check_buffer(const drpo_buffer* b, const char* what) {
+  DRPO_CHECK_ARG(b && b->states && b->actions && b->next_states && b->rewards && b->dones && b->violations && b->constraint_values,
+                 "%s: buffer component pointer is NULL", what);
+  DRPO_CHECK_ARG(b->capacity > 0 && b->state_dim > 0 && b->action_dim > 0 && b->con_dim > 0, "%s: bad buffer dims", what);
+  return DRPO_OK;
+}
+
+int drpo_buffer_gather(const drpo_buffer* real, const drpo_buffer* virt, const int64_t* idx, int64_t n_real, int64_t n_total,
+                       float reward_scale, float alive_bonus, float constraint_scale, float constraint_offset, const drpo_batch* out,
+                       void* stream) {
+  int rc;
+  DRPO_CHECK_ARG(n_real >= 0 && n_total >= n_real && out && idx, "drpo_buffer_gather: bad arguments");
+  if (n_real > 0 && (rc = check_buffer(real, "drpo_buffer_gather(real)"))) return rc;
+  if (n_total > n_real && (rc = check_buffer(virt, "drpo_buffer_gather(virt)"))) return rc;
+  if (n_total == 0) return DRPO_OK;
+  const drpo_buffer* r = n_real > 0 ? real : virt; const drpo_buffer* v = n_total > n_real ? virt : real;
+  DRPO_CHECK_ARG(r->state_dim == v->state_dim && r->action_dim == v->action_dim && r->con_dim == v->con_dim, "buffers disagree on dims");
+  DRPO_LAUNCH(buffer_gather_kernel, grid_for(n_total * r->state_dim), 256, 0, stream, *r, *v, idx, n_real, n_total, reward_scale, alive_bonus,
+              constraint_scale, constraint_offset, *out);
+  return DRPO_OK;
+}
+
+static int check_rollout(const drpo_rollout_args* a) {
+  DRPO_CHECK_ARG(a && a->actor && a->ensemble && a->env, "drpo_rollout: NULL argument");
+  int rc;
+  if ((rc = check_mlp3(a->actor, "drpo_rollout(actor)"))) return rc;
+  if ((rc = check_ens(a->ensemble))) return rc;
+  if ((rc = check_env(a->env))) return rc;
+  if ((rc = check_buffer(&a->virt, "drpo_rollout(virt)"))) return rc;
+  const int S = a->ensemble->state_dim, A = a->ensemble->action_dim;
+  DRPO_CHECK_ARG(a->env->state_dim == S && a->actor->l0.in_dim == S && a->actor->l2.out_dim == 2 * A, "drpo_rollout: actor/ensemble/env dims disagree");
+  DRPO_CHECK_ARG(a->virt.state_dim == S && a->virt.action_dim == A && a->virt.con_dim == a->env->con_dim, "drpo_rollout: buffer dims disagree");
+  DRPO_CHECK_ARG(a->batch >= 0 && a->horizon >= 1 && a->member_idx_host && a->step_counts && a->virt.pointer, "drpo_rollout: bad arguments");
+  DRPO_CHECK_ARG(a->batch < (1LL << 31) && a->traj_id_offset + a->batch < (1LL << 31), "drpo_rollout: batch too large for 32-bit trajectory ids");
+  // SampleBuffer.extend asserts batch <= capacity (src/sampling.py:131); the rollout may append up to batch*horizon rows
+  DRPO_CHECK_ARG(a->batch * a->horizon <= a->virt.capacity, "drpo_rollout: batch*horizon (%lld) exceeds the buffer capacity (%lld)",
+                 (long long)(a->batch * a->horizon), (long long)a->virt.capacity);
+  for (int t = 0; t < a->horizon; ++t)
+    DRPO_CHECK_ARG(a->member_idx_host[t] >= 0 && a->member_idx_host[t] < a->ensemble->ensemble_size, "member index out of range at step %d", t);
+  DRPO_CHECK_ARG((a->eps_policy == nullptr) == (a->eps_model == nullptr), "give both or neither of eps_policy / eps_model");
+  return DRPO_OK;
+}
+
+int64_t drpo_rollout_workspace_bytes(const drpo_rollout_args* a) {
+  if (!a || !a->actor || !a->ensemble || !a->env) return -1;
+  int64_t fp32 = rollout_ws_bytes_fp32(*a);
+  int64_t bf16 = umma_rollout_ws_bytes(*a);
+  return fp32 > bf16 ? fp32 : bf16;
+}
+
+int drpo_rollout(const drpo_rollout_args* a) {
+  int rc = check_rollout(a); if (rc) return rc;
+  if (a->batch == 0) {
+    DRPO_CUDA_OK(cudaMemsetAsync(a->step_counts, 0, sizeof(int32_t) * (a->horizon + 1), (cudaStream_t)a->stream));
+    return DRPO_OK;
+  }
+  if (a->precision == DRPO_PREC_FP32) return rollout_fp32(*a);
+  if (a->precision == DRPO_PREC_BF16) return umma_rollout(*a);
+  set_error("drpo_rollout: unknown precision %d", a->precision);
+  return DRPO_ERR_ARG;
+}
+
+int64_t drpo_critic_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
+  return critic_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+}
+
+int drpo_critic_step(const drpo_critic_args* a) {
+  DRPO_CHECK_ARG(a, "drpo_critic_step: NULL args");
+  int rc;
+  if ((rc = check_mlp3(a->actor, "drpo_critic_step(actor)"))) return rc;
+  if ((rc = check_mlp3(a->actor_safe, "drpo_critic_step(actor_safe)"))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = check_mlp3(&a->q[i], "drpo_critic_step(q)"))) return rc;
+    if ((rc = check_mlp3(&a->q_target[i], "drpo_critic_step(q_target)"))) return rc;
+  }
+  if ((rc = check_qc(&a->qc, "drpo_critic_step(qc)"))) return rc;
+  if ((rc = check_qc(&a->qc_target, "drpo_critic_step(qc_target)"))) return rc;
+  DRPO_CHECK_ARG(a->batch_size >= 1 && a->global_batch_size >= a->batch_size, "drpo_critic_step: bad batch sizes");
+  DRPO_CHECK_ARG(a->con_dim >= 1 && a->con_dim <= DRPO_MAX_CON, "drpo_critic_step: bad con_dim");
+  DRPO_CHECK_ARG(a->params && a->grads && a->adam_m && a->adam_v && a->target_params && a->losses && a->log_alpha, "drpo_critic_step: NULL arena");
+  DRPO_CHECK_ARG(a->q[0].l0.in_dim == a->state_dim + a->action_dim && a->qc.mean1.out_dim == a->con_dim, "drpo_critic_step: dims disagree");
+  DRPO_CHECK_ARG(a->q[0].l0.out_dim <= 256 && a->q[0].l0.in_dim + 1 <= 320, "drpo_critic_step: hidden/input dims too large for the split-K scratch");
+  DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_critic_step: bad phases");
+  if (a->phases & 1) {
+    const drpo_batch& b = a->batch;
+    DRPO_CHECK_ARG(b.obs && b.act && b.next_obs && b.rew && b.done && b.cv, "drpo_critic_step: NULL batch tensor");
+  }
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32, "drpo_critic_step: only DRPO_PREC_FP32 is implemented");
+  return critic_step_fp32(*a);
+}
+
+int64_t drpo_multiplier_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
+  return mult_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+}
+
+int drpo_multiplier_step(const drpo_multiplier_args* a) {
+  DRPO_CHECK_ARG(a, "drpo_multiplier_step: NULL args");
+  int rc;
+  if ((rc = check_mlp3(a->actor, "drpo_multiplier_step(actor)"))) return rc;
+  if ((rc = check_mlp3(a->actor_safe, "drpo_multiplier_step(actor_safe)"))) return rc;
+  if ((rc = check_mlp3(&a->lam, "drpo_multiplier_step(lam)"))) return rc;
+  if ((rc = check_qc(a->qc, "drpo_multiplier_step(qc)"))) return rc;
+  DRPO_CHECK_ARG(a->batch_size >= 1 && a->global_batch_size >= a->batch_size && a->obs, "drpo_multiplier_step: bad batch");
+  DRPO_CHECK_ARG(a->lam.l0.in_dim == a->state_dim + 1 && a->lam.l2.out_dim == 1, "drpo_multiplier_step: multiplier dims disagree");
+  DRPO_CHECK_ARG(a->params && a->grads && a->adam_m && a->adam_v && a->losses, "drpo_multiplier_step: NULL arena");
+  DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_multiplier_step: bad phases");
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32, "drpo_multiplier_step: only DRPO_PREC_FP32 is implemented");
+  return multiplier_step_fp32(*a);
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// fp32 FMA GEMM with fused prologue/epilogue — the DRPO_PREC_FP32 (<=1e-5 parity) path and the workhorse of the
+// hand-written backward pass.  C[M,N] = epilogue( sum_k A(m,k) * B(k,n) ), operands addressed through element
+// strides so that  Y = X W^T (forward),  dX = dY W (backward-data)  and  dW = dY^T X (backward-weight, split-K
+// over the batch) are the same kernel.  64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+#pragma once
+#include "common.cuh"
+
+namespace drpo {
+
+struct GemmArgs {
+  const float* A; int64_t a_sm, a_sk;    // A(m,k) = A[m*a_sm + k*a_sk]
+  const float* B; int64_t b_sk, b_sn;    // B(k,n) = B[k*b_sk + n*b_sn]
+  float* C; int64_t ldc;                 // C[m*ldc + n]
+  const float* bias;                     // [N], added before the activation (may be null)
+  int M, N, K;
+  const int* m_dev;                      // optional device-side row count (rollout: alive rows of this step)
+  int act;                               // Act applied to (acc + bias)
+  const float* mask; int64_t ldmask;     // backward-data: multiply by act'(saved post-activation output)
+  int mask_mode;                         // 0 none, 1 relu' (mask>0), 2 tanh' (1-mask^2)
+  float beta;                            // C = result + beta*C
+  float* bias_out;                       // backward-weight: B gets a virtual all-ones last column; that column of the
+                                         // result (= column sums of dY = db) is routed to bias_out[m]
+  int splitk; float* partial;            // split-K: raw partial sums [splitk, M, N], reduced by splitk_reduce_kernel
+};
+
+constexpr int GM = 64, GN = 64, GK = 16, GPAD = 4;
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[GK][GM + GPAD];
+  __shared__ __align__(16) float Bs[GK][GN + GPAD];
+  int M = g.M;
+  if (g.m_dev) M = min(M, *g.m_dev);
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  if (m0 >= M) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int N = g.N, K = g.K;
+  const int n_real = g.bias_out ? N - 1 : N;     // columns of B that exist in memory
+  int k_begin = 0, k_end = K;
+  if (g.splitk > 1) {
+    int chunk = ((K + g.splitk - 1) / g.splitk + GK - 1) / GK * GK;
+    k_begin = blockIdx.z * chunk;
+    k_end = min(K, k_begin + chunk);
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const bool a_kcontig = (g.a_sk == 1), b_kcontig = (g.b_sk == 1);
+  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      int m, k;
+      if (a_kcontig) { k = tid & 15; m = (tid >> 4) + 16 * p; } else { m = tid & 63; k = (tid >> 6) + 4 * p; }
+      float v = 0.f;
+      if (m0 + m < M && k0 + k < k_end) v = g.A[(int64_t)(m0 + m) * g.a_sm + (int64_t)(k0 + k) * g.a_sk];
+      As[k][m] = v;
+      int n;
+      if (b_kcontig) { k = tid & 15; n = (tid >> 4) + 16 * p; } else { n = tid & 63; k = (tid >> 6) + 4 * p; }
+      v = 0.f;
+      if (k0 + k < k_end) {
+        if (n0 + n < n_real) v = g.B[(int64_t)(k0 + k) * g.b_sk + (int64_t)(n0 + n) * g.b_sn];
+        else if (g.bias_out && n0 + n == N - 1) v = 1.f;
+      }
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (g.splitk > 1) { g.partial[((int64_t)blockIdx.z * g.M + m) * N + n] = v; continue; }
+      if (g.bias) v += g.bias[n];
+      v = apply_act(v, g.act);
+      if (g.mask_mode) {
+        const float mk = g.mask[(int64_t)m * g.ldmask + n];
+        v *= (g.mask_mode == 1) ? (mk > 0.f ? 1.f : 0.f) : (1.f - mk * mk);
+      }
+      if (g.bias_out && n == N - 1) { g.bias_out[m] = v + (g.beta != 0.f ? g.beta * g.bias_out[m] : 0.f); continue; }
+      float* c = g.C + (int64_t)m * g.ldc + n;
+      *c = v + (g.beta != 0.f ? g.beta * *c : 0.f);
+    }
+  }
+}
+
+// deterministic second stage of split-K (fixed summation order over the splits)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splitk, int M, int N, float* C, int64_t ldc,
+                                     float* bias_out, float beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float s = 0.f;
+  for (int z = 0; z < splitk; ++z) s += partial[((int64_t)z * M + m) * N + n];
+  if (bias_out && n == N - 1) { bias_out[m] = s + (beta != 0.f ? beta * bias_out[m] : 0.f); return; }
+  float* c = C + (int64_t)m * ldc + n;
+  *c = s + (beta != 0.f ? beta * *c : 0.f);
+}
+
+static inline GemmArgs gemm_args() { GemmArgs g; memset(&g, 0, sizeof(g)); g.splitk = 1; return g; }
+
+static inline int launch_gemm(const GemmArgs& g, void* stream) {
+  if (g.M <= 0 || g.N <= 0) return DRPO_OK;
+  dim3 grid((g.N + GN - 1) / GN, (g.M + GM - 1) / GM, g.splitk > 1 ? g.splitk : 1);
+  DRPO_LAUNCH(gemm_f32_kernel, grid, 256, 0, stream, g);
+  if (g.splitk > 1) {
+    int64_t total = (int64_t)g.M * g.N;
+    DRPO_LAUNCH(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, g.partial, g.splitk, g.M, g.N,
+                g.C, g.ldc, g.bias_out, g.beta);
+  }
+  return DRPO_OK;
+}
+
+// ---- convenience wrappers -------------------------------------------------------------------------------------
+// Y[M,N] = act(X[M,K] W[N,K]^T + b)
+static inline int linear_fwd(const float* X, int64_t ldx, const drpo_linear& L, float* Y, int64_t ldy, int M, int act,
+                             const int* m_dev, void* stream) {
+  GemmArgs g = gemm_args();
+  g.A = X; g.a_sm = ldx; g.a_sk = 1;
+  g.B = L.w; g.b_sk = 1; g.b_sn = L.in_dim;
+  g.C = Y; g.ldc = ldy; g.bias = L.b; g.M = M; g.N = L.out_dim; g.K = L.in_dim; g.act = act; g.m_dev = m_dev;
+  return launch_gemm(g, stream);
+}
+// dX[M,K] = (dY[M,N] W[N,K]) * act'(saved)   (+ beta*dX)
+static inline int linear_bwd_data(const float* dY, int64_t ldy, const drpo_linear& L, float* dX, int64_t lddx, int M,
+                                  const float* saved, int64_t ldsaved, int mask_mode, float beta, void* stream) {
+  GemmArgs g = gemm_args();
+  g.A = dY; g.a_sm = ldy; g.a_sk = 1;
+  g.B = L.w; g.b_sk = L.in_dim; g.b_sn = 1;
+  g.C = dX; g.ldc = lddx; g.M = M; g.N = L.in_dim; g.K = L.out_dim;
+  g.mask = saved; g.ldmask = ldsaved; g.mask_mode = mask_mode; g.beta = beta;
+  return launch_gemm(g, stream);
+}
+// dW[N,K] = dY[M,N]^T X[M,K],  db[N] = column sums of dY ; split-K over the batch with a deterministic reduction
+static inline int linear_bwd_weight(const float* dY, int64_t ldy, const float* X, int64_t ldx, int M, int n_out, int k_in,
+                                    float* dW, float* db, float* partial, int64_t partial_floats, void* stream) {
+  GemmArgs g = gemm_args();
+  g.A = dY; g.a_sm = 1; g.a_sk = ldy;
+  g.B = X; g.b_sk = ldx; g.b_sn = 1;
+  g.C = dW; g.ldc = k_in; g.M = n_out; g.N = k_in + 1; g.K = M; g.bias_out = db;
+  int tiles = ((g.N + GN - 1) / GN) * ((g.M + GM - 1) / GM);
+  int want = (M + 511) / 512;                         // >= 512 batch rows per split
+  int cap = (296 + tiles - 1) / tiles;                // about two waves of 148 SMs
+  int sk = want < cap ? want : cap;
+  while (sk > 1 && (int64_t)sk * g.M * g.N > partial_floats) --sk;
+  if (sk > 1) { g.splitk = sk; g.partial = partial; }
+  return launch_gemm(g, stream);
+}
+
+}  // namespace drpo

@@ -1,0 +1,7 @@
+// Interface between the C-ABI translation unit and the tcgen05 (DRPO_PREC_BF16) translation unit.
+#pragma once
+#include "../../include/drpo_b200.h"
+namespace drpo {
+int64_t umma_rollout_ws_bytes(const drpo_rollout_args& a);
+int umma_rollout(const drpo_rollout_args& a);
+}  // namespace drpo

@@ -1,0 +1,532 @@
+"""Safe SAC learner with the reference's API (src/ssac.py).  ``update_critic`` and ``update_multiplier`` — the hot
+path — run as hand-written CUDA behind the C ABI (forward, hand-written backward, clip, Adam, EMA); parameters live in
+flat fp32 arenas that the ``nn.Parameter`` views alias, so ``state_dict`` round-trips the reference keys."""
+import copy
+import math
+import random
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import _lib
+from .config import BaseConfig, Configurable, Optional
+from .policy import BasePolicy, SquashedGaussianPolicy
+
+
+class Squeeze(nn.Module):
+    def __init__(self, dim=None):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, x):
+        return x.squeeze(dim=self.dim)
+
+
+_ACTS = {"relu": nn.ReLU, "tanh": nn.Tanh, "identity": nn.Identity, "swish": nn.SiLU}
+
+
+def mlp(dims, activation="relu", output_activation=None, squeeze_output=False, device=None):
+    """src/torch_util.py:190-211: xavier-normal weights, zero biases."""
+    layers = []
+    for i in range(len(dims) - 2):
+        layers += [nn.Linear(dims[i], dims[i + 1], device=device), _ACTS[activation]()]
+    layers.append(nn.Linear(dims[-2], dims[-1], device=device))
+    if output_activation is not None:
+        layers.append(_ACTS[output_activation]())
+    if squeeze_output and dims[-1] == 1:
+        layers.append(Squeeze(1))
+    net = nn.Sequential(*layers)
+    for m in net:
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_normal_(m.weight)
+            nn.init.zeros_(m.bias)
+    return net
+
+
+def _mlp3_struct(seq):
+    return _lib.Mlp3(_lib.linear_of(seq[0].weight.data, seq[0].bias.data), _lib.linear_of(seq[2].weight.data, seq[2].bias.data),
+                     _lib.linear_of(seq[4].weight.data, seq[4].bias.data), None)
+
+
+class CriticEnsemble(Configurable, nn.Module):
+    class Config(BaseConfig):
+        n_critics = 2
+        hidden_layers = 2
+        hidden_dim = 256
+
+    def __init__(self, config, state_dim, action_dim, device=None):
+        Configurable.__init__(self, config)
+        nn.Module.__init__(self)
+        if self.n_critics != 2 or self.hidden_layers != 2:
+            raise NotImplementedError("the CUDA critic step implements the reference's twin 2-hidden-layer Q nets")
+        dims = [state_dim + action_dim, *([self.hidden_dim] * self.hidden_layers), 1]
+        self.qs = nn.ModuleList([mlp(dims, squeeze_output=True, device=device) for _ in range(self.n_critics)])
+
+    def all(self, state, action):
+        sa = torch.cat([state, action], -1)
+        return [q(sa) for q in self.qs]
+
+    def min(self, state, action):
+        return torch.min(*self.all(state, action))
+
+    def mean(self, state, action):
+        qs = self.all(state, action)
+        return sum(qs) / len(qs)
+
+    def random_choice(self, state, action):
+        sa = torch.cat([state, action], -1)
+        return random.choice(self.qs)(sa)
+
+
+class ConstraintCritic(Configurable, nn.Module):
+    """Distributional reachability certificate (src/ssac.py:46-92): mean head + soft-clamped log-std head."""
+
+    class Config(BaseConfig):
+        trunk_layers = 2
+        head_layers = 1
+        hidden_dim = 256
+        log_std_min = -4.
+        log_std_max = 4.
+        std_ratio = 2.
+
+    def __init__(self, config, state_dim, action_dim, output_dim, output_activation=None, device=None):
+        Configurable.__init__(self, config)
+        nn.Module.__init__(self)
+        if self.trunk_layers != 2 or self.head_layers != 1 or (self.log_std_min, self.log_std_max) != (-4., 4.):
+            raise NotImplementedError("the CUDA constraint critic implements the reference's default topology")
+        H = self.hidden_dim
+        self.state_dim, self.action_dim, self.output_dim = state_dim, action_dim, output_dim
+        self.trunk = mlp([state_dim + action_dim, H, H], output_activation="relu", device=device)
+        self.mean_head = mlp([H, H, output_dim], squeeze_output=True, device=device)
+        self.log_std_head = mlp([H, H, output_dim], squeeze_output=True, device=device)
+        self._ws = _lib.Workspace()
+        self.noise_seed = 0x0C0C
+        self._noise_step = 0
+
+    def as_struct(self) -> "_lib.Qc":
+        t, m, l = self.trunk, self.mean_head, self.log_std_head
+        lin = _lib.linear_of
+        return _lib.Qc(lin(t[0].weight.data, t[0].bias.data), lin(t[2].weight.data, t[2].bias.data),
+                       lin(m[0].weight.data, m[0].bias.data), lin(m[2].weight.data, m[2].bias.data),
+                       lin(l[0].weight.data, l[0].bias.data), lin(l[2].weight.data, l[2].bias.data))
+
+    def forward_torch(self, state, action, uncertainty=False, sample=False):
+        """Differentiable torch form (used only by the not-yet-native actor update)."""
+        h = self.trunk(torch.cat([state, action], -1))
+        mean = self.mean_head(h)
+        if (not uncertainty) and (not sample):
+            return mean
+        ls = self.log_std_head(h)
+        ls = self.log_std_max - F.softplus(self.log_std_max - ls)
+        ls = self.log_std_min + F.softplus(ls - self.log_std_min)
+        std = ls.exp()
+        if uncertainty:
+            return mean + self.std_ratio * std
+        return mean, std, mean + torch.clamp(torch.randn_like(std), -2., 2.) * std
+
+    def forward(self, state, action, uncertainty=False, sample=False, eps=None):
+        assert not (uncertainty and sample), "Uncertainty bound and sample cannot be True simultaneously."
+        if torch.is_grad_enabled() and (state.requires_grad or action.requires_grad):
+            return self.forward_torch(state, action, uncertainty, sample)
+        lib = _lib.load()
+        state, action = state.contiguous().float(), action.contiguous().float()
+        B, C = state.shape[0], self.output_dim
+        mode = 1 if uncertainty else (2 if sample else 0)
+        mean = torch.empty((B, C), device=state.device)
+        std = torch.empty((B, C), device=state.device) if mode == 2 else None
+        out = torch.empty((B, C), device=state.device) if mode else None
+        self._noise_step += 1
+        noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, C, self.noise_seed, 18, self._noise_step)
+        ws = self._ws.get(lib.drpo_qc_workspace_bytes(B, self.hidden_dim), state.device)
+        _lib.check(lib.drpo_qc_forward(self.as_struct(), _lib.ptr(state), _lib.ptr(action), B, self.state_dim, self.action_dim, C,
+                                       mode, float(self.std_ratio), noise, _lib.ptr(mean), _lib.ptr(std), _lib.ptr(out),
+                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "drpo_qc_forward")
+        sq = (lambda t: t.squeeze(1)) if C == 1 else (lambda t: t)
+        if mode == 0:
+            return sq(mean)
+        if mode == 1:
+            return sq(out)
+        return sq(mean), sq(std), sq(out)
+
+
+class MLPMultiplier(Configurable, nn.Module):
+    class Config(BaseConfig):
+        hidden_layers = 2
+        hidden_dim = 256
+        upper_bound = 50.
+
+    def __init__(self, config, state_dim, device=None):
+        Configurable.__init__(self, config)
+        nn.Module.__init__(self)
+        if self.hidden_layers != 2:
+            raise NotImplementedError("the CUDA multiplier step implements the reference's 2-hidden-layer net")
+        dims = [state_dim + 1, *([self.hidden_dim] * self.hidden_layers), 1]
+        self.lam = mlp(dims, activation="tanh", output_activation="identity", squeeze_output=True, device=device)
+
+    def forward(self, state, Qc):
+        states_aug = torch.cat([state, Qc.unsqueeze(-1)], -1)
+        return self.upper_bound / 2. * (1. + torch.tanh(self.lam(states_aug) / self.upper_bound * 2))
+
+
+class CosineLR:
+    """torch.optim.lr_scheduler.CosineAnnealingLR's recursive rule, kept on the host (src/ssac.py:204-208)."""
+
+    def __init__(self, opt, T_max, eta_min):
+        self.opt, self.T_max, self.eta_min, self.last_epoch = opt, max(int(T_max), 1), eta_min, 0
+        self.base_lr = opt.param_groups[0]["lr"]
+
+    def step(self):
+        self.last_epoch += 1
+        t, T, lr = self.last_epoch, self.T_max, self.opt.param_groups[0]["lr"]
+        if (t - 1 - T) % (2 * T) == 0:
+            lr = lr + (self.base_lr - self.eta_min) * (1 - math.cos(math.pi / T)) / 2
+        else:
+            lr = (1 + math.cos(math.pi * t / T)) / (1 + math.cos(math.pi * (t - 1) / T)) * (lr - self.eta_min) + self.eta_min
+        self.opt.param_groups[0]["lr"] = lr
+
+    def get_last_lr(self):
+        return [self.opt.param_groups[0]["lr"]]
+
+
+class FusedAdam:
+    """State of the in-kernel Adam (torch.optim.Adam semantics, coupled L2): flat m/v arenas + step count."""
+
+    def __init__(self, arena, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        self.param_groups = [dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)]
+        self.m, self.v, self.grad = torch.zeros_like(arena), torch.zeros_like(arena), torch.zeros_like(arena)
+        self.step_count = 0
+
+    def zero_grad(self):
+        pass                                   # every gradient element is overwritten by the backward kernels
+
+    def as_struct(self) -> "_lib.Adam":
+        g = self.param_groups[0]
+        return _lib.Adam(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count)
+
+    def state_dict(self):
+        return dict(m=self.m, v=self.v, step=self.step_count, lr=self.param_groups[0]["lr"])
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_count = sd["step"]; self.param_groups[0]["lr"] = sd["lr"]
+
+
+def _flatten_into_arena(params):
+    """Move parameters into one flat fp32 tensor; each nn.Parameter becomes a view of it (state_dict order)."""
+    n = sum(p.numel() for p in params)
+    arena = torch.empty(n, dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        k = p.numel()
+        arena[off:off + k].copy_(p.data.reshape(-1))
+        p.data = arena[off:off + k].view(p.shape)
+        off += k
+    return arena
+
+
+def _arena_ok(arena, params):
+    off = 0
+    for p in params:
+        if p.data_ptr() != arena.data_ptr() + 4 * off or not p.is_contiguous():
+            return False
+        off += p.numel()
+    return True
+
+
+class SSAC(Configurable, BasePolicy, nn.Module):
+    class Config(BaseConfig):
+        discount = 0.99
+        init_alpha = 1.0
+        autotune_alpha = True
+        target_entropy = Optional(float)
+        use_log_alpha_loss = False
+        deterministic_backup = False
+        critic_update_multiplier = 1
+        actor_lr = 8e-5
+        actor_lr_end = 4e-5
+        critic_lr = 3e-4
+        critic_lr_end = 8e-5
+        multiplier_lr = 3e-4
+        multiplier_lr_end = 1e-5
+        critic_cfg = CriticEnsemble.Config()
+        constraint_critic_cfg = ConstraintCritic.Config()
+        mlp_multiplier_cfg = MLPMultiplier.Config()
+        tau = 0.005
+        actor_update_interval = 2
+        batch_size = 256
+        hidden_dim = 256
+        hidden_layers = 2
+        update_violation_cost = False
+        grad_norm = 5.
+        constraint_threshold = 0.
+        constrained_fcn = 'reachability'
+        mlp_multiplier = True
+        penalty_lb = -1.0
+        penalty_ub = 100.
+        fixed_multiplier = 15.0
+        multiplier_update_interval = 5
+        lam_epsilon = 1.0
+        qc_under_uncertainty = True
+        qc_td_bound = 5.
+        distributional_qc = True
+
+    def __init__(self, config, state_dim, action_dim, con_dim, horizon, epochs, steps_per_epoch, solver_updates_per_step,
+                 constraint_scale, env_factory=None, model_ensemble=None, optimizer_factory=torch.optim.Adam, device=None):
+        Configurable.__init__(self, config)
+        nn.Module.__init__(self)
+        if not (self.constrained_fcn == 'reachability' and self.mlp_multiplier and self.qc_under_uncertainty
+                and self.distributional_qc and not self.deterministic_backup):
+            raise NotImplementedError("the CUDA SSAC implements DRPO mode: reachability + mlp_multiplier + "
+                                      "qc_under_uncertainty + distributional_qc (run.sh:10-16)")
+        device = torch.device(device if device is not None else "cuda")
+        self.device_ = device
+        self.state_dim, self.action_dim, self.con_dim, self.horizon = state_dim, action_dim, con_dim, horizon
+        self.violation_cost = 0.0
+        self.updates_per_training = epochs * steps_per_epoch * solver_updates_per_step
+        self.lam_updates_num = int(self.updates_per_training / self.multiplier_update_interval)
+        self.actor_updates_num = int(self.updates_per_training / self.actor_update_interval)
+        self.model_ensemble = model_ensemble
+
+        self.actor = SquashedGaussianPolicy(mlp([state_dim, *([self.hidden_dim] * self.hidden_layers), action_dim * 2], device=device))
+        self.actor_safe = copy.deepcopy(self.actor)
+        self.critic = CriticEnsemble(self.critic_cfg, state_dim, action_dim, device=device)
+        self.critic_target = copy.deepcopy(self.critic)
+        self.constraint_critic = ConstraintCritic(self.constraint_critic_cfg, state_dim, action_dim, output_dim=con_dim, device=device)
+        self.constraint_critic_target = copy.deepcopy(self.constraint_critic)
+        for p in [*self.critic_target.parameters(), *self.constraint_critic_target.parameters()]:
+            p.requires_grad = False
+        self.multiplier = MLPMultiplier(self.mlp_multiplier_cfg, state_dim, device=device)
+
+        # ---- flat arenas (params / targets / grads / Adam m,v) --------------------------------------------------
+        self._build_arenas()
+        self.critic_optimizer = FusedAdam(self._critic_arena, self.critic_lr, weight_decay=1e-4)
+        self.critic_lr_scheduler = CosineLR(self.critic_optimizer, self.updates_per_training, self.critic_lr_end)
+        self.multiplier_optimizer = FusedAdam(self._mult_arena, self.multiplier_lr, weight_decay=1e-4)
+        self.multiplier_lr_scheduler = CosineLR(self.multiplier_optimizer, self.lam_updates_num, self.multiplier_lr_end)
+
+        # actors / alpha: SURVEY §8f "next" row 1 — torch optimisers for now
+        self.actor_optimizer = optimizer_factory(self.actor.parameters(), lr=self.actor_lr, weight_decay=1e-4)
+        self.actor_lr_scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.actor_optimizer, T_max=max(self.actor_updates_num, 1), eta_min=self.actor_lr_end)
+        self.actor_safe_optimizer = optimizer_factory(self.actor_safe.parameters(), lr=self.actor_lr, weight_decay=1e-4)
+        self.actor_safe_lr_scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.actor_safe_optimizer, T_max=max(self.actor_updates_num, 1), eta_min=self.actor_lr_end)
+        self.log_alpha = torch.tensor(math.log(self.init_alpha), device=device, requires_grad=True)
+        if self.autotune_alpha:
+            self.alpha_optimizer = optimizer_factory([self.log_alpha], lr=self.actor_lr)
+        if self.target_entropy is None:
+            self.target_entropy = -action_dim
+
+        self.register_buffer('total_updates', torch.zeros([], device=device))
+        self._losses = torch.zeros(8, device=device)
+        self._ws = _lib.Workspace()
+        self.noise_seed = 0xD2B0
+        self.precision = _lib.PREC_FP32
+        self.data_parallel = False          # set True under torchrun: gradients are all-reduced between backward and Adam
+        self._structs = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def _critic_params(self):
+        return [*self.critic.parameters(), *self.constraint_critic.parameters()]
+
+    def _target_params(self):
+        return [*self.critic_target.parameters(), *self.constraint_critic_target.parameters()]
+
+    def _build_arenas(self):
+        self._critic_arena = _flatten_into_arena(self._critic_params())
+        self._target_arena = _flatten_into_arena(self._target_params())
+        self._mult_arena = _flatten_into_arena(list(self.multiplier.parameters()))
+        self._n_q = sum(p.numel() for p in self.critic.parameters())
+        self._n_qc = sum(p.numel() for p in self.constraint_critic.parameters())
+        self._structs = None
+
+    def _ensure_arenas(self):
+        if not (_arena_ok(self._critic_arena, self._critic_params()) and _arena_ok(self._target_arena, self._target_params())
+                and _arena_ok(self._mult_arena, list(self.multiplier.parameters()))):
+            old = (self.critic_optimizer, self.multiplier_optimizer)
+            self._build_arenas()
+            for opt, arena in zip(old, (self._critic_arena, self._mult_arena)):
+                if opt.m.device != arena.device:
+                    opt.m, opt.v, opt.grad = opt.m.to(arena.device), opt.v.to(arena.device), opt.grad.to(arena.device)
+        if self._structs is None:
+            self._structs = dict(
+                actor=self.actor.as_struct(), actor_safe=self.actor_safe.as_struct(),
+                q=[_mlp3_struct(q) for q in self.critic.qs], qt=[_mlp3_struct(q) for q in self.critic_target.qs],
+                qc=self.constraint_critic.as_struct(), qct=self.constraint_critic_target.as_struct(),
+                lam=_mlp3_struct(self.multiplier.lam))
+        return self._structs
+
+    def invalidate_structs(self):
+        """Call after replacing parameter storage by hand (``load_state_dict`` copies in place and needs nothing)."""
+        self._structs = None
+
+    # ---- reference API -------------------------------------------------------------------------------------
+    def act(self, states, eval):
+        return self.actor.act(states, eval)
+
+    @property
+    def alpha(self):
+        return self.log_alpha.exp()
+
+    @property
+    def violation_value(self):
+        return -self.violation_cost / (1. - self.discount)
+
+    def update_r_bounds(self, r_min, r_max):
+        self.r_min, self.r_max = r_min, r_max
+        if self.update_violation_cost:
+            self.violation_cost = (r_max - r_min) / self.discount ** self.horizon - r_max
+
+    def _get_qc(self, qc_con_dim):
+        if self.con_dim > 1:
+            assert qc_con_dim.size(-1) == self.con_dim
+            return torch.max(qc_con_dim, dim=-1)[0]
+        return qc_con_dim
+
+    def _dist(self):
+        import torch.distributed as dist
+        if self.data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+        return None
+
+    def update_critic(self, obs, action, next_obs, reward, done, violation, constraint_value, noise=None):
+        """SSAC.update_critic (src/ssac.py:437-456).  ``noise`` = (eps_actor [B,A], eps_safe [B,A], eps_qc [B(,C)])
+        injects the three Gaussian draws (parity); otherwise the in-kernel Philox stream is used."""
+        lib = _lib.load()
+        st = self._ensure_arenas()
+        dist = self._dist()
+        world = dist.get_world_size() if dist else 1
+        rank = dist.get_rank() if dist else 0
+        B = obs.shape[0]
+        f = lambda t: t.contiguous().float()
+        obs, action, next_obs, reward, cv = f(obs), f(action), f(next_obs), f(reward), f(constraint_value)
+        done, violation = done.contiguous(), violation.contiguous()
+        assert done.dtype == torch.bool and cv.numel() == B * self.con_dim
+        opt = self.critic_optimizer
+        opt.step_count += 1
+        a = _lib.CriticArgs()
+        a.batch = _lib.Batch(_lib.ptr(obs), _lib.ptr(action), _lib.ptr(next_obs), _lib.ptr(reward), _lib.ptr(done),
+                             _lib.ptr(violation), _lib.ptr(cv))
+        a.batch_size, a.global_batch_size = B, B * world
+        a.state_dim, a.action_dim, a.con_dim = self.state_dim, self.action_dim, self.con_dim
+        a.actor, a.actor_safe = C_pointer(st["actor"]), C_pointer(st["actor_safe"])
+        a.q[0], a.q[1], a.q_target[0], a.q_target[1] = st["q"][0], st["q"][1], st["qt"][0], st["qt"][1]
+        a.qc, a.qc_target = st["qc"], st["qct"]
+        a.params, a.grads = _lib.ptr(self._critic_arena), _lib.ptr(opt.grad)
+        a.adam_m, a.adam_v, a.target_params = _lib.ptr(opt.m), _lib.ptr(opt.v), _lib.ptr(self._target_arena)
+        a.n_params_q, a.n_params_qc = self._n_q, self._n_qc
+        a.log_alpha = _lib.ptr(self.log_alpha.data)
+        if noise is not None:
+            n0, n1, n2 = [f(x) for x in noise]
+            a.eps_actor, a.eps_safe, a.eps_qc = _lib.ptr(n0), _lib.ptr(n1), _lib.ptr(n2)
+        a.seed, a.noise_step, a.row_id_offset = self.noise_seed, opt.step_count, rank * B
+        a.discount, a.tau, a.grad_norm, a.qc_td_bound = self.discount, self.tau, self.grad_norm, self.qc_td_bound
+        a.adam = opt.as_struct()
+        a.losses, a.precision = _lib.ptr(self._losses), self.precision
+        ws = self._ws.get(lib.drpo_critic_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim), obs.device)
+        a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        if dist is None:
+            a.phases = 3
+            _lib.check(lib.drpo_critic_step(a), "drpo_critic_step")
+        else:
+            a.phases = 1
+            _lib.check(lib.drpo_critic_step(a), "drpo_critic_step(forward/backward)")
+            dist.all_reduce(opt.grad)                       # NCCL sum over NVLink; losses ride in a second tiny message
+            dist.all_reduce(self._losses[:2])
+            a.phases = 2
+            _lib.check(lib.drpo_critic_step(a), "drpo_critic_step(optimizer)")
+        self.critic_lr_scheduler.step()
+        out = self._losses[:2].clone()
+        return out[0], out[1]
+
+    def update_multiplier(self, obs, eps=None):
+        """SSAC.update_multiplier (src/ssac.py:570-578)."""
+        lib = _lib.load()
+        st = self._ensure_arenas()
+        dist = self._dist()
+        world = dist.get_world_size() if dist else 1
+        rank = dist.get_rank() if dist else 0
+        obs = obs.contiguous().float()
+        B = obs.shape[0]
+        opt = self.multiplier_optimizer
+        opt.step_count += 1
+        a = _lib.MultiplierArgs()
+        a.obs, a.batch_size, a.global_batch_size = _lib.ptr(obs), B, B * world
+        a.state_dim, a.action_dim, a.con_dim = self.state_dim, self.action_dim, self.con_dim
+        a.actor, a.actor_safe, a.qc, a.lam = C_pointer(st["actor"]), C_pointer(st["actor_safe"]), C_pointer(st["qc"]), st["lam"]
+        a.params, a.grads, a.adam_m, a.adam_v = _lib.ptr(self._mult_arena), _lib.ptr(opt.grad), _lib.ptr(opt.m), _lib.ptr(opt.v)
+        a.n_params = self._mult_arena.numel()
+        if eps is not None:
+            eps = eps.contiguous().float()
+            a.eps_actor = _lib.ptr(eps)
+        a.seed, a.noise_step, a.row_id_offset = self.noise_seed + 1, opt.step_count, rank * B
+        a.std_ratio = self.constraint_critic.std_ratio
+        a.constraint_threshold, a.penalty_lb, a.penalty_ub = self.constraint_threshold, self.penalty_lb, self.penalty_ub
+        a.upper_bound, a.lam_epsilon, a.grad_norm = self.multiplier.upper_bound, self.lam_epsilon, self.grad_norm
+        a.adam = opt.as_struct()
+        a.losses, a.precision = _lib.ptr(self._losses[4:]), self.precision
+        ws = self._ws.get(lib.drpo_multiplier_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim), obs.device)
+        a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        if dist is None:
+            a.phases = 3
+            _lib.check(lib.drpo_multiplier_step(a), "drpo_multiplier_step")
+        else:
+            a.phases = 1
+            _lib.check(lib.drpo_multiplier_step(a), "drpo_multiplier_step(forward/backward)")
+            dist.all_reduce(opt.grad)
+            dist.all_reduce(self._losses[4:5])
+            a.phases = 2
+            _lib.check(lib.drpo_multiplier_step(a), "drpo_multiplier_step(optimizer)")
+        self.multiplier_lr_scheduler.step()
+        return self._losses[4].clone()
+
+    # ---- SURVEY §8f "next" row 1: actor / alpha update — eager torch autograd for now ---------------------------
+    def actor_loss(self, obs, include_alpha=True):
+        """src/ssac.py:458-505."""
+        def rsample(pol):
+            mu, std = pol.mu_std(obs)
+            x = mu + std * torch.randn_like(mu)
+            lp = (-((x - mu) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))
+                  - 2. * (math.log(2.) - x - F.softplus(-2. * x))).sum(-1)
+            return torch.tanh(x), lp
+        action, log_prob = rsample(self.actor)
+        actor_Q = self.critic.random_choice(obs, action)
+        alpha = self.alpha
+        uncstr = torch.mean(alpha.detach() * log_prob - actor_Q)
+        actor_Qc = self._get_qc(self.constraint_critic.forward_torch(obs, action, uncertainty=True))
+        with torch.no_grad():
+            action_safe = self.actor_safe.act(obs, eval=True)
+            safe_Qc = self._get_qc(self.constraint_critic(obs, action_safe, uncertainty=True))
+            lams = self.multiplier(obs, safe_Qc)
+        cstr = torch.mean(torch.mul(lams, actor_Qc))
+        a_s, _ = rsample(self.actor_safe)
+        actor_safe_loss = torch.mean(self._get_qc(self.constraint_critic.forward_torch(obs, a_s, uncertainty=True)))
+        losses = [uncstr + cstr]
+        if include_alpha:
+            coef = self.log_alpha if self.use_log_alpha_loss else alpha
+            losses.append(-coef * torch.mean(log_prob.detach() + self.target_entropy))
+        losses.append(actor_safe_loss)
+        return losses
+
+    def update_actor_and_alpha(self, obs):
+        """src/ssac.py:507-527."""
+        losses = self.actor_loss(obs, include_alpha=self.autotune_alpha)
+        optimizers = [self.actor_optimizer] + ([self.alpha_optimizer] if self.autotune_alpha else []) + [self.actor_safe_optimizer]
+        last = len(optimizers) - 1
+        for i, (loss, optimizer) in enumerate(zip(losses, optimizers)):
+            optimizer.zero_grad()
+            loss.backward(retain_graph=True)
+            if i == 0:
+                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), max_norm=self.grad_norm)
+            if i == last:
+                torch.nn.utils.clip_grad_norm_(self.actor_safe.parameters(), max_norm=self.grad_norm)
+            optimizer.step()
+            if i == 0:
+                self.actor_lr_scheduler.step()
+            if i == last:
+                self.actor_safe_lr_scheduler.step()
+        for p in [*self.critic.parameters(), *self.constraint_critic.parameters()]:
+            p.grad = None                     # the torch graph left grads on the (kernel-owned) critic parameters
+
+
+def C_pointer(struct):
+    import ctypes
+    return ctypes.pointer(struct)

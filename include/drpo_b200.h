@@ -1,0 +1,301 @@
+/*
+ * drpo_b200.h — C ABI of libdrpo_sm100.so, the B200 (sm_100a) implementation of DRPO's hot path.
+ *
+ * The reference (ManUtdMoon/Distributional-Reachability-Policy-Optimization) is pure Python/PyTorch and has
+ * NO FFI/plugin interface.  Each entry point below therefore replaces a *Python method* of the
+ * reference; the citation next to it is the reference file:line whose behaviour it reproduces.  The host-side
+ * mirror of those methods (same names / arguments / error behaviour) lives in drpo_b200/*.py and binds these
+ * symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are contiguous row-major fp32,
+ *     masks are uint8 (torch.bool storage), nn.Linear weights are [out,in] (y = x W^T + b) exactly as in the
+ *     reference state_dict, so checkpoints interchange;
+ *   - the library owns no memory: parameters, replay buffers and workspaces are allocated by the caller (PyTorch);
+ *     `*_workspace_bytes` tells how much scratch a call needs;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no call synchronises,
+ *     allocates or frees, so every call is CUDA-graph capturable;
+ *   - return value 0 = ok, negative = error (message from drpo_last_error(), thread-local); nothing throws across
+ *     the boundary;
+ *   - not re-entrant per device; one process per GPU (torchrun), called from the single training thread.
+ */
+#ifndef DRPO_B200_H
+#define DRPO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRPO_ABI_VERSION 1
+
+enum { DRPO_OK = 0, DRPO_ERR_ARG = -1, DRPO_ERR_CUDA = -2, DRPO_ERR_WORKSPACE = -3, DRPO_ERR_UNSUPPORTED = -4 };
+
+/* arithmetic mode of the dense layers */
+enum { DRPO_PREC_FP32 = 0,   /* fp32 FMA path, parity <= 1e-5 relative vs the reference */
+       DRPO_PREC_BF16 = 1 }; /* bf16 tcgen05/TMEM path, fp32 accumulate, parity <= 2e-2 */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Env hooks: check_done / check_violation / get_constraint_values
+ *   point-robot  src/env/point_robot.py:96-130
+ *   bounded      src/env/poles/constraints.py:90-132,203-204,216-247 used by
+ *                src/env/poles/inverted_pendulum.py:79-121 (cartpole) and src/env/quadrotor/quadrotor.py:83-158
+ *   tracking     src/env/tracking/pyth_veh3dofconti_surrcstr_data.py:253-338
+ * The arithmetic is fp64 on fp32 inputs (numpy semantics), result cast to fp32 (src/torch_util.py:20-22).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { DRPO_ENV_POINT_ROBOT = 0, DRPO_ENV_BOUNDED = 1, DRPO_ENV_TRACKING = 2 };
+#define DRPO_MAX_ACTIVE 4
+#define DRPO_MAX_DONE_DIMS 4
+#define DRPO_MAX_HAZARDS 4
+#define DRPO_MAX_CON 8
+
+typedef struct drpo_env_params {
+  int32_t kind;
+  int32_t state_dim;
+  int32_t con_dim;
+  /* point robot */
+  int32_t n_hazards;
+  double hazard_xy[DRPO_MAX_HAZARDS][2];
+  double hazard_size;
+  double goal_xy[2];
+  double goal_size;
+  float xy_bound;
+  /* bounded: cv = [ -x[d_i] + lower_i ..., x[d_i] - upper_i ... ]; violation = any(cv > 0) */
+  int32_t n_active;
+  int32_t active_dims[DRPO_MAX_ACTIVE];
+  double lower[DRPO_MAX_ACTIVE];
+  double upper[DRPO_MAX_ACTIVE];
+  /* bounded: done = violation | any(|x[d_j]| > done_thr_j), compared in fp32 */
+  int32_t n_done_dims;
+  int32_t done_dims[DRPO_MAX_DONE_DIMS];
+  float done_thr[DRPO_MAX_DONE_DIMS];
+  /* tracking */
+  int32_t surr_veh_num;
+  int32_t surr_start;
+  double veh_length;
+  double veh_width;
+} drpo_env_params;
+
+/* replaces env.check_done / check_violation / get_constraint_values as called at src/smbpo.py:63-65,238-240 */
+int drpo_hooks_eval(const drpo_env_params* env, const float* states, int64_t n,
+                    uint8_t* done, uint8_t* violation, float* constraint_values /* [n,con_dim] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Networks (weights are the reference's own tensors)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_linear {       /* one nn.Linear / one member slice of a BatchedLinear */
+  const float* w;                  /* [out,in] */
+  const float* b;                  /* [out]    */
+  int32_t in_dim, out_dim;
+} drpo_linear;
+
+typedef struct drpo_ensemble {     /* BatchedGaussianEnsemble, src/dynamics.py:55-103 */
+  int32_t state_dim, action_dim, ensemble_size, hidden;
+  const float* norm_mean;          /* state_normalizer.mean [S]            */
+  const float* norm_std;           /* state_normalizer.std  [S]            */
+  const float* min_log_var;        /* [S+1] */
+  const float* max_log_var;        /* [S+1] */
+  const float* trunk0_w;  const float* trunk0_b;   /* [E,H,S+A] , [E,H] */
+  const float* trunk1_w;  const float* trunk1_b;   /* [E,H,H]   , [E,H] */
+  const float* diff0_w;   const float* diff0_b;    /* [E,H,H]   , [E,H] */
+  const float* diff1_w;   const float* diff1_b;    /* [E,S+1,H] , [E,S+1] */
+  const float* lvar0_w;   const float* lvar0_b;
+  const float* lvar1_w;   const float* lvar1_b;
+  /* optional bf16 tcgen05 image of the weights, built by drpo_ensemble_pack_bf16 (NULL => fp32 only) */
+  const void* packed_bf16;
+} drpo_ensemble;
+
+typedef struct drpo_mlp3 {         /* Linear-act-Linear-act-Linear: actor, Q_i, multiplier (src/torch_util.py:190-211) */
+  drpo_linear l0, l1, l2;
+  const void* packed_bf16;         /* optional tcgen05 image (drpo_mlp3_pack_bf16) */
+} drpo_mlp3;
+
+typedef struct drpo_qc {           /* ConstraintCritic, src/ssac.py:46-92 */
+  drpo_linear trunk0, trunk1, mean0, mean1, lstd0, lstd1;
+} drpo_qc;
+
+/* Noise: either injected tensors (parity runs) or the in-kernel Philox4x32-10 stream (throughput runs).
+ * Philox counter = (row id, column, stream tag, step); key = seed -> results do not depend on how rows are sharded. */
+typedef struct drpo_noise {
+  const float* eps;                /* injected N(0,1) draws, or NULL to use Philox */
+  int64_t row_stride;              /* elements between consecutive rows of eps */
+  uint64_t seed;
+  uint32_t stream_tag;             /* distinguishes the draws of one call */
+  uint32_t step;
+} drpo_noise;
+
+/* Fill out[n,cols] with the exact N(0,1) values the kernels would draw for (seed, tag, step, row ids).  Lets the
+ * CPU oracle consume the same noise as a Philox-mode run. row_ids may be NULL (= 0..n-1). */
+int drpo_philox_normal(float* out, int64_t n, int32_t cols, const int32_t* row_ids, uint64_t seed,
+                       uint32_t stream_tag, uint32_t step, void* stream);
+
+/* BatchedGaussianEnsemble._forward1 (src/dynamics.py:112-122) when member >= 0, _forward_all (:124-134) when
+ * member == -1 (states/actions are then [E,B,*] if per_member_inputs, else [B,*] shared by all members as in
+ * means() :206-210).  Outputs means/log_vars [B,S+1] or [E,B,S+1]. */
+int64_t drpo_ensemble_workspace_bytes(const drpo_ensemble* ens, int64_t batch);
+int drpo_ensemble_forward(const drpo_ensemble* ens, int32_t member, int32_t per_member_inputs,
+                          const float* states, const float* actions, int64_t batch,
+                          float* means, float* log_vars, int32_t precision,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* BatchedGaussianEnsemble.sample (src/dynamics.py:198-203) with the member already picked on the host
+ * (random.choice(self._elite_inds), :199): next_states [B,S], rewards [B]. */
+int drpo_ensemble_sample(const drpo_ensemble* ens, int32_t member, const float* states, const float* actions,
+                         int64_t batch, const drpo_noise* noise, float* next_states, float* rewards,
+                         int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* SquashedGaussianPolicy: TorchPolicy.act (src/policy.py:77-80) + _distr (:89-97) + SquashedGaussian
+ * (src/squashed_gaussian.py:7-16).  eval_mode != 0 -> tanh(mu).  log_prob (optional, may be NULL) is
+ * Independent(SquashedGaussian).log_prob of the drawn action with the cached pre-tanh value (src/ssac.py:286-288). */
+int64_t drpo_policy_workspace_bytes(const drpo_mlp3* actor, int64_t batch);
+int drpo_policy_act(const drpo_mlp3* actor, const float* states, int64_t batch, int32_t eval_mode,
+                    const drpo_noise* noise, float* actions, float* log_prob, int32_t precision,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Device replay buffer (ConstraintSafetySampleBuffer, src/sampling.py:12-151,215-229): ring of 7 components.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_buffer {
+  float* states;            /* [capacity,S] */
+  float* actions;           /* [capacity,A] */
+  float* next_states;       /* [capacity,S] */
+  float* rewards;           /* [capacity]   */
+  uint8_t* dones;           /* [capacity]   */
+  uint8_t* violations;      /* [capacity]   */
+  float* constraint_values; /* [capacity] if C==1 else [capacity,C] */
+  int64_t* pointer;         /* device scalar, monotone; slot = pointer % capacity (src/sampling.py:128-145) */
+  int64_t capacity;
+  int32_t state_dim, action_dim, con_dim;
+} drpo_buffer;
+
+/* SampleBuffer.sample (src/sampling.py:147-151) fused with SMBPO.update_solver's minibatch assembly
+ * (src/smbpo.py:253-270): rows [0,n_real) gathered from `real` at indices idx[0..n_real), the rest from `virt`;
+ * rewards*reward_scale+alive_bonus; cv*constraint_scale (+offset where > 0).  Outputs are the 7 batch tensors. */
+typedef struct drpo_batch {
+  float* obs; float* act; float* next_obs; float* rew; uint8_t* done; uint8_t* viol; float* cv;
+} drpo_batch;
+int drpo_buffer_gather(const drpo_buffer* real, const drpo_buffer* virt, const int64_t* idx, int64_t n_real,
+                       int64_t n_total, float reward_scale, float alive_bonus, float constraint_scale,
+                       float constraint_offset, const drpo_batch* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SMBPO.rollout (src/smbpo.py:229-249): H x (policy sample -> member sample -> hooks -> store -> compact).
+ * Transitions are written step-major, survivor-order-preserving, straight into `virt` at
+ * (pointer + row) % capacity; `pointer` is advanced on the device; no host synchronisation.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_rollout_args {
+  const drpo_mlp3* actor;
+  const drpo_ensemble* ensemble;
+  const drpo_env_params* env;
+  const float* initial_states;     /* [B0,S] */
+  int64_t batch;                   /* B0 (this rank's shard) */
+  int64_t traj_id_offset;          /* global id of row 0 (multi-GPU sharding: noise is keyed by global id) */
+  int32_t horizon;
+  const int32_t* member_idx_host;  /* HOST array [horizon]: the elite picked for each step (src/dynamics.py:199) */
+  /* noise: injected (parity) eps_policy [H,B_total,A], eps_model [H,B_total,S+1] indexed by global traj id, or Philox */
+  const float* eps_policy;
+  const float* eps_model;
+  int64_t eps_batch_stride;        /* B_total */
+  uint64_t seed;
+  drpo_buffer virt;                /* destination ring */
+  int32_t* step_counts;            /* device [horizon+1]: rows stored at each step; [horizon] = total */
+  int32_t precision;
+  void* workspace;
+  int64_t workspace_bytes;
+  void* stream;
+} drpo_rollout_args;
+
+int64_t drpo_rollout_workspace_bytes(const drpo_rollout_args* args);
+int drpo_rollout(const drpo_rollout_args* args);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SSAC.update_critic (src/ssac.py:437-456 with compute_target :284-294, compute_cons_target :338-362,
+ * cons_critic_loss_given_target :415-427) in DRPO mode (reachability, qc_under_uncertainty, distributional_qc):
+ * forward of all passes, hand-written backward, two grad-norm clips, Adam (coupled L2), EMA of both targets.
+ * Trainable parameters live in ONE flat fp32 arena `params` ([Q1 | Q2 | Qc] in state_dict order) with same-size
+ * arenas for grads, Adam m/v and targets; the drpo_mlp3/drpo_qc structs point into them.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_adam {
+  double lr;           /* from the host-side CosineAnnealingLR (src/ssac.py:204-208) */
+  double beta1, beta2, eps, weight_decay;   /* doubles: torch derives its fp32 scalars from python floats */
+  int32_t step;        /* 1-based step count of THIS update */
+} drpo_adam;
+
+typedef struct drpo_critic_args {
+  /* batch (already reward/constraint-scaled, src/smbpo.py:261-270) */
+  drpo_batch batch;
+  int64_t batch_size;          /* local rows */
+  int64_t global_batch_size;   /* rows over all ranks: losses/gradients are normalised by this */
+  int32_t state_dim, action_dim, con_dim;
+  /* frozen nets */
+  const drpo_mlp3* actor;
+  const drpo_mlp3* actor_safe;
+  /* trainable nets + targets: pointers into the arenas below */
+  drpo_mlp3 q[2];
+  drpo_mlp3 q_target[2];
+  drpo_qc qc;
+  drpo_qc qc_target;
+  float* params;  float* grads;  float* adam_m;  float* adam_v;  float* target_params;
+  int64_t n_params_q;          /* params of Q1+Q2 (first clip group) */
+  int64_t n_params_qc;         /* params of Qc (second clip group) */
+  const float* log_alpha;      /* device scalar (src/ssac.py:225-226) */
+  /* noise: injected eps_actor [B,A], eps_safe [B,A], eps_qc [B,C] or Philox(seed, step) */
+  const float* eps_actor; const float* eps_safe; const float* eps_qc;
+  uint64_t seed; uint32_t noise_step; int64_t row_id_offset;
+  /* hyper-parameters (src/ssac.py:116,133,142,156) */
+  double discount, tau, grad_norm, qc_td_bound;
+  drpo_adam adam;
+  /* phases: bit0 = forward+backward (fills grads, losses), bit1 = clip+Adam+EMA.  Multi-GPU callers run bit0,
+   * all-reduce `grads` and `losses` (NCCL), then run bit1. */
+  int32_t phases;
+  float* losses;               /* device [4]: loss_Q, loss_C, grad-norm Q, grad-norm Qc */
+  int32_t precision;
+  void* workspace; int64_t workspace_bytes; void* stream;
+} drpo_critic_args;
+
+int64_t drpo_critic_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim,
+                                    int32_t hidden);
+int drpo_critic_step(const drpo_critic_args* args);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SSAC.update_multiplier (src/ssac.py:529-578) in DRPO mode (mlp_multiplier): actor rsample, two Qc passes with
+ * the Phi^-1(beta) shift mu + std_ratio*sigma (:85), lambda net forward/backward, clip, Adam.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_multiplier_args {
+  const float* obs; int64_t batch_size; int64_t global_batch_size;
+  int32_t state_dim, action_dim, con_dim;
+  const drpo_mlp3* actor; const drpo_mlp3* actor_safe; const drpo_qc* qc;
+  drpo_mlp3 lam;               /* trainable, pointers into params */
+  float* params; float* grads; float* adam_m; float* adam_v; int64_t n_params;
+  const float* eps_actor; uint64_t seed; uint32_t noise_step; int64_t row_id_offset;
+  double std_ratio, constraint_threshold, penalty_lb, penalty_ub, upper_bound, lam_epsilon, grad_norm;
+  drpo_adam adam;
+  int32_t phases;
+  float* losses;               /* device [4]: loss, grad norm, (unused), (unused) */
+  int32_t precision;
+  void* workspace; int64_t workspace_bytes; void* stream;
+} drpo_multiplier_args;
+
+int64_t drpo_multiplier_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim,
+                                        int32_t hidden);
+int drpo_multiplier_step(const drpo_multiplier_args* args);
+
+/* ConstraintCritic.forward (src/ssac.py:64-92): mode 0 -> mean; 1 -> mean + std_ratio*std (uncertainty=True);
+ * 2 -> (mean, std, mean + clamp(eps,-2,2)*std) (sample=True).  out_mean/out_std/out_sample are [B,C]. */
+int64_t drpo_qc_workspace_bytes(int64_t batch, int32_t hidden);
+int drpo_qc_forward(const drpo_qc* qc, const float* states, const float* actions, int64_t batch,
+                    int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t mode, float std_ratio,
+                    const drpo_noise* noise, float* out_mean, float* out_std, float* out_sample,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* misc */
+const char* drpo_last_error(void);
+int drpo_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t drpo_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRPO_B200_H */
