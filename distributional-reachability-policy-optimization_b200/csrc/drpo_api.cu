@@ -83,7 +83,7 @@ int drpo_ensemble_forward(const drpo_ensemble* ens, int32_t member, int32_t per_
                           int64_t workspace_bytes, void* stream) {
   int rc = check_ens(ens); if (rc) return rc;
   DRPO_CHECK_ARG(member >= -1 && member < ens->ensemble_size, "member %d out of range", member);
-  DRPO_CHECK_ARG(batch >= 0 && states && actions && means && log_vars, "drpo_ensemble_forward: bad arguments");
+  DRPO_CHECK_ARG(batch >= 0 && (batch == 0 || (states && actions && means && log_vars)), "drpo_ensemble_forward: bad arguments");
   DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_ensemble_forward: only DRPO_PREC_FP32 here (the bf16 path is fused into drpo_rollout)");
   if (batch == 0) return DRPO_OK;
   Arena ar(workspace, workspace_bytes);
@@ -107,7 +107,7 @@ int drpo_ensemble_sample(const drpo_ensemble* ens, int32_t member, const float* 
                          int64_t workspace_bytes, void* stream) {
   int rc = check_ens(ens); if (rc) return rc;
   DRPO_CHECK_ARG(member >= 0 && member < ens->ensemble_size, "member %d out of range", member);
-  DRPO_CHECK_ARG(batch >= 0 && states && actions && noise && next_states && rewards, "drpo_ensemble_sample: bad arguments");
+  DRPO_CHECK_ARG(batch >= 0 && (batch == 0 || (states && actions && noise && next_states && rewards)), "drpo_ensemble_sample: bad arguments");
   DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_ensemble_sample: only DRPO_PREC_FP32 here");
   if (batch == 0) return DRPO_OK;
   Arena ar(workspace, workspace_bytes);
@@ -141,7 +141,7 @@ int64_t drpo_policy_workspace_bytes(const drpo_mlp3* actor, int64_t batch) {
 int drpo_policy_act(const drpo_mlp3* actor, const float* states, int64_t batch, int32_t eval_mode, const drpo_noise* noise,
                     float* actions, float* log_prob, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_mlp3(actor, "drpo_policy_act"); if (rc) return rc;
-  DRPO_CHECK_ARG(batch >= 0 && states && actions && (eval_mode || noise), "drpo_policy_act: bad arguments");
+  DRPO_CHECK_ARG(batch >= 0 && (batch == 0 || (states && actions && (eval_mode || noise))), "drpo_policy_act: bad arguments");
   DRPO_CHECK_ARG(actor->l2.out_dim % 2 == 0, "actor output dim must be 2*action_dim");
   DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_policy_act: only DRPO_PREC_FP32 here");
   if (batch == 0) return DRPO_OK;
@@ -163,7 +163,7 @@ int drpo_qc_forward(const drpo_qc* qc, const float* states, const float* actions
                     int32_t con_dim, int32_t mode, float std_ratio, const drpo_noise* noise, float* out_mean, float* out_std,
                     float* out_sample, void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_qc(qc, "drpo_qc_forward"); if (rc) return rc;
-  DRPO_CHECK_ARG(batch >= 0 && states && actions && mode >= 0 && mode <= 2, "drpo_qc_forward: bad arguments");
+  DRPO_CHECK_ARG(batch >= 0 && (batch == 0 || (states && actions)) && mode >= 0 && mode <= 2, "drpo_qc_forward: bad arguments");
   DRPO_CHECK_ARG(qc->trunk0.in_dim == state_dim + action_dim && qc->mean1.out_dim == con_dim, "drpo_qc_forward: dims do not match the network");
   DRPO_CHECK_ARG(mode == 0 ? out_mean != nullptr : out_sample != nullptr, "drpo_qc_forward: output pointer is NULL");
   DRPO_CHECK_ARG(mode != 2 || noise, "drpo_qc_forward: sample mode needs noise");

@@ -134,7 +134,9 @@ def _make_alg(spec, wm, ws, B, capacity=None):
     cfg = drpo_b200.SMBPO.Config()
     cfg.rollout_batch_size = B
     cfg.buffer_max = capacity or max(B * 16, 4096)
-    alg = drpo_b200.SMBPO(cfg, oracle_spec_to_device_env(spec), device=dev())
+    env = oracle_spec_to_device_env(spec)
+    env.action_dim = wm["trunk.0.weight"].shape[2] - spec.state_dim
+    alg = drpo_b200.SMBPO(cfg, env, device=dev())
     alg.model_ensemble.load_state_dict(wm, strict=True)
     alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
     alg.solver.load_state_dict(ws, strict=False)
