@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — DRPO hot path on B200: model-rollout transitions/s (headline) and SSAC critic updates/s.
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --steps K --warmup W  # the reference's algorithm on the box's host cores (oracle port)
+
+A "step" is one SMBPO.rollout over one batch of synthetic start states (B0 per GPU, horizon 10) through the
+probabilistic ensemble; `value` counts the transitions all ranks wrote to their device replay buffers per second with
+the start states already resident in HBM; `e2e` is the same metric through the public Python API (SMBPO.rollout) with the
+start states in pinned HOST memory (H2D inside the timed region) and a D2H read of the per-step transition counts.
+Prints exactly ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+HORIZON = 10
+DEFAULT_B0 = {"quadrotor": 1_000_000, "cartpole-move": 100_000, "safetygym-point-synthetic": 400_000, "point-robot": 100_000}
+CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
+
+
+def flops_per_transition(S, A):
+    """2*[MACs_policy + MACs_member]."""
+    return 2 * ((256 * S + 65536 + 512 * A) + (120000 + 200 * (S + A) + 400 * (S + 1)))
+
+
+def flops_per_critic_sample(S, A, C):
+    """2*(8Q + 2P + 5T + 9H)."""
+    Q = (S + A) * 256 + 65792
+    P = 256 * S + 65536 + 512 * A
+    T = (S + A) * 256 + 65536
+    H = 65536 + 256 * C
+    return 2 * (8 * Q + 2 * P + 5 * T + 9 * H)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()) if self.rows else None,
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def build_alg(workload, B0, device, precision):
+    import drpo_b200
+    from drpo_b200 import synthetic
+    env_name, S, A, C = synthetic.WORKLOADS[workload]
+    cfg = drpo_b200.SMBPO.Config()
+    cfg.rollout_batch_size, cfg.horizon = B0, HORIZON
+    cfg.buffer_max = B0 * HORIZON + 1024           # SampleBuffer.extend needs batch <= capacity (src/sampling.py:131)
+    alg = drpo_b200.SMBPO(cfg, drpo_b200.device_env(env_name), device=device)
+    alg.model_ensemble.load_state_dict(synthetic.make_ensemble_weights(64578, S, A))
+    alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
+    alg.solver.load_state_dict(synthetic.make_ssac_weights(219803, S, A, C), strict=False)
+    alg.rollout_precision = precision
+    return alg
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import drpo_b200
+    from drpo_b200 import _lib, synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
+    lib = _lib.load()
+    precision = {"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16}[args.precision]
+    workload = args.workload
+    _, S, A, C = synthetic.WORKLOADS[workload]
+    B0 = args.batch or DEFAULT_B0[workload]
+    alg = build_alg(workload, B0, device, precision)
+    alg.shard_rank, alg.shard_world = rank, world          # weak scaling: every rank rolls out its own B0 start states
+    init_host = synthetic.make_start_states(workload, B0, 4354 + rank).pin_memory()
+    init_dev = init_host.to(device)
+    members = [i % 5 for i in range(HORIZON)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        alg.virt_buffer._pointer.zero_()
+        return alg.rollout(alg.actor, initial_states=init_dev, member_idx=members)
+
+    def step_e2e():
+        alg.virt_buffer._pointer.zero_()
+        dev_init = init_host.to(device, non_blocking=True)                    # H2D of this step's inputs (pinned)
+        view = alg.rollout(alg.actor, initial_states=dev_init, member_idx=members)
+        return view.step_counts.to("cpu", non_blocking=False)                  # D2H of the step's result
+
+    for _ in range(args.warmup):
+        view = step_device()
+    barrier()
+    # ---- device-resident timing: K steps between two events ---------------------------------------------------
+    launches0 = lib.drpo_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total = torch.zeros((), dtype=torch.int64, device=device)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            view = step_device()
+            total += view.step_counts[-1]
+        ev1.record()
+        barrier()
+    launches = lib.drpo_launch_count() - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    tot = total.clone()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms_total = float(ms)
+    transitions = int(tot)
+    value = transitions / (ms_total * 1e-3)
+
+    # ---- end-to-end timing through the public API with host inputs ------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    tot_e = 0
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0.record()
+    for _ in range(args.steps):
+        tot_e += int(step_e2e()[-1])
+    t_ev1.record()
+    barrier()
+    ms_e = torch.tensor([t_ev0.elapsed_time(t_ev1)], device=device, dtype=torch.float64)
+    te = torch.tensor([tot_e], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te)
+    e2e_value = int(te) / (float(ms_e) * 1e-3)
+
+    # ---- roofline of the dominant kernel (measured live: CUDA events around the rollout's launches) ---------------
+    pk = peaks()
+    per_gpu_tr_per_step = transitions / world / args.steps
+    flops = flops_per_transition(S, A) * per_gpu_tr_per_step
+    step_ms = ms_total / args.steps
+    kern = alg.last_kernel_stats() if hasattr(alg, "last_kernel_stats") else None
+    achieved_tf = flops / (step_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                "kernel": "whole rollout step (policy+member GEMM chain + epilogues)" if kern is None else kern,
+                "algorithmic_flops_per_transition": flops_per_transition(S, A)}
+
+    out = {
+        "metric": "model_rollout_transitions_per_s", "value": value, "unit": "transitions/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"{workload} DRPO rollout: {B0} start states/GPU x horizon {HORIZON}, 7x4x200 ensemble + 256x2 actor",
+                   "state_dim": S, "action_dim": A, "con_dim": C, "start_states_per_gpu": B0, "horizon": HORIZON,
+                   "precision": args.precision, "parallelism": f"dp{world} (start states sharded, no collective)",
+                   "l2": "per-step working set (states in + records out) exceeds the 126 MB L2"},
+        "transitions_per_step": transitions / args.steps,
+        "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": int(init_host.numel() * 4),
+                "d2h_bytes_per_step": int((HORIZON + 1) * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+    }
+
+    # ---- SSAC critic updates/s (second half of the metric) -------------------------------------------------------------
+    if not args.skip_critic:
+        out["critic"] = bench_critic(args, device, world, rank, pk)
+    # ---- CPU baseline (oracle port) on rank 0, N=1 only --------------------------------------------------------------
+    if world == 1 and not args.skip_cpu:
+        out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=2)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_critic(args, device, world, rank, pk):
+    import torch.distributed as dist
+    import drpo_b200
+    from drpo_b200 import _lib, synthetic
+    _, S, A, C = synthetic.WORKLOADS[CRITIC_WORKLOAD]
+    Bg = CRITIC_B
+    B = Bg // world                                     # strong scaling: the 64k minibatch is sharded over ranks
+    cfg = drpo_b200.SSAC.Config()
+    cfg.batch_size = B
+    cfg.constraint_critic_cfg.std_ratio = 1.0
+    solver = drpo_b200.SSAC(cfg, S, A, C, HORIZON, 100, 1000, 10, 5.0, device=device)
+    solver.load_state_dict(synthetic.make_ssac_weights(43567, S, A, C), strict=False)
+    solver.data_parallel = world > 1
+    full = synthetic.make_critic_batch(CRITIC_WORKLOAD, Bg, 49283)
+    batch = [t[rank * B:(rank + 1) * B].to(device) for t in full]
+    lib = _lib.load()
+    for _ in range(3):
+        solver.update_critic(*batch)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n = args.critic_steps
+    l0 = lib.drpo_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        lq, lc = solver.update_critic(*batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ups = n / (float(ms) * 1e-3)
+    fl = flops_per_critic_sample(S, A, C) * Bg
+    ach = fl * ups / 1e12 / world
+    res = {"metric": "ssac_critic_updates_per_s", "value": ups, "unit": "updates/s", "samples_per_s": ups * Bg,
+           "global_batch": Bg, "per_gpu_batch": B, "scaling": "strong", "ms_per_update": float(ms) / n, "dtype": "f32",
+           "gpu_launches": int(lib.drpo_launch_count() - l0), "loss_q": float(lq), "loss_c": float(lc),
+           "roofline": {"bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                        "frac": round(ach / pk["tensor_sustained"], 5), "traffic": None,
+                        "algorithmic_flops_per_sample": flops_per_critic_sample(S, A, C)}}
+    if world == 1 and not args.skip_cpu:
+        res["cpu_baseline"] = cpu_critic_baseline(args.cpu_critic_batch)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs: the oracle port of the reference's algorithm (the reference itself is Python and cannot travel to the box)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_rollout_baseline(workload, B0, reps):
+    from oracle import drpo_oracle as O
+    from drpo_b200 import synthetic
+    env_name, S, A, C = synthetic.WORKLOADS[workload]
+    spec = {"quadrotor": O.env_quadrotor, "cartpole-move": O.env_cartpole, "point-robot": O.env_point_robot,
+            "safetygym-point-synthetic": O.env_safetygym60}[workload]()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    wm, ws = synthetic.make_ensemble_weights(64578, S, A), synthetic.make_ssac_weights(219803, S, A, C)
+    init = synthetic.make_start_states(workload, B0, 4354)
+    g = torch.Generator().manual_seed(1)
+    eps_p, eps_m = torch.randn(HORIZON, B0, A, generator=g), torch.randn(HORIZON, B0, S + 1, generator=g)
+    members = [i % 5 for i in range(HORIZON)]
+    O.rollout(ws, wm, spec, init[:2000], HORIZON, eps_p[:, :2000], eps_m[:, :2000], members)        # warm-up
+    t0, n = time.perf_counter(), 0
+    for _ in range(reps):
+        res, counts, _ = O.rollout(ws, wm, spec, init, HORIZON, eps_p, eps_m, members)
+        n += sum(counts)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x oracle rollout of {B0} start states x horizon {HORIZON} ({workload} dims), torch CPU fp32, {threads} threads, {dt:.1f}s"}
+
+
+def cpu_critic_baseline(B):
+    from oracle import drpo_oracle as O
+    from drpo_b200 import synthetic
+    _, S, A, C = synthetic.WORKLOADS[CRITIC_WORKLOAD]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    w = synthetic.make_ssac_weights(43567, S, A, C)
+    batch = synthetic.make_critic_batch(CRITIC_WORKLOAD, B, 49283)
+    g = torch.Generator().manual_seed(2)
+    noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g), torch.randn(B, generator=g))
+    adam, hp = O.AdamState(), O.SSACHyper(std_ratio=1.0)
+    O.critic_update(w, batch, noise, hp, 0.0, adam, 3e-4)
+    t0, reps = time.perf_counter(), 3
+    for _ in range(reps):
+        O.critic_update(w, batch, noise, hp, 0.0, adam, 3e-4)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads,
+            "kind": "port", "sample": f"{reps} x oracle critic_update at B={B} (tracking dims), torch CPU fp32 autograd, {threads} threads"}
+
+
+def run_reference(args):
+    """The reference's algorithm on the host cores: the oracle port (the reference is pure Python + torch; its files cannot
+    travel to the GPU box, oracle/drpo_oracle.py restates it and is pinned to it by tests/golden)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from drpo_b200 import synthetic
+    workload = args.workload
+    _, S, A, C = synthetic.WORKLOADS[workload]
+    B0 = args.cpu_batch
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_rollout_baseline(workload, min(B0, 5000), 1)
+    t0 = time.perf_counter()
+    res = cpu_rollout_baseline(workload, B0, max(args.steps, 1))
+    dt = time.perf_counter() - t0
+    out = {"impl": "reference", "metric": "model_rollout_transitions_per_s", "value": res["value"], "unit": "transitions/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{workload} DRPO rollout: bounded CPU sample of {B0} start states x horizon {HORIZON} per step",
+                      "state_dim": S, "action_dim": A, "con_dim": C, "horizon": HORIZON},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="quadrotor", choices=list(DEFAULT_B0))
+    ap.add_argument("--batch", type=int, default=0, help="start states per GPU (default: the workload's BASELINE size)")
+    ap.add_argument("--precision", default=os.environ.get("DRPO_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--critic-steps", type=int, default=20)
+    ap.add_argument("--cpu-batch", type=int, default=100_000)
+    ap.add_argument("--cpu-critic-batch", type=int, default=16384)
+    ap.add_argument("--skip-critic", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

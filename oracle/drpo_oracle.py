@@ -30,81 +30,8 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 W = Dict[str, Tensor]
 
-# ----------------------------------------------------------------------------------------------
-# deterministic synthetic weights (shared by make_golden.py, the tests and bench.py)
-# ----------------------------------------------------------------------------------------------
-
-
-def _randn(gen, *shape, scale=1.0):
-    return torch.randn(*shape, generator=gen, dtype=torch.float32) * scale
-
-
-def make_ensemble_weights(seed: int, S: int, A: int, E: int = 7, hidden: int = 200,
-                          diff_scale: float = 0.01) -> W:
-    """Weights with the reference's key names/shapes (src/dynamics.py:70-101).
-
-    Not the reference's initialiser: a seeded generator so that fixtures need not store 0.9 M
-    parameters.  ``diff_scale`` shrinks the last diff-head layer so trajectories survive several
-    steps."""
-    g = torch.Generator().manual_seed(seed)
-    D, O = S + A, S + 1
-    w = {
-        "min_log_var": torch.full([O], -10.0) + _randn(g, O, scale=0.1),
-        "max_log_var": torch.full([O], 1.0) + _randn(g, O, scale=0.1),
-        "state_normalizer.mean": _randn(g, S, scale=0.3),
-        "state_normalizer.std": 0.5 + torch.rand(S, generator=g),
-        "trunk.0.weight": _randn(g, E, hidden, D, scale=1.0 / math.sqrt(D)),
-        "trunk.0.bias": _randn(g, E, hidden, scale=0.1),
-        "trunk.2.weight": _randn(g, E, hidden, hidden, scale=1.0 / math.sqrt(hidden)),
-        "trunk.2.bias": _randn(g, E, hidden, scale=0.1),
-        "diff_head.0.weight": _randn(g, E, hidden, hidden, scale=1.0 / math.sqrt(hidden)),
-        "diff_head.0.bias": _randn(g, E, hidden, scale=0.1),
-        "diff_head.2.weight": _randn(g, E, O, hidden, scale=diff_scale / math.sqrt(hidden)),
-        "diff_head.2.bias": _randn(g, E, O, scale=diff_scale),
-        "log_var_head.0.weight": _randn(g, E, hidden, hidden, scale=1.0 / math.sqrt(hidden)),
-        "log_var_head.0.bias": _randn(g, E, hidden, scale=0.1),
-        "log_var_head.2.weight": _randn(g, E, O, hidden, scale=1.0 / math.sqrt(hidden)),
-        "log_var_head.2.bias": _randn(g, E, O, scale=0.5) - 7.0,
-    }
-    return w
-
-
-def _mlp_weights(g, prefix: str, dims: List[int], idx=(0, 2, 4), out_scale=1.0) -> W:
-    w = {}
-    for li, (i, o) in enumerate(zip(dims[:-1], dims[1:])):
-        last = li == len(dims) - 2
-        w[f"{prefix}{idx[li]}.weight"] = _randn(g, o, i, scale=(out_scale if last else 1.0) * math.sqrt(2.0 / (i + o)))
-        w[f"{prefix}{idx[li]}.bias"] = _randn(g, o, scale=0.05)
-    return w
-
-
-def make_ssac_weights(seed: int, S: int, A: int, C: int, hidden: int = 256) -> W:
-    """All SSAC networks (src/ssac.py:184-197,233-234) under the reference's state_dict keys."""
-    g = torch.Generator().manual_seed(seed)
-    w: W = {}
-    w.update(_mlp_weights(g, "actor.net.", [S, hidden, hidden, 2 * A]))
-    w.update(_mlp_weights(g, "actor_safe.net.", [S, hidden, hidden, 2 * A]))
-    for q in range(2):
-        w.update(_mlp_weights(g, f"critic.qs.{q}.", [S + A, hidden, hidden, 1]))
-    w.update(_mlp_weights(g, "constraint_critic.trunk.", [S + A, hidden, hidden], idx=(0, 2)))
-    w.update(_mlp_weights(g, "constraint_critic.mean_head.", [hidden, hidden, C], idx=(0, 2)))
-    w.update(_mlp_weights(g, "constraint_critic.log_std_head.", [hidden, hidden, C], idx=(0, 2)))
-    w.update(_mlp_weights(g, "multiplier.lam.", [S + 1, hidden, hidden, 1]))
-    # centre mu + std_ratio*sigma around 0 so both the safe and unsafe branches of the losses are exercised
-    w["constraint_critic.mean_head.2.bias"] -= 0.5
-    w["constraint_critic.log_std_head.2.bias"] -= 1.5
-    for k in list(w.keys()):
-        if k.startswith("critic."):
-            w["critic_target." + k[len("critic."):]] = w[k].clone() + 0.01 * _randn(g, *w[k].shape)
-        if k.startswith("constraint_critic."):
-            w["constraint_critic_target." + k[len("constraint_critic."):]] = \
-                w[k].clone() + 0.01 * _randn(g, *w[k].shape)
-    return w
-
-
-def weights_checksum(w: W) -> float:
-    return float(sum(v.double().abs().sum().item() * (i + 1) for i, (k, v) in enumerate(sorted(w.items()))))
-
+# deterministic synthetic weights: one definition shared by make_golden.py, the tests and bench.py
+from drpo_b200.synthetic import (make_ensemble_weights, make_ssac_weights, weights_checksum)  # noqa: E402,F401
 
 # ----------------------------------------------------------------------------------------------
 # env hooks: check_done / check_violation / get_constraint_values  (numpy, fp64 on fp32 inputs)
