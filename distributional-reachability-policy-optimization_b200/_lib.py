@@ -136,6 +136,7 @@ SYMBOLS = [
                                      C.c_float, C.c_float, C.c_float, C.POINTER(Batch), C.c_void_p]),
     ("drpo_rollout_workspace_bytes", C.c_int64, [C.POINTER(RolloutArgs)]),
     ("drpo_rollout", C.c_int, [C.POINTER(RolloutArgs)]),
+    ("drpo_debug_rollout_layer", C.c_int, [C.POINTER(RolloutArgs), C.c_int32, C.c_void_p]),
     ("drpo_critic_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_critic_step", C.c_int, [C.POINTER(CriticArgs)]),
     ("drpo_multiplier_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -24,7 +24,7 @@ struct CriticLossArgs {
 
 __device__ __forceinline__ float dsoftplus(float x) { return x > 20.f ? 1.f : sigmoid_f(x); }
 
-__global__ void __launch_bounds__(256) critic_loss_kernel(CriticLossArgs a) {
+static __global__ void __launch_bounds__(256) critic_loss_kernel(CriticLossArgs a) {
   double lq = 0.0, lc = 0.0;
   const float alpha = expf(*a.log_alpha);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.B; r += (int64_t)gridDim.x * blockDim.x) {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) critic_loss_kernel(CriticLossArgs a) {
   }
 }
 
-__global__ void loss_finalize_kernel(const double* partials, int nblocks, int ncols, const double* scale, float* out) {
+static __global__ void loss_finalize_kernel(const double* partials, int nblocks, int ncols, const double* scale, float* out) {
   if (threadIdx.x < ncols) {
     double s = 0;
     for (int b = 0; b < nblocks; ++b) s += partials[ncols * b + threadIdx.x];
@@ -72,7 +72,7 @@ __global__ void loss_finalize_kernel(const double* partials, int nblocks, int nc
   }
 }
 struct Scale2 { double v[2]; };
-__global__ void loss_finalize2_kernel(const double* partials, int nblocks, Scale2 sc, float* out) {
+static __global__ void loss_finalize2_kernel(const double* partials, int nblocks, Scale2 sc, float* out) {
   if (threadIdx.x < 2) {
     double s = 0;
     for (int b = 0; b < nblocks; ++b) s += partials[2 * b + threadIdx.x];
@@ -83,7 +83,7 @@ __global__ void loss_finalize2_kernel(const double* partials, int nblocks, Scale
 // ---------------------------------------------------------------------------------------------------------------
 // optimiser: grad norms (two clip groups), fused clip + coupled-L2 + Adam + EMA
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n0, int64_t n1, double* partials) {
+static __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n0, int64_t n1, double* partials) {
   // partials[2*block + k] = sum of squares of group k handled by this block (group 0 = [0,n0), group 1 = [n0,n0+n1))
   double s0 = 0, s1 = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (int64_t)gridDim.x * blockDim.x) {
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 // norms[k] = sqrt(sum), coef[k] = min(1, max_norm/(norm+1e-6))        torch.nn.utils.clip_grad_norm_
-__global__ void clip_coef_kernel(const double* partials, int nblocks, float max_norm, float* norms_out, float* coef) {
+static __global__ void clip_coef_kernel(const double* partials, int nblocks, float max_norm, float* norms_out, float* coef) {
   if (threadIdx.x < 2) {
     double s = 0;
     for (int b = 0; b < nblocks; ++b) s += partials[2 * b + threadIdx.x];
@@ -121,7 +121,7 @@ static inline AdamScalars adam_scalars(const drpo_adam& a, double tau) {
   return s;
 }
 // torch.optim.Adam (coupled L2, src/ssac.py:199-203) + update_ema (src/torch_util.py:223-226) in one pass
-__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+static __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ tgt, int64_t n0, int64_t n,
                                                        const float* __restrict__ coef, AdamScalars s) {
   const float c0 = coef[0], c1 = coef[1];
@@ -277,7 +277,7 @@ static inline int critic_step_fp32(const drpo_critic_args& a) {
 // multiplier step
 // ---------------------------------------------------------------------------------------------------------------
 // x_aug = [obs, safe_qc], with safe_qc = max_c(mean + ratio*std) of the safe action; also penalty from the actor action
-__global__ void mult_prep_kernel(const float* __restrict__ obs, const float* __restrict__ qc_a, const float* __restrict__ qc_s,
+static __global__ void mult_prep_kernel(const float* __restrict__ obs, const float* __restrict__ qc_a, const float* __restrict__ qc_s,
                                  float* __restrict__ xaug, float* __restrict__ penalty, float* __restrict__ safe_qc, int64_t B, int S,
                                  int C, float thr, float lb, float ub) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
@@ -289,7 +289,7 @@ __global__ void mult_prep_kernel(const float* __restrict__ obs, const float* __r
     xaug[r * (S + 1) + S] = ms;
   }
 }
-__global__ void __launch_bounds__(256) mult_loss_kernel(const float* __restrict__ raw, const float* __restrict__ penalty,
+static __global__ void __launch_bounds__(256) mult_loss_kernel(const float* __restrict__ raw, const float* __restrict__ penalty,
                                                         const float* __restrict__ safe_qc, float ub, float lam_eps, float inv_bg,
                                                         float* __restrict__ draw, double* partials, int64_t B) {
   double l0 = 0, l1 = 0;

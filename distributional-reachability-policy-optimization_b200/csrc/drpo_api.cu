@@ -252,6 +252,12 @@ int drpo_rollout(const drpo_rollout_args* a) {
   return DRPO_ERR_ARG;
 }
 
+int drpo_debug_rollout_layer(const drpo_rollout_args* a, int32_t layer, float* out) {
+  int rc = check_rollout(a); if (rc) return rc;
+  DRPO_CHECK_ARG(layer >= 0 && out && a->batch > 0, "drpo_debug_rollout_layer: bad arguments");
+  return umma_debug_layer(*a, layer, out);
+}
+
 int64_t drpo_critic_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
   return critic_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
 }

@@ -25,7 +25,7 @@ struct GemmArgs {
 
 constexpr int GM = 64, GN = 64, GK = 16, GPAD = 4;
 
-__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
+static __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[GK][GM + GPAD];
   __shared__ __align__(16) float Bs[GK][GN + GPAD];
   int M = g.M;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
 }
 
 // deterministic second stage of split-K (fixed summation order over the splits)
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splitk, int M, int N, float* C, int64_t ldc,
+static __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splitk, int M, int N, float* C, int64_t ldc,
                                      float* bias_out, float beta) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;

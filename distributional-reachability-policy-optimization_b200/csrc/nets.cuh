@@ -13,7 +13,7 @@ namespace drpo {
 // ---------------------------------------------------------------------------------------------------------------
 
 // x0 = [(s - mean)/(std + 1e-6), a]      src/normalization.py:23-24 + src/dynamics.py:113-114
-__global__ void ens_pack_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ mean,
+static __global__ void ens_pack_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ mean,
                                 const float* __restrict__ stdv, float* __restrict__ x0, int64_t n, int S, int A,
                                 const int* n_dev) {
   if (n_dev) n = min(n, (int64_t)*n_dev);
@@ -25,7 +25,7 @@ __global__ void ens_pack_kernel(const float* __restrict__ s, const float* __rest
 }
 
 // sa = [s, a]
-__global__ void cat2_kernel(const float* __restrict__ s, const float* __restrict__ a, float* __restrict__ out, int64_t n,
+static __global__ void cat2_kernel(const float* __restrict__ s, const float* __restrict__ a, float* __restrict__ out, int64_t n,
                             int S, int A) {
   const int D = S + A;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * D; i += (int64_t)gridDim.x * blockDim.x) {
@@ -35,7 +35,7 @@ __global__ void cat2_kernel(const float* __restrict__ s, const float* __restrict
 }
 
 // means = diffs + [s,0]; log_vars soft-clamped      src/dynamics.py:118-121
-__global__ void ens_head_kernel(const float* __restrict__ dd, const float* __restrict__ lr, const float* __restrict__ s,
+static __global__ void ens_head_kernel(const float* __restrict__ dd, const float* __restrict__ lr, const float* __restrict__ s,
                                 const float* __restrict__ min_lv, const float* __restrict__ max_lv,
                                 float* __restrict__ means, float* __restrict__ log_vars, int64_t n, int S) {
   const int O = S + 1;
@@ -47,7 +47,7 @@ __global__ void ens_head_kernel(const float* __restrict__ dd, const float* __res
 }
 
 // samples = means + sqrt(exp(log_vars)) * eps ; split into next_states / rewards     src/dynamics.py:201-203
-__global__ void ens_sample_kernel(const float* __restrict__ dd, const float* __restrict__ lr, const float* __restrict__ s,
+static __global__ void ens_sample_kernel(const float* __restrict__ dd, const float* __restrict__ lr, const float* __restrict__ s,
                                   const float* __restrict__ min_lv, const float* __restrict__ max_lv, NoiseView noise,
                                   const int32_t* __restrict__ row_ids, float* __restrict__ next_states,
                                   float* __restrict__ rewards, int64_t n, int S, const int* n_dev) {
@@ -65,7 +65,7 @@ __global__ void ens_sample_kernel(const float* __restrict__ dd, const float* __r
 }
 
 // squashed-Gaussian head: out[n,2A] -> action (+ log-prob)       src/policy.py:89-97, src/ssac.py:286-288
-__global__ void policy_head_kernel(const float* __restrict__ out, NoiseView noise, const int32_t* __restrict__ row_ids,
+static __global__ void policy_head_kernel(const float* __restrict__ out, NoiseView noise, const int32_t* __restrict__ row_ids,
                                    int eval_mode, float* __restrict__ actions, float* __restrict__ log_prob, int64_t n,
                                    int A, const int* n_dev) {
   if (n_dev) n = min(n, (int64_t)*n_dev);
@@ -91,7 +91,7 @@ __global__ void policy_head_kernel(const float* __restrict__ out, NoiseView nois
 
 // constraint-critic head: raw mean [n,C], raw log-std [n,C] -> mean / std / shifted or sampled value
 // mode 0: mean ; 1: mean + std_ratio*std (src/ssac.py:85) ; 2: mean, std, mean + clamp(eps,-2,2)*std (:88-90)
-__global__ void qc_head_kernel(const float* __restrict__ mean_raw, const float* __restrict__ ls_raw, int mode,
+static __global__ void qc_head_kernel(const float* __restrict__ mean_raw, const float* __restrict__ ls_raw, int mode,
                                float std_ratio, NoiseView noise, int64_t row_off, float* __restrict__ out_mean,
                                float* __restrict__ out_std, float* __restrict__ out_sample, int64_t n, int C) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * C; i += (int64_t)gridDim.x * blockDim.x) {
@@ -107,7 +107,7 @@ __global__ void qc_head_kernel(const float* __restrict__ mean_raw, const float* 
 }
 
 // hooks over a batch of rows
-__global__ void hooks_kernel(drpo_env_params p, const float* __restrict__ states, int64_t n, uint8_t* __restrict__ done,
+static __global__ void hooks_kernel(drpo_env_params p, const float* __restrict__ states, int64_t n, uint8_t* __restrict__ done,
                              uint8_t* __restrict__ viol, float* __restrict__ cv, const int* n_dev) {
   if (n_dev) n = min(n, (int64_t)*n_dev);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {

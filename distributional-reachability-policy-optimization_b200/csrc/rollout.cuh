@@ -16,7 +16,7 @@ struct RolloutState {         // device-resident control block
 
 constexpr int CBLK = 1024;
 
-__global__ void rollout_init_kernel(int32_t* ids, int64_t n, int64_t id_offset, int32_t* n_alive, RolloutState* st,
+static __global__ void rollout_init_kernel(int32_t* ids, int64_t n, int64_t id_offset, int32_t* n_alive, RolloutState* st,
                                     const int64_t* pointer) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     ids[i] = (int32_t)(id_offset + i);
@@ -24,7 +24,7 @@ __global__ void rollout_init_kernel(int32_t* ids, int64_t n, int64_t id_offset, 
 }
 
 // write the step's rows into the ring at (base + r) % capacity  (SampleBuffer.extend with wrap, src/sampling.py:128-145)
-__global__ void rollout_store_kernel(drpo_buffer buf, const RolloutState* st, const int32_t* n_dev,
+static __global__ void rollout_store_kernel(drpo_buffer buf, const RolloutState* st, const int32_t* n_dev,
                                      const float* __restrict__ s, const float* __restrict__ a,
                                      const float* __restrict__ ns, const float* __restrict__ rew,
                                      const uint8_t* __restrict__ done, const uint8_t* __restrict__ viol,
@@ -51,7 +51,7 @@ __global__ void rollout_store_kernel(drpo_buffer buf, const RolloutState* st, co
   }
 }
 
-__global__ void __launch_bounds__(CBLK) compact_count_kernel(const uint8_t* __restrict__ done, const int32_t* n_dev,
+static __global__ void __launch_bounds__(CBLK) compact_count_kernel(const uint8_t* __restrict__ done, const int32_t* n_dev,
                                                              int32_t* __restrict__ block_counts) {
   __shared__ int warp_cnt[CBLK / 32];
   const int n = *n_dev;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(CBLK) compact_count_kernel(const uint8_t* __re
 }
 
 // one block: exclusive scan of the block counts; publishes next step's row count and advances the ring base
-__global__ void __launch_bounds__(CBLK) compact_scan_kernel(int32_t* __restrict__ block_counts, int nblocks, int32_t* n_alive,
+static __global__ void __launch_bounds__(CBLK) compact_scan_kernel(int32_t* __restrict__ block_counts, int nblocks, int32_t* n_alive,
                                                             int t, RolloutState* st, int32_t* step_counts) {
   __shared__ int tmp[CBLK];
   __shared__ int carry;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(CBLK) compact_scan_kernel(int32_t* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint8_t* __restrict__ done, const int32_t* n_dev,
+static __global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint8_t* __restrict__ done, const int32_t* n_dev,
                                                                const int32_t* __restrict__ block_offsets,
                                                                const float* __restrict__ ns, const int32_t* __restrict__ ids,
                                                                float* __restrict__ cur_next, int32_t* __restrict__ ids_next, int S) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint8_t* __
   }
 }
 
-__global__ void rollout_finish_kernel(int64_t* pointer, const RolloutState* st, int32_t* step_counts, int horizon) {
+static __global__ void rollout_finish_kernel(int64_t* pointer, const RolloutState* st, int32_t* step_counts, int horizon) {
   int total = 0;
   for (int t = 0; t < horizon; ++t) total += step_counts[t];
   step_counts[horizon] = total;
@@ -196,7 +196,7 @@ static inline int rollout_fp32(const drpo_rollout_args& a) {
 }
 
 // SampleBuffer.sample + SMBPO.update_solver assembly (src/sampling.py:147-151, src/smbpo.py:253-270)
-__global__ void buffer_gather_kernel(drpo_buffer real, drpo_buffer virt, const int64_t* __restrict__ idx, int64_t n_real,
+static __global__ void buffer_gather_kernel(drpo_buffer real, drpo_buffer virt, const int64_t* __restrict__ idx, int64_t n_real,
                                      int64_t n, float reward_scale, float alive_bonus, float c_scale, float c_off, drpo_batch out) {
   const int S = real.state_dim, A = real.action_dim, C = real.con_dim;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -4,4 +4,5 @@
 namespace drpo {
 int64_t umma_rollout_ws_bytes(const drpo_rollout_args& a);
 int umma_rollout(const drpo_rollout_args& a);
+int umma_debug_layer(const drpo_rollout_args& a, int layer, float* out);
 }  // namespace drpo

@@ -93,7 +93,7 @@ class SMBPO(Configurable, nn.Module):
                                             device=device or self.virt_buffer.device)
 
     # ---- SMBPO.rollout  (src/smbpo.py:229-249) -------------------------------------------------------------------
-    def rollout(self, policy, initial_states=None, noise=None, member_idx=None):
+    def rollout(self, policy, initial_states=None, noise=None, member_idx=None, _debug_layer=None):
         """Branched H-step model rollout.  Appends the transitions to ``self.virt_buffer`` (one write, on the device)
         and returns a view of them.  ``noise=(eps_policy [H,B,A], eps_model [H,B,S+1])`` injects the Gaussian draws
         indexed by original trajectory id (parity); ``member_idx`` overrides the per-step elite picks."""
@@ -125,6 +125,13 @@ class SMBPO(Configurable, nn.Module):
         a.virt, a.step_counts, a.precision = ring.as_struct(), _lib.ptr(counts), self.rollout_precision
         ws = self._ws.get(lib.drpo_rollout_workspace_bytes(a), initial_states.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        if _debug_layer is not None:
+            n_out = [policy.net[0].weight.shape[0], policy.net[2].weight.shape[0], policy.net[4].weight.shape[0],
+                     self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim,
+                     self.state_dim + 1, self.model_ensemble.hidden_dim, self.state_dim + 1][_debug_layer]
+            out = torch.zeros((B, n_out), device=initial_states.device)
+            _lib.check(lib.drpo_debug_rollout_layer(a, _debug_layer, _lib.ptr(out)), "drpo_debug_rollout_layer")
+            return out
         _lib.check(lib.drpo_rollout(a), "drpo_rollout")
         return RolloutView(ring, start, counts)
 

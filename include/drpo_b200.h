@@ -208,6 +208,9 @@ typedef struct drpo_rollout_args {
 
 int64_t drpo_rollout_workspace_bytes(const drpo_rollout_args* args);
 int drpo_rollout(const drpo_rollout_args* args);
+/* Debug aid for the DRPO_PREC_BF16 path: runs step 0 only and dumps the fp32 TMEM accumulator of dense layer `layer`
+ * (0..8 = actor L0,L1,L2, member trunk0, trunk1, diff0, diff1, logvar0, logvar1) as out[batch, out_dim]. */
+int drpo_debug_rollout_layer(const drpo_rollout_args* args, int32_t layer, float* out);
 
 /* ------------------------------------------------------------------------------------------------------------
  * SSAC.update_critic (src/ssac.py:437-456 with compute_target :284-294, compute_cons_target :338-362,
