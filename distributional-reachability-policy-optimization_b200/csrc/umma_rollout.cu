@@ -2,15 +2,17 @@
 //   policy MLP -> squashed-Gaussian sample -> ensemble-member MLP (trunk + 2 heads) -> Gaussian next-state sample
 //   -> env hooks
 // chain for a 128-row tile without ever leaving the SM:
-//   * every dense layer is a tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with M = 128 rows of trajectories,
-//   * the accumulator AND the activations live in TMEM (the A operand of layer l+1 is read from TMEM, where the epilogue
-//     of layer l stored it as packed bf16), so activations never touch shared or global memory,
-//   * weights are pre-packed once per rollout into the UMMA canonical K-major (no-swizzle) layout and streamed from L2
-//     into a shared-memory ring by TMA bulk copies (cp.async.bulk, mbarrier complete_tx),
-//   * bias rides in the GEMM: every activation tile carries a constant-1 column and the packed weights carry the bias in
-//     the matching K slot, so the epilogue is activation + bf16 pack only.
-// Warp roles: warps 0-3 = epilogue (thread t owns TMEM lane t = trajectory row t), warp 4 = TMA producer,
-// warp 5 = MMA issuer (one elected thread) + TMEM allocator.
+//   * every dense layer is a sequence of tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M = 128 trajectories) issued per
+//     64-column output slab into one of three TMEM accumulator buffers, so the epilogue of slab j overlaps the MMAs of
+//     slab j+1 (and of the next independent layer);
+//   * the activations live in TMEM too: the epilogue stores them as packed bf16 and the next layer reads its A operand
+//     straight from TMEM (TS-mode MMA) — activations never touch shared or global memory;
+//   * weights are packed once per rollout into the UMMA canonical K-major (no-swizzle) layout, one contiguous block per
+//     (layer, 64-row slab), and streamed from L2 into a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier);
+//   * bias rides in the GEMM: every activation tile carries a constant-1 column and the packed weights hold the bias in
+//     the matching K slot; the epilogue is activation (packed bf16x2 math) + TMEM store only.
+// Warp roles: warps 0-7 = epilogue (warp w owns TMEM lanes 32*(w%4).. and column half w/4 of each slab),
+// warp 8 = TMA producer, warp 9 = MMA issuer (one elected thread) + TMEM allocator.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -25,12 +27,20 @@ namespace drpo {
 namespace umma {
 
 constexpr int TILE_M = 128;
-constexpr int KCHUNK = 64;                 // K elements per weight chunk (4 MMA k-steps)
-constexpr int MAX_CHUNKS = 48;
+constexpr int NSLAB = 64;                  // output columns per slab / accumulator buffer
+constexpr int NACC = 3;                    // accumulator buffers in TMEM
+constexpr int MAX_CHUNKS = 32;
 constexpr int MAX_LAYERS = 9;
-constexpr int NUM_THREADS = 192;
-constexpr uint32_t TM_ACC = 0, TM_ACTA = 256, TM_ACTB = 392, TM_COLS = 512;
-constexpr int ACTA_COLS = 136, ACTB_COLS = 120;
+constexpr int EPI_THREADS = 256;
+constexpr int NUM_THREADS = EPI_THREADS + 64;
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t TM_COLS = 512;
+// TMEM column map (32-bit columns; bf16 activations take kp/2 columns)
+constexpr uint32_t TM_ACC = 0;                                   // 3 x 64 fp32 accumulator columns
+constexpr uint32_t TM_PA = 192, TM_PB = 328, TM_XP = 464;        // policy: hidden A (<=136), hidden B (<=136), input (<=32)
+constexpr uint32_t TM_H2 = 192, TM_D1 = 296, TM_L1 = 400;        // model: h2, h1/d1, x_m/l1 (<=104 each)
+
+enum LayerKind { HID_RELU = 0, HID_SILU = 1, OUT_POLICY = 2, OUT_DIFF = 3, OUT_LOGVAR = 4 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -62,7 +72,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   __trap();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -102,13 +111,24 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {       // element 2j in the low half, 2j+1 in the high half
+// packed bf16x2 math for the epilogues (element 2j in the low half, 2j+1 in the high half)
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float silu_fast(float x) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }   // x*sigmoid(x)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
+  uint32_t r; const uint32_t z = 0u;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(z));
+  return r;
+}
+__device__ __forceinline__ uint32_t silu_bf16x2(uint32_t x) {          // x*sigmoid(x) = h + h*tanh(h), h = x/2
+  uint32_t h, t, r; const uint32_t half2 = 0x3F003F00u;                  // (0.5, 0.5) in bf16
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(half2));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(h));
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(h), "r"(t), "r"(h));
+  return r;
+}
 
 // K-major, no-swizzle UMMA shared-memory descriptor: core matrix = 8 rows x 16 B, LBO = K-direction stride,
 // SBO = 8-row-group stride (cute::UMMA::SmemDescriptor, version 1)
@@ -126,36 +146,36 @@ __host__ __device__ inline uint32_t make_idesc(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// weight image: per layer, per 64-wide K chunk, a contiguous block in canonical layout  [n/8][k/8][8 rows][8 elems]
+// weight image: per layer, per 64-row slab, a contiguous block in canonical layout  [n/8][k/8][8 rows][8 elems]
 // ---------------------------------------------------------------------------------------------------------------
 struct LayerSpec {
   int n_real, k_real;      // nn.Linear out / in
   int np, kp;              // padded MMA N (x16) and K (x16, includes the bias slot at k_real)
-  int act;                 // ACT_RELU / ACT_SILU / ACT_NONE (final layers)
+  int kind;                // LayerKind
   int a_col, out_col;      // TMEM column of the A operand / of the activation written by the epilogue
   int first_chunk, n_chunks;
+  int dep;                 // layer whose epilogue must be complete before this layer's MMAs may read a_col (-1: tile input)
+  int next_kp;             // K (padded) of the consumer of out_col
 };
-struct ChunkSpec { uint32_t offset, bytes; uint16_t n, kc; };     // byte offset inside the net image
+struct ChunkSpec { uint32_t offset, bytes; uint16_t n0, nc; uint16_t layer, pad; };     // byte offset inside the net image
 struct NetPlan {
   LayerSpec layer[MAX_LAYERS];
   ChunkSpec chunk[MAX_CHUNKS];
   int n_layers, n_chunks;
-  uint32_t policy_bytes, model_bytes;     // image sizes; policy chunks index into the policy image, model chunks into the member image
+  uint32_t policy_bytes, model_bytes;     // image sizes; policy slabs index the actor image, model slabs the member image
   int n_policy_chunks;
   uint32_t max_chunk_bytes;
 };
 
 __global__ void pack_layer_kernel(const float* __restrict__ W, const float* __restrict__ b, int n_real, int k_real, int np, int kp,
                                   __nv_bfloat16* __restrict__ dst /* start of this layer inside the image */) {
-  // one thread per padded element (n, k)
   const int total = np * kp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i / kp, k = i % kp;
     float v = 0.f;
     if (n < n_real) v = k < k_real ? W[(int64_t)n * k_real + k] : (k == k_real ? b[n] : 0.f);
-    const int kc0 = (k / KCHUNK) * KCHUNK, kc = min(KCHUNK, kp - kc0), kk = k - kc0;
-    const int64_t chunk_off = (int64_t)np * kc0;                                   // elements before this chunk
-    const int64_t idx = chunk_off + ((int64_t)(n >> 3) * (kc >> 3) + (kk >> 3)) * 64 + (n & 7) * 8 + (kk & 7);
+    const int slab = n / NSLAB, nin = n - slab * NSLAB;
+    const int64_t idx = (int64_t)slab * NSLAB * kp + ((int64_t)(nin >> 3) * (kp >> 3) + (k >> 3)) * 64 + (nin & 7) * 8 + (k & 7);
     dst[idx] = __float2bfloat16_rn(v);
   }
 }
@@ -166,7 +186,6 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, const float* __re
 struct StepParams {
   NetPlan plan;
   const uint8_t* policy_img; const uint8_t* model_img;
-  // data
   const float* cur; const int32_t* ids; const int* n_dev; int64_t n_max;
   float *actions, *next_states, *rewards, *cv; uint8_t *done, *viol;
   const float *norm_mean, *norm_std, *min_lv, *max_lv;
@@ -174,52 +193,15 @@ struct StepParams {
   drpo_env_params env;
   int S, A, C, SP, OP, stages;
   int* err_flag;
-  // debug / self-test: dump the fp32 accumulator of layer `dump_layer` (n_real columns) into dump_out[row, col]
-  int dump_layer; float* dump_out;
+  int dump_layer; float* dump_out;       // debug: dump the fp32 accumulator of one layer
 };
 
 struct SmemLayout {
-  uint64_t full[8], empty[8], in_ready, acc_ready;
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_free[NACC], tile_ready;
   uint32_t tmem_base, pad;
 };
 
-__device__ __forceinline__ void act_store_const_tail(uint32_t lane_base, uint32_t out_col, int from_elem, int kp, int one_at) {
-  // activation elements [from_elem, kp) are constants: 1.0 at `one_at`, 0 elsewhere (from_elem, kp multiples of 16)
-  for (int e0 = from_elem; e0 < kp; e0 += 16) {
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16((e0 + 2 * j) == one_at ? 1.f : 0.f, (e0 + 2 * j + 1) == one_at ? 1.f : 0.f);
-    tmem_st8(lane_base + out_col + (uint32_t)(e0 >> 1), pk);
-  }
-}
-
-// epilogue of a hidden layer: ACC[0,np) -> act -> bf16 pairs -> TMEM activation buffer with the constant-1 bias column
-__device__ __forceinline__ void hidden_epilogue(uint32_t lane_base, const LayerSpec& L, int next_kp) {
-  for (int c0 = 0; c0 < L.np; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld16(lane_base + TM_ACC + (uint32_t)c0, r);
-    tmem_ld_wait();
-    float v[16];
-    if (L.act == ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]), 0.f);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = silu_fast(__uint_as_float(r[j]));
-    }
-    if (L.n_real >= c0 && L.n_real < c0 + 16) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) if (c0 + j == L.n_real) v[j] = 1.f;           // bias slot of the next layer
-    }
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-    tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(c0 >> 1), pk);
-  }
-  if (next_kp > L.np) act_store_const_tail(lane_base, (uint32_t)L.out_col, L.np, next_kp, L.n_real);
-}
-
-// write one input row (k_real values from smem scratch + constant 1) as packed bf16 into a TMEM activation buffer
+// write one input row (k_real values + constant 1) as packed bf16 into a TMEM activation buffer
 __device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col, const float* row, int k_real, int kp) {
   for (int e0 = 0; e0 < kp; e0 += 16) {
     uint32_t pk[8];
@@ -234,34 +216,65 @@ __device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col
   }
 }
 
+// epilogue of one slab of a hidden layer: ACC[acc_col + (c - n0)] -> activation -> packed bf16 -> TMEM out_col + c/2
+template <bool kSilu>
+__device__ __forceinline__ void hidden_slab(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int c_begin, int c_end) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(lane_base + acc_col + (uint32_t)(c0 - n0), r);
+    tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t x = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      pk[j] = kSilu ? silu_bf16x2(x) : relu_bf16x2(x);
+    }
+    if (L.n_real >= c0 && L.n_real < c0 + 16) {                 // constant-1 column = bias slot of the consumer
+      const int e = L.n_real - c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == (e >> 1)) pk[j] = (e & 1) ? ((pk[j] & 0x0000FFFFu) | 0x3F800000u) : ((pk[j] & 0xFFFF0000u) | 0x00003F80u);
+    }
+    tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(c0 >> 1), pk);
+  }
+}
+
+// debug timing (dump_layer == 100): CTA 0 stamps clock() for its first 4 tiles into dump_out viewed as uint32
+// [(tile*32 + slab)*8 + k], k: 0 epi wait begin, 1 accumulator ready, 2 epilogue done, 3 mma deps ok, 4 weights ready,
+// 5 mma issued, 6 E0 begin, 7 E0 end
+__device__ __forceinline__ void stamp(const StepParams& p, uint32_t tile_it, int slab, int k) {
+  if (p.dump_layer == 100 && blockIdx.x == 0 && tile_it < 4)
+    reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + slab) * 8 + k] = (uint32_t)clock();
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const NetPlan& plan = p.plan;
-  // carve shared memory: [weight ring | state tile | out tile | x tile | barriers]
+  // shared memory: [weight ring | state tile | out tile | barriers]
   uint8_t* ring = smem_raw;
   const uint32_t slot_bytes = (plan.max_chunk_bytes + 1023u) & ~1023u;
   float* st_s = reinterpret_cast<float*>(ring + (size_t)slot_bytes * p.stages);      // [128][SP] current states (fp32)
-  float* st_o = st_s + TILE_M * p.SP;                                                // [128][OP] diff-head output -> next state
+  float* st_o = st_s + TILE_M * p.SP;                                                // [128][OP] model input / next state
   SmemLayout* sl = reinterpret_cast<SmemLayout*>(st_o + TILE_M * p.OP);
 
-  int n = min((int64_t)*p.n_dev, p.n_max);
+  const int n = (int)min((int64_t)*p.n_dev, p.n_max);
   const int n_tiles = (n + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&sl->full[s], 1); mbar_init(&sl->empty[s], 1); }
-    mbar_init(&sl->in_ready, TILE_M);
-    mbar_init(&sl->acc_ready, 1);
+    for (int b = 0; b < NACC; ++b) { mbar_init(&sl->acc_full[b], 1); mbar_init(&sl->acc_free[b], EPI_THREADS); }
+    mbar_init(&sl->tile_ready, EPI_THREADS);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&sl->tmem_base, TM_COLS);
+  if (warp == 9) tmem_alloc(&sl->tmem_base, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sl->tmem_base;
 
-  if (warp == 4) {
-    // ===================== TMA producer: stream every weight chunk of every tile through the ring =====================
+  if (warp == 8) {
+    // ===================== TMA producer: stream every weight slab of every tile through the ring =====================
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -275,150 +288,202 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t it = 0, lphase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < plan.n_layers; ++l, ++lphase) {
+      uint32_t it = 0;            // ring iteration == global slab counter g (one ring slot per slab)
+      int64_t done_upto = -1;     // every slab with global index <= done_upto is known to be epilogued
+      uint32_t tile_it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+        const int64_t g_tile = (int64_t)tile_it * plan.n_chunks;
+        mbar_wait(&sl->tile_ready, tile_it & 1, p.err_flag, 2);
+        tc_fence_after();
+        for (int l = 0; l < plan.n_layers; ++l) {
           const LayerSpec& L = plan.layer[l];
-          mbar_wait(&sl->in_ready, lphase & 1, p.err_flag, 2);           // A operand written, accumulator free
-          tc_fence_after();
-          const uint32_t idesc = make_idesc(L.np);
-          int kdone = 0;
+          if (L.dep >= 0) {       // A operand = output of layer dep: all of its slabs must be through the epilogue
+            const int64_t G = g_tile + plan.layer[L.dep].first_chunk + plan.layer[L.dep].n_chunks - 1;
+            if (G > done_upto) {
+              mbar_wait(&sl->acc_free[G % NACC], (uint32_t)(G / NACC) & 1, p.err_flag, 5);
+              done_upto = G; tc_fence_after();
+            }
+          }
+          const uint32_t sbo = (uint32_t)(L.kp >> 3) * 128u;
           for (int c = 0; c < L.n_chunks; ++c, ++it) {
-            const int s = it % p.stages; const uint32_t round = it / p.stages;
             const ChunkSpec& ch = plan.chunk[L.first_chunk + c];
+            const int64_t g = g_tile + L.first_chunk + c;
+            const int b = (int)(g % NACC);
+            if (g >= NACC && g - NACC > done_upto) {                     // accumulator buffer still being drained?
+              mbar_wait(&sl->acc_free[b], (uint32_t)((g - NACC) / NACC) & 1, p.err_flag, 6);
+              done_upto = g - NACC; tc_fence_after();
+            }
+            stamp(p, tile_it, L.first_chunk + c, 3);
+            const int s = it % p.stages; const uint32_t round = it / p.stages;
             mbar_wait(&sl->full[s], round & 1, p.err_flag, 3);
             tc_fence_after();
+            stamp(p, tile_it, L.first_chunk + c, 4);
             const uint32_t b_base = smem_u32(ring + (size_t)s * slot_bytes);
-            const uint32_t sbo = (uint32_t)(ch.kc >> 3) * 128u;
-            for (int ks = 0; ks < ch.kc; ks += 16, kdone += 16) {
+            const uint32_t idesc = make_idesc(ch.nc);
+            const uint32_t d_addr = tmem + TM_ACC + (uint32_t)b * NSLAB;
+            for (int ks = 0; ks < L.kp; ks += 16) {
               const uint64_t bdesc = make_b_desc(b_base + (uint32_t)(ks >> 3) * 128u, 128u, sbo);
-              mma_ts(tmem + TM_ACC, tmem + (uint32_t)L.a_col + (uint32_t)(kdone >> 1), bdesc, idesc, kdone > 0 ? 1u : 0u);
+              mma_ts(d_addr, tmem + (uint32_t)L.a_col + (uint32_t)(ks >> 1), bdesc, idesc, ks > 0 ? 1u : 0u);
             }
             tc_commit(&sl->empty[s]);                                    // frees the ring slot when these MMAs retire
+            tc_commit(&sl->acc_full[b]);                                 // slab accumulator complete -> epilogue
+            stamp(p, tile_it, L.first_chunk + c, 5);
           }
-          tc_commit(&sl->acc_ready);                                     // accumulator complete -> epilogue
         }
       }
     }
   } else {
-    // ===================== epilogue warps: thread t <-> TMEM lane t <-> trajectory row t of the tile =====================
-    const int t = threadIdx.x;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warps =====================
+    const int q = warp & 3, hf = warp >> 2;
+    const int t = q * 32 + lane;                                          // trajectory row of the tile == TMEM lane
+    const int et = threadIdx.x;                                           // 0..255
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int S = p.S, A = p.A, O = S + 1;
-    uint32_t aphase = 0;
     float* my_s = st_s + t * p.SP;
     float* my_o = st_o + t * p.OP;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      const int64_t g_tile = (int64_t)tile_it * plan.n_chunks;
       const int64_t row0 = (int64_t)tile * TILE_M;
       const int rows = min(TILE_M, n - (int)row0);
       const bool valid = t < rows;
       const int64_t row = row0 + t;
       // ---- E0: stage the tile's states (coalesced), write the policy input [s, 1] into TMEM ----
-      asm volatile("bar.sync 1, 128;" ::: "memory");                     // previous tile's readers of st_s/st_o are done
-      for (int i = t; i < TILE_M * S; i += TILE_M) {
+      if (et == 0) stamp(p, tile_it, 0, 6);
+      asm volatile("bar.sync 1, 256;" ::: "memory");                     // previous tile's readers of st_s/st_o are done
+      for (int i = et; i < TILE_M * S; i += EPI_THREADS) {
         const int r = i / S, c = i - r * S;
         st_s[r * p.SP + c] = r < rows ? p.cur[row0 * S + i] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      int l = 0;
-      write_input_row(lane_base, (uint32_t)plan.layer[0].a_col, my_s, S, plan.layer[0].kp);
-      tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->in_ready);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hf == 0) write_input_row(lane_base, (uint32_t)plan.layer[0].a_col, my_s, S, plan.layer[0].kp);
+      tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->tile_ready);
+      if (et == 0) stamp(p, tile_it, 0, 7);
 
-      float act_v[4];          // sampled action (A <= 4)
-      for (; l < plan.n_layers; ++l, ++aphase) {
-        const LayerSpec& L = plan.layer[l];
-        mbar_wait(&sl->acc_ready, aphase & 1, p.err_flag, 4);
+      for (int c = 0; c < plan.n_chunks; ++c) {
+        const ChunkSpec& ch = plan.chunk[c];
+        const LayerSpec& L = plan.layer[ch.layer];
+        const int64_t g = g_tile + c;
+        const int b = (int)(g % NACC);
+        const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
+        if (et == 0) stamp(p, tile_it, c, 0);
+        mbar_wait(&sl->acc_full[b], (uint32_t)(g / NACC) & 1, p.err_flag, 4);
         tc_fence_after();
-        if (p.dump_layer == l) {                                         // self-test hook: raw accumulator to global
-          for (int c0 = 0; c0 < L.np; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(lane_base + TM_ACC + (uint32_t)c0, r); tmem_ld_wait();
-            if (valid) for (int j = 0; j < 16; ++j) if (c0 + j < L.n_real) p.dump_out[row * L.n_real + c0 + j] = __uint_as_float(r[j]);
+        if (et == 0) stamp(p, tile_it, c, 1);
+        if (p.dump_layer == (int)ch.layer && hf == 0) {                  // debug hook: raw accumulator to global
+          for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+            uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
+            if (valid) for (int j = 0; j < 16; ++j) if (ch.n0 + c0 + j < L.n_real) p.dump_out[row * L.n_real + ch.n0 + c0 + j] = __uint_as_float(r[j]);
           }
         }
-        if (L.act != ACT_NONE) {
-          hidden_epilogue(lane_base, L, plan.layer[l + 1].kp);
-        } else if (l == 2) {
-          // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
-          uint32_t r[16]; tmem_ld16(lane_base + TM_ACC, r); tmem_ld_wait();
-          const int64_t id = valid ? (int64_t)p.ids[row] : 0;
+        if (L.kind == HID_RELU || L.kind == HID_SILU) {
+          int c_begin = ch.n0, c_end = ch.n0 + ch.nc;
+          if ((ch.nc & 31) == 0) { const int cw = ch.nc >> 1; c_begin += hf * cw; c_end = c_begin + cw; }
+          else if (hf == 1) c_end = c_begin;                             // narrow slab: column half 0 does it all
+          if (L.kind == HID_SILU) hidden_slab<true>(lane_base, acc_col, L, ch.n0, c_begin, c_end);
+          else hidden_slab<false>(lane_base, acc_col, L, ch.n0, c_begin, c_end);
+          if (hf == 0 && ch.n0 + ch.nc == L.np && L.next_kp > L.np) {    // constant tail [np, next_kp): 1 at n_real, else 0
+            for (int e0 = L.np; e0 < L.next_kp; e0 += 16) {
+              uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < A) {
-              float mu = 0.f, raw = 0.f;
-#pragma unroll
-              for (int q = 0; q < 16; ++q) { if (q == j) mu = __uint_as_float(r[q]); if (q == A + j) raw = __uint_as_float(r[q]); }
-              const float sd = __expf(-6.f + 10.f / (1.f + __expf(-raw)));
-              const float x = valid ? fmaf(p.noise_p.get(id, j), sd, mu) : 0.f;
-              act_v[j] = tanhf(x);
-              if (valid) p.actions[row * A + j] = act_v[j];
+              for (int j = 0; j < 8; ++j) pk[j] = pack_bf16((e0 + 2 * j) == L.n_real ? 1.f : 0.f, (e0 + 2 * j + 1) == L.n_real ? 1.f : 0.f);
+              tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(e0 >> 1), pk);
             }
           }
-          // model input x0 = [(s - mean)/(std + 1e-6), a, 1]                               src/dynamics.py:113-114
-          for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - p.norm_mean[c]) / (p.norm_std[c] + 1e-6f);
+        } else if (L.kind == OUT_POLICY) {
+          // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
+          if (hf == 0) {
+            uint32_t r[16]; tmem_ld16(lane_base + acc_col, r); tmem_ld_wait();
+            const int64_t id = valid ? (int64_t)p.ids[row] : 0;
+            const float4 e4 = valid ? noise_get4(p.noise_p, id, 0, A) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - p.norm_mean[c]) / (p.norm_std[c] + 1e-6f);   // src/dynamics.py:113
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < A) my_o[S + j] = act_v[j];
-          write_input_row(lane_base, (uint32_t)plan.layer[3].a_col, my_o, S + A, plan.layer[3].kp);
-        } else if (l == 6) {
-          // ---- diff head: means = diffs + [s, 0]  -> shared-memory row                  src/dynamics.py:118 ----
-          for (int c0 = 0; c0 < L.np; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(lane_base + TM_ACC + (uint32_t)c0, r); tmem_ld_wait();
+            for (int j = 0; j < 4; ++j) {
+              if (j < A) {
+                float mu = 0.f, raw = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (c0 + j < O) my_o[c0 + j] = __uint_as_float(r[j]) + (c0 + j < S ? my_s[c0 + j] : 0.f);
+                for (int k = 0; k < 16; ++k) { if (k == j) mu = __uint_as_float(r[k]); if (k == A + j) raw = __uint_as_float(r[k]); }
+                const float sd = __expf(-6.f + 10.f / (1.f + __expf(-raw)));
+                const float a = tanhf(fmaf(ev[j], sd, mu));
+                my_o[S + j] = a;
+                if (valid) p.actions[row * A + j] = a;
+              }
+            }
+            // model input x0 = [(s - mean)/(std + 1e-6), a, 1]                               src/dynamics.py:113-114
+            write_input_row(lane_base, (uint32_t)plan.layer[ch.layer + 1].a_col, my_o, S + A, plan.layer[ch.layer + 1].kp);
           }
-        } else {
-          // ---- log-var head + sampling + hooks                                         src/dynamics.py:119-121,201-203 ----
-          const int64_t id = valid ? (int64_t)p.ids[row] : 0;
-          float reward = 0.f;
-          for (int c0 = 0; c0 < L.np; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(lane_base + TM_ACC + (uint32_t)c0, r); tmem_ld_wait();
+        } else if (L.kind == OUT_DIFF) {
+          // ---- diff head: means = diffs + [s, 0]  (kept in shared memory)                   src/dynamics.py:118 ----
+          asm volatile("bar.sync 2, 256;" ::: "memory");                 // my_o (model input scratch) no longer read by row owner
+          for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+            uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int c = c0 + j;
-              if (c < O) {
-                const float lv = soft_clamp(__uint_as_float(r[j]), p.min_lv[c], p.max_lv[c]);
-                const float sd = sqrtf(__expf(lv));
-                const float y = valid ? fmaf(sd, p.noise_m.get(id, c), my_o[c]) : 0.f;
-                if (c < S) my_o[c] = y; else reward = y;
+              const int cc = c0 + j;
+              if (cc < O && ((cc >> 2) & 1) == hf) my_o[cc] = __uint_as_float(r[j]) + (cc < S ? my_s[cc] : 0.f);
+            }
+          }
+        } else {
+          // ---- log-var head + Gaussian sample + hooks                                       src/dynamics.py:119-121,201-203 ----
+          const int64_t id = valid ? (int64_t)p.ids[row] : 0;
+          for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+            uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
+#pragma unroll
+            for (int jg = 0; jg < 4; ++jg) {
+              const int cg = (c0 >> 2) + jg;
+              if ((cg & 1) == hf && 4 * cg < O) {
+                const float4 e4 = valid ? noise_get4(p.noise_m, id, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int cc = 4 * cg + k;
+                  if (cc < O) {
+                    const float lv = soft_clamp(__uint_as_float(r[4 * jg + k]), p.min_lv[cc], p.max_lv[cc]);
+                    my_o[cc] = fmaf(sqrtf(__expf(lv)), ev[k], my_o[cc]);
+                  }
+                }
               }
             }
           }
-          if (valid) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");                 // both column halves of every row are in st_o
+          if (hf == 0 && valid) {
             HookOut ho;
             eval_hooks(p.env, [my_o](int d) { return my_o[d]; }, ho);
-            p.rewards[row] = reward; p.done[row] = ho.done; p.viol[row] = ho.viol;
-            for (int c = 0; c < p.C; ++c) p.cv[row * p.C + c] = ho.cv[c];
+            p.rewards[row] = my_o[S]; p.done[row] = ho.done; p.viol[row] = ho.viol;
+            for (int cc = 0; cc < p.C; ++cc) p.cv[row * p.C + cc] = ho.cv[cc];
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = t; i < rows * S; i += TILE_M) {                   // coalesced store of the tile's next states
-            const int r = i / S, c = i - r * S;
-            p.next_states[row0 * S + i] = st_o[r * p.OP + c];
+          for (int i = et; i < rows * S; i += EPI_THREADS) {             // coalesced store of the tile's next states
+            const int r = i / S, cc = i - r * S;
+            p.next_states[row0 * S + i] = st_o[r * p.OP + cc];
           }
         }
-        if (l + 1 < plan.n_layers) {                                     // hand the accumulator (and new activations) back
-          tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->in_ready);
-        }
+        tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->acc_free[b]);   // accumulator drained, activations visible
+        if (et == 0) stamp(p, tile_it, c, 2);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, TM_COLS);
+  if (warp == 9) tmem_dealloc(tmem, TM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static void add_layer(NetPlan& P, int n_real, int k_real, int act, int a_col, int out_col, uint32_t& img_off) {
-  LayerSpec& L = P.layer[P.n_layers++];
+static void add_layer(NetPlan& P, int n_real, int k_real, int kind, int a_col, int out_col, int dep, uint32_t& img_off) {
+  const int l = P.n_layers++;
+  LayerSpec& L = P.layer[l];
   L.n_real = n_real; L.k_real = k_real; L.np = round_up(n_real, 16); L.kp = round_up(k_real + 1, 16);
-  L.act = act; L.a_col = a_col; L.out_col = out_col; L.first_chunk = P.n_chunks; L.n_chunks = 0;
-  for (int k0 = 0; k0 < L.kp; k0 += KCHUNK) {
+  L.kind = kind; L.a_col = a_col; L.out_col = out_col; L.first_chunk = P.n_chunks; L.n_chunks = 0; L.dep = dep;
+  L.next_kp = (kind == HID_RELU || kind == HID_SILU) ? round_up(n_real + 1, 16) : 0;
+  for (int n0 = 0; n0 < L.np; n0 += NSLAB) {
     ChunkSpec& c = P.chunk[P.n_chunks++];
-    c.kc = (uint16_t)std::min(KCHUNK, L.kp - k0); c.n = (uint16_t)L.np;
-    c.offset = img_off + (uint32_t)L.np * k0 * 2; c.bytes = (uint32_t)L.np * c.kc * 2;
+    c.n0 = (uint16_t)n0; c.nc = (uint16_t)std::min(NSLAB, L.np - n0); c.layer = (uint16_t)l; c.pad = 0;
+    c.offset = img_off + (uint32_t)n0 * L.kp * 2; c.bytes = (uint32_t)c.nc * L.kp * 2;
     P.max_chunk_bytes = std::max(P.max_chunk_bytes, c.bytes);
     ++L.n_chunks;
   }
@@ -429,27 +494,28 @@ static int build_plan(const drpo_rollout_args& a, NetPlan& P) {
   memset(&P, 0, sizeof(P));
   const int S = a.ensemble->state_dim, A = a.ensemble->action_dim, Hm = a.ensemble->hidden;
   const int Hp = a.actor->l0.out_dim;
-  if (a.actor->l1.out_dim != Hp || Hp > 256 || round_up(Hp + 1, 16) / 2 > ACTA_COLS || round_up(Hm + 1, 16) / 2 > ACTB_COLS ||
-      round_up(S + A + 1, 16) / 2 > 32 || 2 * A > 16 || A > 4 || round_up(S + 1, 16) > 256 || Hm > 256) {
-    set_error("bf16 rollout: dims outside the TMEM plan (S=%d A=%d Hp=%d Hm=%d)", S, A, Hp, Hm);
+  if (a.actor->l1.out_dim != Hp || round_up(Hp + 1, 16) > 272 || round_up(Hm + 1, 16) > 208 || round_up(S + A + 1, 16) > 64 ||
+      2 * A > 16 || A > 4 || round_up(S + 1, 16) > NSLAB) {
+    set_error("bf16 rollout: dims outside the TMEM plan (S=%d A=%d actor hidden=%d model hidden=%d)", S, A, Hp, Hm);
     return DRPO_ERR_UNSUPPORTED;
   }
   uint32_t off = 0;
-  add_layer(P, Hp, S, ACT_RELU, TM_ACTB, TM_ACTA, off);          // P1
-  add_layer(P, Hp, Hp, ACT_RELU, TM_ACTA, TM_ACTA, off);         // P2 (in place: all MMAs retired before the epilogue)
-  add_layer(P, 2 * A, Hp, ACT_NONE, TM_ACTA, 0, off);            // P3 -> policy head
+  add_layer(P, Hp, S, HID_RELU, TM_XP, TM_PA, -1, off);           // 0 actor L0
+  add_layer(P, Hp, Hp, HID_RELU, TM_PA, TM_PB, 0, off);           // 1 actor L1
+  add_layer(P, 2 * A, Hp, OUT_POLICY, TM_PB, 0, 1, off);          // 2 actor L2 -> policy head (writes the model input)
   P.policy_bytes = off; P.n_policy_chunks = P.n_chunks;
   off = 0;
-  add_layer(P, Hm, S + A, ACT_SILU, TM_ACTB, TM_ACTA, off);      // M1
-  add_layer(P, Hm, Hm, ACT_SILU, TM_ACTA, TM_ACTB, off);         // M2 -> h2 kept in ACTB for both heads
-  add_layer(P, Hm, Hm, ACT_SILU, TM_ACTB, TM_ACTA, off);         // M3d
-  add_layer(P, S + 1, Hm, ACT_NONE, TM_ACTA, 0, off);            // M4d -> diffs
-  add_layer(P, Hm, Hm, ACT_SILU, TM_ACTB, TM_ACTA, off);         // M3l
-  add_layer(P, S + 1, Hm, ACT_NONE, TM_ACTA, 0, off);            // M4l -> log-vars
+  add_layer(P, Hm, S + A, HID_SILU, TM_L1, TM_D1, 2, off);        // 3 trunk0: x_m lives in the (still unused) l1 region
+  add_layer(P, Hm, Hm, HID_SILU, TM_D1, TM_H2, 3, off);           // 4 trunk1 -> h2, kept for both heads
+  add_layer(P, Hm, Hm, HID_SILU, TM_H2, TM_D1, 4, off);           // 5 diff head hidden
+  add_layer(P, Hm, Hm, HID_SILU, TM_H2, TM_L1, 4, off);           // 6 log-var head hidden (independent of 5: no bubble)
+  add_layer(P, S + 1, Hm, OUT_DIFF, TM_D1, 0, 5, off);            // 7 diffs
+  add_layer(P, S + 1, Hm, OUT_LOGVAR, TM_L1, 0, 6, off);          // 8 log-vars
   P.model_bytes = off;
   return DRPO_OK;
 }
 
+// order of drpo_linear's handed to pack_net for the member net: trunk0, trunk1, diff0, lvar0, diff1, lvar1 (= layers 3..8)
 static int pack_net(const drpo_linear* lin, const LayerSpec* L, int count, uint8_t* img, void* stream) {
   uint32_t off = 0;
   for (int i = 0; i < count; ++i) {
@@ -461,7 +527,7 @@ static int pack_net(const drpo_linear* lin, const LayerSpec* L, int count, uint8
 }
 
 static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP) {
-  SP = S | 1; OP = std::max(S + 1, S + 4 + 1) | 1;           // st_o also holds the model input row [norm s, a]
+  SP = S | 1; OP = (S + 4 + 1) | 1;                        // st_o holds [norm s, a] and later [next state, reward]
   const uint32_t slot = (P.max_chunk_bytes + 1023u) & ~1023u;
   return (int)(slot * stages + (size_t)TILE_M * (SP + OP) * 4 + sizeof(SmemLayout) + 64);
 }
@@ -481,7 +547,7 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
   if ((rc = build_plan(a, P))) return rc;
   const int64_t B = a.batch; const int S = a.ensemble->state_dim, A = a.ensemble->action_dim, C = a.env->con_dim;
   const int H = dump_layer >= 0 ? 1 : a.horizon; void* stream = a.stream;
-  if (dump_layer >= P.n_layers) { set_error("debug dump: layer %d out of range", dump_layer); return DRPO_ERR_ARG; }
+  if (dump_layer >= P.n_layers && dump_layer != 100) { set_error("debug dump: layer %d out of range", dump_layer); return DRPO_ERR_ARG; }
   Arena ar(a.workspace, a.workspace_bytes);
   RolloutScratch w;
   w.curA = ar.take<float>(B * S); w.curB = ar.take<float>(B * S); w.actions = ar.take<float>(B * A);
@@ -506,7 +572,7 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
     for (int m = 0; m < E; ++m) {
       if (!used[m]) continue;
       MemberNet mn = member_of(*a.ensemble, m);
-      drpo_linear ml[6] = {mn.t0, mn.t1, mn.d0, mn.d1, mn.l0, mn.l1};
+      drpo_linear ml[6] = {mn.t0, mn.t1, mn.d0, mn.l0, mn.d1, mn.l1};       // plan order: 3 trunk0, 4 trunk1, 5 diff0, 6 lvar0, 7 diff1, 8 lvar1
       if ((rc = pack_net(ml, &P.layer[3], 6, mem_img + (int64_t)m * align_up(P.model_bytes, 1024), stream))) return rc;
     }
   }
@@ -514,9 +580,10 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int SP, OP, stages = 6;
+  int SP, OP, stages = MAX_STAGES;
   while (stages > 2 && smem_bytes_for(P, S, stages, SP, OP) > max_smem) --stages;
   const int smem = smem_bytes_for(P, S, stages, SP, OP);
+  if (smem > max_smem) { set_error("bf16 rollout: needs %d B of shared memory, device offers %d", smem, max_smem); return DRPO_ERR_UNSUPPORTED; }
   DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 
   DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));

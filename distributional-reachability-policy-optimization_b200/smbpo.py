@@ -126,10 +126,10 @@ class SMBPO(Configurable, nn.Module):
         ws = self._ws.get(lib.drpo_rollout_workspace_bytes(a), initial_states.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
         if _debug_layer is not None:
-            n_out = [policy.net[0].weight.shape[0], policy.net[2].weight.shape[0], policy.net[4].weight.shape[0],
+            n_out = 1024 if _debug_layer == 100 else [policy.net[0].weight.shape[0], policy.net[2].weight.shape[0], policy.net[4].weight.shape[0],
                      self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim,
-                     self.state_dim + 1, self.model_ensemble.hidden_dim, self.state_dim + 1][_debug_layer]
-            out = torch.zeros((B, n_out), device=initial_states.device)
+                     self.model_ensemble.hidden_dim, self.state_dim + 1, self.state_dim + 1][_debug_layer]
+            out = torch.zeros((max(B, 8), n_out), device=initial_states.device)
             _lib.check(lib.drpo_debug_rollout_layer(a, _debug_layer, _lib.ptr(out)), "drpo_debug_rollout_layer")
             return out
         _lib.check(lib.drpo_rollout(a), "drpo_rollout")

@@ -9,7 +9,7 @@ from tests.util import assert_close, dev, oracle_spec_to_device_env, to_dev
 
 pytestmark = pytest.mark.gpu
 
-LAYERS = ["actor.0", "actor.2", "actor.4", "trunk.0", "trunk.2", "diff.0", "diff.2", "lvar.0", "lvar.2"]
+LAYERS = ["actor.0", "actor.2", "actor.4", "trunk.0", "trunk.2", "diff.0", "lvar.0", "diff.2", "lvar.2"]
 
 
 def bf(x):
@@ -34,8 +34,8 @@ def emulate(ws, wm, member, states, eps_p):
     t1 = lin(torch.nn.functional.silu(t0), W("trunk.2.weight"), W("trunk.2.bias")); acc.append(t1)
     h2 = torch.nn.functional.silu(t1)
     d0 = lin(h2, W("diff_head.0.weight"), W("diff_head.0.bias")); acc.append(d0)
-    d1 = lin(torch.nn.functional.silu(d0), W("diff_head.2.weight"), W("diff_head.2.bias")); acc.append(d1)
     l0 = lin(h2, W("log_var_head.0.weight"), W("log_var_head.0.bias")); acc.append(l0)
+    d1 = lin(torch.nn.functional.silu(d0), W("diff_head.2.weight"), W("diff_head.2.bias")); acc.append(d1)
     l1 = lin(torch.nn.functional.silu(l0), W("log_var_head.2.weight"), W("log_var_head.2.bias")); acc.append(l1)
     return acc, action
 
