@@ -91,11 +91,39 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]^T      (A: 128 lanes x K bf16 packed two per column; B: K-major canonical layout)
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// The descriptor travels as two 32-bit words so that stepping along K is one 32-bit add in the issue loop.
+template <bool kAccumulate>
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc) {
+  if (kAccumulate)
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 d;\n\tsetp.eq.u32 p, 1, 1;\n\tmov.b64 d, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 d;\n\tsetp.eq.u32 p, 1, 0;\n\tmov.b64 d, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus / soft clamp with fast intrinsics (bf16-path tolerance)
+__device__ __forceinline__ float softplus_fast(float x) { return x > 15.f ? x : __logf(1.f + __expf(x)); }
+__device__ __forceinline__ float soft_clamp_fast(float x, float lo, float hi) {
+  x = hi - softplus_fast(hi - x);
+  return lo + softplus_fast(x - lo);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -199,7 +227,16 @@ struct StepParams {
 struct SmemLayout {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_free[NACC], tile_ready;
   uint32_t tmem_base, pad;
+  float norm_mean[64], norm_inv[64], min_lv[64], max_lv[64];     // per-dim constants of the member, staged once per CTA
 };
+
+// debug timing (dump_layer == 100): CTA 0 stamps clock() for its first 4 tiles into dump_out viewed as uint32
+// [(tile*32 + slab)*8 + k], k: 0 epi wait begin, 1 accumulator ready, 2 epilogue done, 3 mma deps ok, 4 weights ready,
+// 5 mma issued, 6 E0 begin, 7 E0 end
+__device__ __forceinline__ void stamp(const StepParams& p, uint32_t tile_it, int slab, int k) {
+  if (p.dump_layer == 100 && blockIdx.x == 0 && tile_it < 4)
+    reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + slab) * 8 + k] = (uint32_t)clock();
+}
 
 // write one input row (k_real values + constant 1) as packed bf16 into a TMEM activation buffer
 __device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col, const float* row, int k_real, int kp) {
@@ -208,9 +245,7 @@ __device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int a = e0 + 2 * j, b = a + 1;
-      const float lo = a < k_real ? row[a] : (a == k_real ? 1.f : 0.f);
-      const float hi = b < k_real ? row[b] : (b == k_real ? 1.f : 0.f);
-      pk[j] = pack_bf16(lo, hi);
+      pk[j] = pack_bf16(row[a], row[b]);          // rows are staged with their [.., 1, 0, ..] tail up to kp
     }
     tmem_st8(lane_base + col + (uint32_t)(e0 >> 1), pk);
   }
@@ -218,7 +253,35 @@ __device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col
 
 // epilogue of one slab of a hidden layer: ACC[acc_col + (c - n0)] -> activation -> packed bf16 -> TMEM out_col + c/2
 template <bool kSilu>
-__device__ __forceinline__ void hidden_slab(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int c_begin, int c_end) {
+__device__ __forceinline__ void hidden_slab32(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int c0,
+                                              const StepParams& p, uint32_t tile_it, int slab, bool do_stamp) {
+  uint32_t r[32];
+  tmem_ld32(lane_base + acc_col + (uint32_t)(c0 - n0), r);
+  tmem_ld_wait();
+  if (do_stamp && slab > 0) stamp(p, tile_it, slab, 6);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t x = pack_bf16(__uint_as_float(r[16 * h + 2 * j]), __uint_as_float(r[16 * h + 2 * j + 1]));
+      pk[j] = kSilu ? silu_bf16x2(x) : relu_bf16x2(x);
+    }
+    const int cb = c0 + 16 * h;
+    if (L.n_real >= cb && L.n_real < cb + 16) {
+      const int e = L.n_real - cb;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == (e >> 1)) pk[j] = (e & 1) ? ((pk[j] & 0x0000FFFFu) | 0x3F800000u) : ((pk[j] & 0xFFFF0000u) | 0x00003F80u);
+    }
+    tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(cb >> 1), pk);
+  }
+  if (do_stamp && slab > 0) stamp(p, tile_it, slab, 7);
+}
+template <bool kSilu>
+__device__ __forceinline__ void hidden_slab(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int c_begin, int c_end,
+                                            const StepParams& p, uint32_t tile_it, int slab, bool do_stamp) {
+  if (c_end - c_begin == 32) { hidden_slab32<kSilu>(lane_base, acc_col, L, n0, c_begin, p, tile_it, slab, do_stamp); return; }
   for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(lane_base + acc_col + (uint32_t)(c0 - n0), r);
@@ -239,14 +302,6 @@ __device__ __forceinline__ void hidden_slab(uint32_t lane_base, uint32_t acc_col
   }
 }
 
-// debug timing (dump_layer == 100): CTA 0 stamps clock() for its first 4 tiles into dump_out viewed as uint32
-// [(tile*32 + slab)*8 + k], k: 0 epi wait begin, 1 accumulator ready, 2 epilogue done, 3 mma deps ok, 4 weights ready,
-// 5 mma issued, 6 E0 begin, 7 E0 end
-__device__ __forceinline__ void stamp(const StepParams& p, uint32_t tile_it, int slab, int k) {
-  if (p.dump_layer == 100 && blockIdx.x == 0 && tile_it < 4)
-    reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + slab) * 8 + k] = (uint32_t)clock();
-}
-
 __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,8 +309,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
   // shared memory: [weight ring | state tile | out tile | barriers]
   uint8_t* ring = smem_raw;
   const uint32_t slot_bytes = (plan.max_chunk_bytes + 1023u) & ~1023u;
-  float* st_s = reinterpret_cast<float*>(ring + (size_t)slot_bytes * p.stages);      // [128][SP] current states (fp32)
-  float* st_o = st_s + TILE_M * p.SP;                                                // [128][OP] model input / next state
+  float* st_s = reinterpret_cast<float*>(ring + (size_t)slot_bytes * p.stages);      // [2][128][SP] states (fp32), double-buffered
+  float* st_o = st_s + 2 * TILE_M * p.SP;                                            // [128][OP] model input row / next state row
   SmemLayout* sl = reinterpret_cast<SmemLayout*>(st_o + TILE_M * p.OP);
 
   const int n = (int)min((int64_t)*p.n_dev, p.n_max);
@@ -267,6 +322,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
     mbar_init(&sl->tile_ready, EPI_THREADS);
     fence_barrier_init();
   }
+  if (threadIdx.x < EPI_THREADS) {
+    // constants + the constant tails of the staging rows: [.., 1, 0, 0 ..] = bias slot and K padding of the two input layers
+    const int et0 = threadIdx.x;
+    if (et0 < p.S) { sl->norm_mean[et0] = p.norm_mean[et0]; sl->norm_inv[et0] = 1.f / (p.norm_std[et0] + 1e-6f); }
+    if (et0 <= p.S) { sl->min_lv[et0] = p.min_lv[et0]; sl->max_lv[et0] = p.max_lv[et0]; }
+    for (int i = et0; i < 2 * TILE_M * p.SP; i += EPI_THREADS) { const int c = i % p.SP; st_s[i] = c == p.S ? 1.f : 0.f; }
+    for (int i = et0; i < TILE_M * p.OP; i += EPI_THREADS) { const int c = i % p.OP; st_o[i] = c == p.S + p.A ? 1.f : 0.f; }
+  }
   if (warp == 9) tmem_alloc(&sl->tmem_base, TM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -276,61 +339,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
   if (warp == 8) {
     // ===================== TMA producer: stream every weight slab of every tile through the ring =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0; uint32_t round = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < plan.n_chunks; ++c, ++it) {
-          const int s = it % p.stages; const uint32_t round = it / p.stages;
+        for (int c = 0; c < plan.n_chunks; ++c) {
           if (round > 0) mbar_wait(&sl->empty[s], (round - 1) & 1, p.err_flag, 1);
           const ChunkSpec& ch = plan.chunk[c];
           const uint8_t* src = (c < plan.n_policy_chunks ? p.policy_img : p.model_img) + ch.offset;
           mbar_expect_tx(&sl->full[s], ch.bytes);
           bulk_g2s(ring + (size_t)s * slot_bytes, src, ch.bytes, &sl->full[s]);
+          if (++s == p.stages) { s = 0; ++round; }
         }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t it = 0;            // ring iteration == global slab counter g (one ring slot per slab)
-      int64_t done_upto = -1;     // every slab with global index <= done_upto is known to be epilogued
+      // Per-buffer use counters replace every div/mod: slab g lives in accumulator buffer b = g % NACC as its use[b]-th use.
+      int s = 0; uint32_t ring_par = 0;      // weight ring slot + parity of its current use
+      int b = 0;                             // accumulator buffer of the next slab
+      uint32_t use[NACC] = {0, 0, 0};        // number of slabs issued into each accumulator buffer so far
+      uint32_t seen[NACC] = {0, 0, 0};       // number of epilogue completions already observed per buffer
       uint32_t tile_it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-        const int64_t g_tile = (int64_t)tile_it * plan.n_chunks;
         mbar_wait(&sl->tile_ready, tile_it & 1, p.err_flag, 2);
         tc_fence_after();
+        int c_abs = 0;                       // slab index inside the tile
         for (int l = 0; l < plan.n_layers; ++l) {
           const LayerSpec& L = plan.layer[l];
-          if (L.dep >= 0) {       // A operand = output of layer dep: all of its slabs must be through the epilogue
-            const int64_t G = g_tile + plan.layer[L.dep].first_chunk + plan.layer[L.dep].n_chunks - 1;
-            if (G > done_upto) {
-              mbar_wait(&sl->acc_free[G % NACC], (uint32_t)(G / NACC) & 1, p.err_flag, 5);
-              done_upto = G; tc_fence_after();
+          if (L.dep >= 0) {
+            // A operand = output of layer dep: its LAST slab must be through the epilogue.  That slab was issued
+            // (c_abs - last) slabs ago; if that is within the last NACC slabs its buffer has not been reused and we can
+            // wait on it, otherwise a later reuse of the buffer already proved it complete.
+            const int last = plan.layer[L.dep].first_chunk + plan.layer[L.dep].n_chunks - 1;
+            const int back = c_abs - last;                       // >= 1
+            if (back <= NACC) {
+              int bb = b - back; if (bb < 0) bb += NACC;
+              if (seen[bb] < use[bb]) { mbar_wait(&sl->acc_free[bb], (use[bb] - 1) & 1, p.err_flag, 5); seen[bb] = use[bb]; tc_fence_after(); }
             }
           }
           const uint32_t sbo = (uint32_t)(L.kp >> 3) * 128u;
-          for (int c = 0; c < L.n_chunks; ++c, ++it) {
+          const int nk = L.kp >> 4;
+          for (int c = 0; c < L.n_chunks; ++c, ++c_abs) {
             const ChunkSpec& ch = plan.chunk[L.first_chunk + c];
-            const int64_t g = g_tile + L.first_chunk + c;
-            const int b = (int)(g % NACC);
-            if (g >= NACC && g - NACC > done_upto) {                     // accumulator buffer still being drained?
-              mbar_wait(&sl->acc_free[b], (uint32_t)((g - NACC) / NACC) & 1, p.err_flag, 6);
-              done_upto = g - NACC; tc_fence_after();
+            if (seen[b] < use[b]) {                                      // accumulator buffer still being drained?
+              mbar_wait(&sl->acc_free[b], (use[b] - 1) & 1, p.err_flag, 6);
+              seen[b] = use[b]; tc_fence_after();
             }
-            stamp(p, tile_it, L.first_chunk + c, 3);
-            const int s = it % p.stages; const uint32_t round = it / p.stages;
-            mbar_wait(&sl->full[s], round & 1, p.err_flag, 3);
+            stamp(p, tile_it, c_abs, 3);
+            mbar_wait(&sl->full[s], ring_par, p.err_flag, 3);
             tc_fence_after();
-            stamp(p, tile_it, L.first_chunk + c, 4);
+            stamp(p, tile_it, c_abs, 4);
             const uint32_t b_base = smem_u32(ring + (size_t)s * slot_bytes);
             const uint32_t idesc = make_idesc(ch.nc);
             const uint32_t d_addr = tmem + TM_ACC + (uint32_t)b * NSLAB;
-            for (int ks = 0; ks < L.kp; ks += 16) {
-              const uint64_t bdesc = make_b_desc(b_base + (uint32_t)(ks >> 3) * 128u, 128u, sbo);
-              mma_ts(d_addr, tmem + (uint32_t)L.a_col + (uint32_t)(ks >> 1), bdesc, idesc, ks > 0 ? 1u : 0u);
+            const uint64_t bdesc = make_b_desc(b_base, 128u, sbo);
+            uint32_t desc_lo = (uint32_t)bdesc; const uint32_t desc_hi = (uint32_t)(bdesc >> 32);
+            uint32_t a_addr = tmem + (uint32_t)L.a_col;
+            mma_ts<false>(d_addr, a_addr, desc_lo, desc_hi, idesc);
+#pragma unroll 4
+            for (int k = 1; k < nk; ++k) {                              // one k-step = 2 core matrices = 256 B = +16 in the address field
+              desc_lo += 16u; a_addr += 8u;
+              mma_ts<true>(d_addr, a_addr, desc_lo, desc_hi, idesc);
             }
             tc_commit(&sl->empty[s]);                                    // frees the ring slot when these MMAs retire
             tc_commit(&sl->acc_full[b]);                                 // slab accumulator complete -> epilogue
-            stamp(p, tile_it, L.first_chunk + c, 5);
+            stamp(p, tile_it, c_abs, 5);
+            ++use[b];
+            if (++b == NACC) b = 0;
+            if (++s == p.stages) { s = 0; ring_par ^= 1u; }
           }
         }
       }
@@ -342,35 +418,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
     const int et = threadIdx.x;                                           // 0..255
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int S = p.S, A = p.A, O = S + 1;
-    float* my_s = st_s + t * p.SP;
     float* my_o = st_o + t * p.OP;
+    // prefetch the first tile's states (cp.async, 4 B granules into the padded rows)
+    auto prefetch = [&](int tile, int buf) {
+      const int64_t r0 = (int64_t)tile * TILE_M;
+      const int rws = min(TILE_M, n - (int)r0);
+      float* dst = st_s + buf * TILE_M * p.SP;
+      for (int i = et; i < rws * S; i += EPI_THREADS) { const int r = i / S, c = i - r * S; cp_async4(dst + r * p.SP + c, p.cur + r0 * S + i); }
+      cp_async_commit();
+    };
+    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
     uint32_t tile_it = 0;
+    int b = 0; uint32_t acc_par[NACC] = {0, 0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-      const int64_t g_tile = (int64_t)tile_it * plan.n_chunks;
       const int64_t row0 = (int64_t)tile * TILE_M;
       const int rows = min(TILE_M, n - (int)row0);
       const bool valid = t < rows;
       const int64_t row = row0 + t;
-      // ---- E0: stage the tile's states (coalesced), write the policy input [s, 1] into TMEM ----
+      const int64_t id = valid ? (int64_t)p.ids[row] : 0;                // global trajectory id (noise key), fetched early
+      float* my_s = st_s + (tile_it & 1) * TILE_M * p.SP + t * p.SP;
+      // ---- E0: this tile's states have been prefetched; write the policy input [s, 1] into TMEM, normalise for the model ----
       if (et == 0) stamp(p, tile_it, 0, 6);
-      asm volatile("bar.sync 1, 256;" ::: "memory");                     // previous tile's readers of st_s/st_o are done
-      for (int i = et; i < TILE_M * S; i += EPI_THREADS) {
-        const int r = i / S, c = i - r * S;
-        st_s[r * p.SP + c] = r < rows ? p.cur[row0 * S + i] : 0.f;
+      cp_async_wait_all();
+      asm volatile("bar.sync 1, 256;" ::: "memory");                     // states landed; previous tile's readers of st_o are done
+      if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, (tile_it + 1) & 1);
+      if (hf == 0) {
+        write_input_row(lane_base, (uint32_t)plan.layer[0].a_col, my_s, plan.layer[0].kp, plan.layer[0].kp);
+      } else {
+        for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - sl->norm_mean[c]) * sl->norm_inv[c];          // src/dynamics.py:113
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (hf == 0) write_input_row(lane_base, (uint32_t)plan.layer[0].a_col, my_s, S, plan.layer[0].kp);
       tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->tile_ready);
       if (et == 0) stamp(p, tile_it, 0, 7);
 
       for (int c = 0; c < plan.n_chunks; ++c) {
         const ChunkSpec& ch = plan.chunk[c];
         const LayerSpec& L = plan.layer[ch.layer];
-        const int64_t g = g_tile + c;
-        const int b = (int)(g % NACC);
         const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
         if (et == 0) stamp(p, tile_it, c, 0);
-        mbar_wait(&sl->acc_full[b], (uint32_t)(g / NACC) & 1, p.err_flag, 4);
+        mbar_wait(&sl->acc_full[b], acc_par[b], p.err_flag, 4);
         tc_fence_after();
         if (et == 0) stamp(p, tile_it, c, 1);
         if (p.dump_layer == (int)ch.layer && hf == 0) {                  // debug hook: raw accumulator to global
@@ -383,8 +468,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
           int c_begin = ch.n0, c_end = ch.n0 + ch.nc;
           if ((ch.nc & 31) == 0) { const int cw = ch.nc >> 1; c_begin += hf * cw; c_end = c_begin + cw; }
           else if (hf == 1) c_end = c_begin;                             // narrow slab: column half 0 does it all
-          if (L.kind == HID_SILU) hidden_slab<true>(lane_base, acc_col, L, ch.n0, c_begin, c_end);
-          else hidden_slab<false>(lane_base, acc_col, L, ch.n0, c_begin, c_end);
+          if (L.kind == HID_SILU) hidden_slab<true>(lane_base, acc_col, L, ch.n0, c_begin, c_end, p, tile_it, c, et == 0);
+          else hidden_slab<false>(lane_base, acc_col, L, ch.n0, c_begin, c_end, p, tile_it, c, et == 0);
           if (hf == 0 && ch.n0 + ch.nc == L.np && L.next_kp > L.np) {    // constant tail [np, next_kp): 1 at n_real, else 0
             for (int e0 = L.np; e0 < L.next_kp; e0 += 16) {
               uint32_t pk[8];
@@ -397,10 +482,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
           // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
           if (hf == 0) {
             uint32_t r[16]; tmem_ld16(lane_base + acc_col, r); tmem_ld_wait();
-            const int64_t id = valid ? (int64_t)p.ids[row] : 0;
             const float4 e4 = valid ? noise_get4(p.noise_p, id, 0, A) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-            for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - p.norm_mean[c]) / (p.norm_std[c] + 1e-6f);   // src/dynamics.py:113
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j < A) {
@@ -408,17 +491,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
 #pragma unroll
                 for (int k = 0; k < 16; ++k) { if (k == j) mu = __uint_as_float(r[k]); if (k == A + j) raw = __uint_as_float(r[k]); }
                 const float sd = __expf(-6.f + 10.f / (1.f + __expf(-raw)));
-                const float a = tanhf(fmaf(ev[j], sd, mu));
+                const float a = tanh_fast(fmaf(ev[j], sd, mu));
                 my_o[S + j] = a;
                 if (valid) p.actions[row * A + j] = a;
               }
             }
-            // model input x0 = [(s - mean)/(std + 1e-6), a, 1]                               src/dynamics.py:113-114
-            write_input_row(lane_base, (uint32_t)plan.layer[ch.layer + 1].a_col, my_o, S + A, plan.layer[ch.layer + 1].kp);
+            // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written during E0  (src/dynamics.py:113-114)
+            const int kpm = plan.layer[ch.layer + 1].kp;
+            write_input_row(lane_base, (uint32_t)plan.layer[ch.layer + 1].a_col, my_o, kpm, kpm);
           }
         } else if (L.kind == OUT_DIFF) {
           // ---- diff head: means = diffs + [s, 0]  (kept in shared memory)                   src/dynamics.py:118 ----
-          asm volatile("bar.sync 2, 256;" ::: "memory");                 // my_o (model input scratch) no longer read by row owner
           for (int c0 = 0; c0 < ch.nc; c0 += 16) {
             uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
 #pragma unroll
@@ -429,7 +512,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
           }
         } else {
           // ---- log-var head + Gaussian sample + hooks                                       src/dynamics.py:119-121,201-203 ----
-          const int64_t id = valid ? (int64_t)p.ids[row] : 0;
           for (int c0 = 0; c0 < ch.nc; c0 += 16) {
             uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
 #pragma unroll
@@ -442,14 +524,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
                 for (int k = 0; k < 4; ++k) {
                   const int cc = 4 * cg + k;
                   if (cc < O) {
-                    const float lv = soft_clamp(__uint_as_float(r[4 * jg + k]), p.min_lv[cc], p.max_lv[cc]);
-                    my_o[cc] = fmaf(sqrtf(__expf(lv)), ev[k], my_o[cc]);
+                    const float lv = soft_clamp_fast(__uint_as_float(r[4 * jg + k]), sl->min_lv[cc], sl->max_lv[cc]);
+                    my_o[cc] = fmaf(__expf(0.5f * lv), ev[k], my_o[cc]);          // sqrt(exp(lv)) = exp(lv/2)
                   }
                 }
               }
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");                 // both column halves of every row are in st_o
+          asm volatile("bar.sync 2, 256;" ::: "memory");                 // both column halves of every row are in st_o
           if (hf == 0 && valid) {
             HookOut ho;
             eval_hooks(p.env, [my_o](int d) { return my_o[d]; }, ho);
@@ -460,9 +542,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
             const int r = i / S, cc = i - r * S;
             p.next_states[row0 * S + i] = st_o[r * p.OP + cc];
           }
+          if (hf == 0) my_o[S + A] = 1.f;                                // restore the bias slot if the reward column overwrote it (A == 0 never)
         }
         tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->acc_free[b]);   // accumulator drained, activations visible
         if (et == 0) stamp(p, tile_it, c, 2);
+        acc_par[b] ^= 1u;
+        if (++b == NACC) b = 0;
       }
     }
   }
@@ -527,9 +612,10 @@ static int pack_net(const drpo_linear* lin, const LayerSpec* L, int count, uint8
 }
 
 static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP) {
-  SP = S | 1; OP = (S + 4 + 1) | 1;                        // st_o holds [norm s, a] and later [next state, reward]
+  SP = P.layer[0].kp | 1;                                  // state row [s, 1, 0..] padded to the first layer's K
+  OP = P.layer[3].kp | 1;                                  // [norm s, a, 1, 0..] padded to trunk0's K; later [next state, reward]
   const uint32_t slot = (P.max_chunk_bytes + 1023u) & ~1023u;
-  return (int)(slot * stages + (size_t)TILE_M * (SP + OP) * 4 + sizeof(SmemLayout) + 64);
+  return (int)(slot * stages + (size_t)TILE_M * (2 * SP + OP) * 4 + sizeof(SmemLayout) + 64);
 }
 
 }  // namespace umma

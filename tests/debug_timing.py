@@ -23,4 +23,5 @@ for tile in range(1, 3):
     print(" slab      mma_deps_ok weights_ok  issued | epi_wait_begin acc_ready epi_done")
     for c in range(27):
         r = st[tile, c] - t0
-        print(f" {c:2d} {names[c]:3s} {r[3]:10d} {r[4]:10d} {r[5]:8d} | {r[0]:12d} {r[1]:9d} {r[2]:8d}   (mma wait {r[1]-r[5]}, epi {r[2]-r[1]})")
+        inner = f" ld {r[6]-r[1]} math {r[7]-r[6]} st+arrive {r[2]-r[7]}" if c > 0 else ""
+        print(f" {c:2d} {names[c]:3s} {r[3]:10d} {r[4]:10d} {r[5]:8d} | {r[0]:12d} {r[1]:9d} {r[2]:8d}   (mma wait {r[1]-r[5]}, epi {r[2]-r[1]}{inner})")
