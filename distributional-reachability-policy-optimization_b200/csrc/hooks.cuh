@@ -47,27 +47,40 @@ __device__ __forceinline__ void eval_hooks(const drpo_env_params& p, Load s, Hoo
   } else if (p.kind == DRPO_ENV_BOUNDED) {
     // src/env/poles/constraints.py:203-204: x @ filter.T @ A.T - b with fp64 filter/A/b.  The 0/1 filter multiplies
     // EVERY state dim, so a non-finite value in another dim turns y into NaN (0*inf); we reproduce that.
+    // (loops are unrolled to their compile-time maxima with predicates so that yv[] / o.cv[] stay in registers)
     int n_nonfinite = 0;
     for (int d = 0; d < p.state_dim; ++d) n_nonfinite += !isfinite(s(d));
     double yv[DRPO_MAX_ACTIVE];
-    for (int a = 0; a < p.n_active; ++a) {
-      const float xa = s(p.active_dims[a]);
-      const int others = n_nonfinite - (!isfinite(xa) ? 1 : 0);
-      yv[a] = others > 0 ? (double)NAN : (double)xa;
+    const int na = p.n_active;
+#pragma unroll
+    for (int a = 0; a < DRPO_MAX_ACTIVE; ++a) {
+      yv[a] = 0.0;
+      if (a < na) {
+        const float xa = s(p.active_dims[a]);
+        const int others = n_nonfinite - (!isfinite(xa) ? 1 : 0);
+        yv[a] = others > 0 ? (double)NAN : (double)xa;
+      }
     }
     bool viol = false;
-    const int na = p.n_active;
-    for (int c = 0; c < 2 * na; ++c) {
-      // row c of A = [-I; I]; literal sum_a y[a]*A[c][a] so NaN/inf propagate exactly as in the matmul
-      double acc = 0.0;
-      for (int a = 0; a < na; ++a) {
-        const double coef = (c < na) ? ((a == c) ? -1.0 : 0.0) : ((a == c - na) ? 1.0 : 0.0);
-        acc = __dadd_rn(acc, __dmul_rn(yv[a], coef));
+#pragma unroll
+    for (int c = 0; c < 2 * DRPO_MAX_ACTIVE; ++c) {
+      if (c < 2 * na) {
+        // row c of A = [-I; I]; literal sum_a y[a]*A[c][a] so NaN/inf propagate exactly as in the matmul
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < DRPO_MAX_ACTIVE; ++a) {
+          if (a < na) {
+            const double coef = (c < na) ? ((a == c) ? -1.0 : 0.0) : ((a == c - na) ? 1.0 : 0.0);
+            acc = __dadd_rn(acc, __dmul_rn(yv[a], coef));
+          }
+        }
+        double bb = 0.0;
+#pragma unroll
+        for (int a = 0; a < DRPO_MAX_ACTIVE; ++a) { if (c < na && a == c) bb = -p.lower[a]; if (c >= na && a == c - na) bb = p.upper[a]; }
+        const double cv = __dsub_rn(acc, bb);
+        viol = viol || (cv > 0.0);
+        o.cv[c] = __double2float_rn(cv);
       }
-      const double bb = (c < na) ? -p.lower[c] : p.upper[c - na];
-      const double cv = __dsub_rn(acc, bb);
-      viol = viol || (cv > 0.0);
-      o.cv[c] = __double2float_rn(cv);
     }
     bool done = viol;                         // inverted_pendulum.py:79-82 ; quadrotor.py:112-114
     for (int j = 0; j < p.n_done_dims; ++j) {

@@ -3,16 +3,25 @@
 //   -> env hooks
 // chain for a 128-row tile without ever leaving the SM:
 //   * every dense layer is a sequence of tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M = 128 trajectories) issued per
-//     64-column output slab into one of three TMEM accumulator buffers, so the epilogue of slab j overlaps the MMAs of
-//     slab j+1 (and of the next independent layer);
+//     <=64-column output chunk into one of three TMEM accumulator buffers, so the epilogue of chunk j overlaps the MMAs of
+//     chunk j+1 (and of the next independent layer);
 //   * the activations live in TMEM too: the epilogue stores them as packed bf16 and the next layer reads its A operand
-//     straight from TMEM (TS-mode MMA) — activations never touch shared or global memory;
+//     straight from TMEM (TS-mode MMA) - activations never touch shared or global memory;
 //   * weights are packed once per rollout into the UMMA canonical K-major (no-swizzle) layout, one contiguous block per
-//     (layer, 64-row slab), and streamed from L2 into a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier);
+//     (layer, chunk), and streamed from L2 into a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier);
 //   * bias rides in the GEMM: every activation tile carries a constant-1 column and the packed weights hold the bias in
 //     the matching K slot; the epilogue is activation (packed bf16x2 math) + TMEM store only.
-// Warp roles: warps 0-7 = epilogue (warp w owns TMEM lanes 32*(w%4).. and column half w/4 of each slab),
-// warp 8 = TMA producer, warp 9 = MMA issuer (one elected thread) + TMEM allocator.
+// Warp roles (512 threads):
+//   warp 0     MMA issuer (one elected lane) + TMEM allocator; warp 1 TMA producer; warps 2-3 idle;
+//   warps 4-7  group C: the three narrow output chunks (policy head, diff head, log-var head), the Philox noise, the
+//              env hooks, the global stores, and the NEXT tile's prologue (state prefetch, normalisation, policy input),
+//              so that the tail of tile i overlaps the first policy layers of tile i+1;
+//   warps 8-11 hidden-layer epilogue group A, warps 12-15 group B: the 24 hidden-layer chunks of a tile alternate between
+//              the two groups, so the fixed latencies of one group's chunk (barrier wake-up, tcgen05.ld, tcgen05.st,
+//              fence) hide behind the other group's MUFU work.
+// Measured design inputs (tools/ubench_*.cu, profiles/): tcgen05.mma issues at the N/2-cycle hardware floor only from an
+// elect.sync branch (a `lane == 0` branch costs 63 cycles/MMA); tcgen05.ld moves ~3 KB/clk/SM; MUFU is 4 lanes/clk/SMSP and
+// tanh.approx.bf16x2 is two MUFU ops, which makes the SiLU epilogues MUFU-bound.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -27,18 +36,23 @@ namespace drpo {
 namespace umma {
 
 constexpr int TILE_M = 128;
-constexpr int NSLAB = 64;                  // output columns per slab / accumulator buffer
+constexpr int NSLAB = 64;                  // max output columns per chunk / accumulator buffer
 constexpr int NACC = 3;                    // accumulator buffers in TMEM
 constexpr int MAX_CHUNKS = 32;
 constexpr int MAX_LAYERS = 9;
-constexpr int EPI_THREADS = 256;
-constexpr int NUM_THREADS = EPI_THREADS + 64;
+constexpr int GROUP_THREADS = 128;         // one epilogue group = 4 warps = the 128 TMEM lanes
+constexpr int EPI_THREADS = 3 * GROUP_THREADS;      // groups C (output chunks, prologue, tail), A and B (hidden chunks)
+constexpr int NUM_THREADS = EPI_THREADS + 128;      // warp 0 MMA issuer, warp 1 TMA producer, warps 2-3 idle (keep the groups 4-aligned)
+constexpr int MMA_WARP = 0, PRODUCER_WARP = 1;
+constexpr int GROUP_C_WARP0 = 4, GROUP_A_WARP0 = 8; // a warp reaches TMEM lanes 32*(warp%4)..; the SM's arbiter prefers high warp ids
 constexpr int MAX_STAGES = 6;
+constexpr int NSPECIAL = 3;                // output chunks per tile: policy head, diff head, log-var head
 constexpr uint32_t TM_COLS = 512;
 // TMEM column map (32-bit columns; bf16 activations take kp/2 columns)
 constexpr uint32_t TM_ACC = 0;                                   // 3 x 64 fp32 accumulator columns
-constexpr uint32_t TM_PA = 192, TM_PB = 328, TM_XP = 464;        // policy: hidden A (<=136), hidden B (<=136), input (<=32)
+constexpr uint32_t TM_PA = 192, TM_PB = 328, TM_XP = 504;        // policy: hidden A (<=136), hidden B (<=136), input (8)
 constexpr uint32_t TM_H2 = 192, TM_D1 = 296, TM_L1 = 400;        // model: h2, h1/d1, x_m/l1 (<=104 each)
+// TM_XP is outside every model-phase region, so group C can stage tile i+1's policy input while tile i is in its model phase
 
 enum LayerKind { HID_RELU = 0, HID_SILU = 1, OUT_POLICY = 2, OUT_DIFF = 3, OUT_LOGVAR = 4 };
 
@@ -58,20 +72,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or ~10 ms pass) instead of
+// returning after a few dozen cycles.  Without the hint every waiting warp polls in a hot loop; the profile of the first
+// version of this kernel showed 40% of all issued instructions were such polls, issued by the highest-priority warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (fails the launch) instead of hanging the GPU
+// bounded wait: a protocol bug traps (fails the launch) after ~4 s of SM clocks instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
-  for (uint32_t it = 0; it < (1u << 22); ++it)
-    if (mbar_try_wait(bar, parity)) return;
-  if (err_flag) atomicExch(err_flag, code);
-  __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+#pragma unroll 1
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) {
+      if (err_flag) atomicExch(err_flag, code);
+      __trap();
+    }
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one elected lane of a converged warp: unlike `lane == 0`, the compiler knows the branch is single-threaded, keeps the
+// tcgen05.mma operands in uniform registers and emits back-to-back UTCHMMA (measured: 9-32 cycles/MMA instead of 63)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred;
+}
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -137,6 +166,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // packed bf16x2 math for the epilogues (element 2j in the low half, 2j+1 in the high half)
@@ -185,25 +219,33 @@ struct LayerSpec {
   int dep;                 // layer whose epilogue must be complete before this layer's MMAs may read a_col (-1: tile input)
   int next_kp;             // K (padded) of the consumer of out_col
 };
-struct ChunkSpec { uint32_t offset, bytes; uint16_t n0, nc; uint16_t layer, pad; };     // byte offset inside the net image
+// One MMA group: output columns [n0, n0+nc) of a layer, accumulated into TMEM buffer (chunk index % NACC).
+// special = -1 for hidden-layer chunks (epilogue groups A/B, `hid` = ordinal among the tile's hidden chunks), else the
+// index of the group-C barrier pair (0 policy head, 1 diff head, 2 log-var head).
+struct ChunkSpec { uint32_t offset, bytes; uint16_t n0, nc; uint16_t layer; int8_t special; uint8_t hid; };
 struct NetPlan {
   LayerSpec layer[MAX_LAYERS];
   ChunkSpec chunk[MAX_CHUNKS];
   int n_layers, n_chunks;
-  uint32_t policy_bytes, model_bytes;     // image sizes; policy slabs index the actor image, model slabs the member image
+  uint32_t policy_bytes, model_bytes;     // image sizes; policy chunks index the actor image, model chunks the member image
   int n_policy_chunks;
   uint32_t max_chunk_bytes;
 };
 
+// Weight image of one layer: per chunk a contiguous block in the canonical K-major layout [n/8][k/8][8 rows][8 elems];
+// column kp-? : the bias sits in K slot k_real (the activations carry a constant 1 there).
+struct PackChunks { int n; int n0[5]; };      // chunk boundaries n0[0..n]
 __global__ void pack_layer_kernel(const float* __restrict__ W, const float* __restrict__ b, int n_real, int k_real, int np, int kp,
-                                  __nv_bfloat16* __restrict__ dst /* start of this layer inside the image */) {
+                                  PackChunks pc, __nv_bfloat16* __restrict__ dst /* start of this layer inside the image */) {
   const int total = np * kp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i / kp, k = i % kp;
     float v = 0.f;
     if (n < n_real) v = k < k_real ? W[(int64_t)n * k_real + k] : (k == k_real ? b[n] : 0.f);
-    const int slab = n / NSLAB, nin = n - slab * NSLAB;
-    const int64_t idx = (int64_t)slab * NSLAB * kp + ((int64_t)(nin >> 3) * (kp >> 3) + (k >> 3)) * 64 + (nin & 7) * 8 + (k & 7);
+    int ci = 0;
+    while (ci + 1 < pc.n && n >= pc.n0[ci + 1]) ++ci;
+    const int nin = n - pc.n0[ci];
+    const int64_t idx = (int64_t)pc.n0[ci] * kp + ((int64_t)(nin >> 3) * (kp >> 3) + (k >> 3)) * 64 + (nin & 7) * 8 + (k & 7);
     dst[idx] = __float2bfloat16_rn(v);
   }
 }
@@ -219,125 +261,129 @@ struct StepParams {
   const float *norm_mean, *norm_std, *min_lv, *max_lv;
   NoiseView noise_p, noise_m;
   drpo_env_params env;
-  int S, A, C, SP, OP, stages;
+  int S, A, C, SP, OP, NM, stages;
   int* err_flag;
   int dump_layer; float* dump_out;       // debug: dump the fp32 accumulator of one layer
 };
 
 struct SmemLayout {
-  uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_free[NACC], tile_ready;
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_free[NACC], sp_full[NSPECIAL], sp_free[NSPECIAL], tile_ready;
   uint32_t tmem_base, pad;
-  float norm_mean[64], norm_inv[64], min_lv[64], max_lv[64];     // per-dim constants of the member, staged once per CTA
+  // per-dim constants of the member, staged once per CTA: normaliser, and the log-var soft clamp folded into
+  //   std = exp(lv/2) = s0 * sqrt(1 + E / (1 + exp(hi - x)))   with s0 = exp(lo/2), E = exp(hi - lo)      (src/dynamics.py:120-121,201)
+  float norm_mean[64], norm_inv[64], lv_hi[64], lv_E[64], lv_s0[64];
 };
 
 // debug timing (dump_layer == 100): CTA 0 stamps clock() for its first 4 tiles into dump_out viewed as uint32
-// [(tile*32 + slab)*8 + k], k: 0 epi wait begin, 1 accumulator ready, 2 epilogue done, 3 mma deps ok, 4 weights ready,
-// 5 mma issued, 6 E0 begin, 7 E0 end
-__device__ __forceinline__ void stamp(const StepParams& p, uint32_t tile_it, int slab, int k) {
+// [(tile*32 + chunk)*8 + k], k: 0 epilogue wait begin, 1 accumulator ready, 2 epilogue done, 3 mma deps ok, 4 weights ready,
+// 5 mma issued, 6 tile prologue begin (chunk 0 only), 7 tile prologue end
+__device__ __forceinline__ void stamp(const StepParams& p, uint32_t tile_it, int chunk, int k) {
   if (p.dump_layer == 100 && blockIdx.x == 0 && tile_it < 4)
-    reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + slab) * 8 + k] = (uint32_t)clock();
+    reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + chunk) * 8 + k] = (uint32_t)clock();
 }
 
 // write one input row (k_real values + constant 1) as packed bf16 into a TMEM activation buffer
-__device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col, const float* row, int k_real, int kp) {
+__device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col, const float* row, int kp) {
   for (int e0 = 0; e0 < kp; e0 += 16) {
     uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int a = e0 + 2 * j, b = a + 1;
-      pk[j] = pack_bf16(row[a], row[b]);          // rows are staged with their [.., 1, 0, ..] tail up to kp
-    }
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(row[e0 + 2 * j], row[e0 + 2 * j + 1]);    // rows are staged with their [.., 1, 0, ..] tail up to kp
     tmem_st8(lane_base + col + (uint32_t)(e0 >> 1), pk);
   }
 }
 
-// epilogue of one slab of a hidden layer: ACC[acc_col + (c - n0)] -> activation -> packed bf16 -> TMEM out_col + c/2
+// 16 accumulator columns -> activation -> 8 packed bf16x2 words; `one` = element of this piece that must read 1.0 (the bias
+// slot of the consumer layer) or anything outside [0,16)
 template <bool kSilu>
-__device__ __forceinline__ void hidden_slab32(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int c0,
-                                              const StepParams& p, uint32_t tile_it, int slab, bool do_stamp) {
-  uint32_t r[32];
-  tmem_ld32(lane_base + acc_col + (uint32_t)(c0 - n0), r);
+__device__ __forceinline__ void act_pack16(const uint32_t (&r)[16], uint32_t (&pk)[8], int one) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t x = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    pk[j] = kSilu ? silu_bf16x2(x) : relu_bf16x2(x);
+  }
+  if (one >= 0 && one < 16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (one == 2 * j) pk[j] = (pk[j] & 0xFFFF0000u) | 0x00003F80u;
+      if (one == 2 * j + 1) pk[j] = (pk[j] & 0x0000FFFFu) | 0x3F800000u;
+    }
+  }
+}
+
+// epilogue of one chunk (nc = 16, 32, 48 or 64 columns) of a hidden layer for one row:
+// ACC[acc_col + j] -> activation -> packed bf16 -> TMEM out_col + (n0 + j)/2.  All loads are issued before the single wait.
+template <bool kSilu>
+__device__ __forceinline__ void hidden_chunk(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int nc) {
+  uint32_t ra[16], rb[16], rc[16], rd[16];
+  const uint32_t src = lane_base + acc_col;
+  tmem_ld16(src, ra);
+  if (nc > 16) tmem_ld16(src + 16, rb);
+  if (nc > 32) tmem_ld16(src + 32, rc);
+  if (nc > 48) tmem_ld16(src + 48, rd);
   tmem_ld_wait();
-  if (do_stamp && slab > 0) stamp(p, tile_it, slab, 6);
+  const int one = L.n_real - n0;                       // position of the consumer's bias slot relative to this chunk
+  const uint32_t dst = lane_base + (uint32_t)L.out_col + (uint32_t)(n0 >> 1);
+  uint32_t pk[8];
+  act_pack16<kSilu>(ra, pk, one);
+  tmem_st8(dst, pk);
+  if (nc > 16) { act_pack16<kSilu>(rb, pk, one - 16); tmem_st8(dst + 8, pk); }
+  if (nc > 32) { act_pack16<kSilu>(rc, pk, one - 32); tmem_st8(dst + 16, pk); }
+  if (nc > 48) { act_pack16<kSilu>(rd, pk, one - 48); tmem_st8(dst + 24, pk); }
+  if (n0 + nc == L.np && L.next_kp > L.np) {             // constant tail [np, next_kp): 1 at n_real, else 0
+    for (int e0 = L.np; e0 < L.next_kp; e0 += 16) {
+      uint32_t t8[8];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t x = pack_bf16(__uint_as_float(r[16 * h + 2 * j]), __uint_as_float(r[16 * h + 2 * j + 1]));
-      pk[j] = kSilu ? silu_bf16x2(x) : relu_bf16x2(x);
+      for (int j = 0; j < 8; ++j) t8[j] = pack_bf16((e0 + 2 * j) == L.n_real ? 1.f : 0.f, (e0 + 2 * j + 1) == L.n_real ? 1.f : 0.f);
+      tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(e0 >> 1), t8);
     }
-    const int cb = c0 + 16 * h;
-    if (L.n_real >= cb && L.n_real < cb + 16) {
-      const int e = L.n_real - cb;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j == (e >> 1)) pk[j] = (e & 1) ? ((pk[j] & 0x0000FFFFu) | 0x3F800000u) : ((pk[j] & 0xFFFF0000u) | 0x00003F80u);
-    }
-    tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(cb >> 1), pk);
-  }
-  if (do_stamp && slab > 0) stamp(p, tile_it, slab, 7);
-}
-template <bool kSilu>
-__device__ __forceinline__ void hidden_slab(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int c_begin, int c_end,
-                                            const StepParams& p, uint32_t tile_it, int slab, bool do_stamp) {
-  if (c_end - c_begin == 32) { hidden_slab32<kSilu>(lane_base, acc_col, L, n0, c_begin, p, tile_it, slab, do_stamp); return; }
-  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld16(lane_base + acc_col + (uint32_t)(c0 - n0), r);
-    tmem_ld_wait();
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t x = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-      pk[j] = kSilu ? silu_bf16x2(x) : relu_bf16x2(x);
-    }
-    if (L.n_real >= c0 && L.n_real < c0 + 16) {                 // constant-1 column = bias slot of the consumer
-      const int e = L.n_real - c0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j == (e >> 1)) pk[j] = (e & 1) ? ((pk[j] & 0x0000FFFFu) | 0x3F800000u) : ((pk[j] & 0xFFFF0000u) | 0x00003F80u);
-    }
-    tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(c0 >> 1), pk);
   }
 }
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const NetPlan& plan = p.plan;
-  // shared memory: [weight ring | state tile | out tile | barriers]
+  // shared memory: [weight ring | raw states x2 | model input / next state rows x2 | policy noise | model noise | barriers, constants]
   uint8_t* ring = smem_raw;
   const uint32_t slot_bytes = (plan.max_chunk_bytes + 1023u) & ~1023u;
-  float* st_s = reinterpret_cast<float*>(ring + (size_t)slot_bytes * p.stages);      // [2][128][SP] states (fp32), double-buffered
-  float* st_o = st_s + 2 * TILE_M * p.SP;                                            // [128][OP] model input row / next state row
-  SmemLayout* sl = reinterpret_cast<SmemLayout*>(st_o + TILE_M * p.OP);
+  float* st_s = reinterpret_cast<float*>(ring + (size_t)slot_bytes * p.stages);      // [2][128][SP] raw states (fp32)
+  float* st_o = st_s + 2 * TILE_M * p.SP;                                            // [2][128][OP] [norm s, a, 1, 0..] then [next state, reward]
+  float* st_np = st_o + 2 * TILE_M * p.OP;                                           // [128][4]  policy noise of the tile in its policy phase
+  float* st_nm = st_np + TILE_M * 4;                                                 // [128][NM] model noise of the tile in its model phase
+  SmemLayout* sl = reinterpret_cast<SmemLayout*>(st_nm + TILE_M * p.NM);
 
   const int n = (int)min((int64_t)*p.n_dev, p.n_max);
   const int n_tiles = (n + TILE_M - 1) / TILE_M;
+  const int S = p.S, A = p.A, O = S + 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&sl->full[s], 1); mbar_init(&sl->empty[s], 1); }
-    for (int b = 0; b < NACC; ++b) { mbar_init(&sl->acc_full[b], 1); mbar_init(&sl->acc_free[b], EPI_THREADS); }
-    mbar_init(&sl->tile_ready, EPI_THREADS);
+    for (int b = 0; b < NACC; ++b) { mbar_init(&sl->acc_full[b], 1); mbar_init(&sl->acc_free[b], GROUP_THREADS); }
+    for (int k = 0; k < NSPECIAL; ++k) { mbar_init(&sl->sp_full[k], 1); mbar_init(&sl->sp_free[k], GROUP_THREADS); }
+    mbar_init(&sl->tile_ready, GROUP_THREADS);
     fence_barrier_init();
   }
-  if (threadIdx.x < EPI_THREADS) {
+  if (threadIdx.x >= NUM_THREADS - EPI_THREADS) {
     // constants + the constant tails of the staging rows: [.., 1, 0, 0 ..] = bias slot and K padding of the two input layers
-    const int et0 = threadIdx.x;
-    if (et0 < p.S) { sl->norm_mean[et0] = p.norm_mean[et0]; sl->norm_inv[et0] = 1.f / (p.norm_std[et0] + 1e-6f); }
-    if (et0 <= p.S) { sl->min_lv[et0] = p.min_lv[et0]; sl->max_lv[et0] = p.max_lv[et0]; }
-    for (int i = et0; i < 2 * TILE_M * p.SP; i += EPI_THREADS) { const int c = i % p.SP; st_s[i] = c == p.S ? 1.f : 0.f; }
-    for (int i = et0; i < TILE_M * p.OP; i += EPI_THREADS) { const int c = i % p.OP; st_o[i] = c == p.S + p.A ? 1.f : 0.f; }
+    const int et0 = threadIdx.x - (NUM_THREADS - EPI_THREADS);
+    if (et0 < S) { sl->norm_mean[et0] = p.norm_mean[et0]; sl->norm_inv[et0] = 1.f / (p.norm_std[et0] + 1e-6f); }
+    if (et0 <= S) {
+      const float lo = p.min_lv[et0], hi = p.max_lv[et0];
+      sl->lv_hi[et0] = hi; sl->lv_E[et0] = __expf(hi - lo); sl->lv_s0[et0] = __expf(0.5f * lo);
+    }
+    for (int i = et0; i < 2 * TILE_M * p.SP; i += EPI_THREADS) { const int c = i % p.SP; st_s[i] = c == S ? 1.f : 0.f; }
+    for (int i = et0; i < 2 * TILE_M * p.OP; i += EPI_THREADS) { const int c = i % p.OP; st_o[i] = c == S + A ? 1.f : 0.f; }
   }
-  if (warp == 9) tmem_alloc(&sl->tmem_base, TM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(&sl->tmem_base, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sl->tmem_base;
 
-  if (warp == 8) {
-    // ===================== TMA producer: stream every weight slab of every tile through the ring =====================
+  if (warp == PRODUCER_WARP) {
+    // ===================== TMA producer: stream every weight chunk of every tile through the ring =====================
     if (lane == 0) {
       int s = 0; uint32_t round = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -351,40 +397,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // Per-buffer use counters replace every div/mod: slab g lives in accumulator buffer b = g % NACC as its use[b]-th use.
+    if (elect_one()) {
       int s = 0; uint32_t ring_par = 0;      // weight ring slot + parity of its current use
-      int b = 0;                             // accumulator buffer of the next slab
-      uint32_t use[NACC] = {0, 0, 0};        // number of slabs issued into each accumulator buffer so far
-      uint32_t seen[NACC] = {0, 0, 0};       // number of epilogue completions already observed per buffer
+      // accumulator buffer b = chunk index % NACC (n_chunks is a multiple of NACC).  owner[b]: who drains the buffer's current
+      // contents (-1 nobody yet, 0 a hidden group via acc_free[b], 1+k group C via sp_free[k]).  commits/seen count the
+      // phases of each "free" barrier that were started / already observed by this thread (at most one outstanding).
+      int owner[NACC] = {-1, -1, -1};
+      uint32_t hid_commits[NACC] = {0, 0, 0}, hid_seen[NACC] = {0, 0, 0};
+      uint32_t sp_commits[NSPECIAL] = {0, 0, 0}, sp_seen[NSPECIAL] = {0, 0, 0};
+      auto ensure_drained = [&](int b, int code) {
+        // unrolled selects keep the small state arrays in registers
+#pragma unroll
+        for (int bb = 0; bb < NACC; ++bb) {
+          if (bb != b) continue;
+          if (owner[bb] == 0) {
+            if (hid_seen[bb] < hid_commits[bb]) { mbar_wait(&sl->acc_free[bb], (hid_commits[bb] - 1) & 1, p.err_flag, code); hid_seen[bb] = hid_commits[bb]; tc_fence_after(); }
+          } else if (owner[bb] > 0) {
+#pragma unroll
+            for (int k = 0; k < NSPECIAL; ++k)
+              if (owner[bb] == 1 + k && sp_seen[k] < sp_commits[k]) { mbar_wait(&sl->sp_free[k], (sp_commits[k] - 1) & 1, p.err_flag, code); sp_seen[k] = sp_commits[k]; tc_fence_after(); }
+          }
+        }
+      };
       uint32_t tile_it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
         mbar_wait(&sl->tile_ready, tile_it & 1, p.err_flag, 2);
         tc_fence_after();
-        int c_abs = 0;                       // slab index inside the tile
+        int c_abs = 0, b = 0;
         for (int l = 0; l < plan.n_layers; ++l) {
           const LayerSpec& L = plan.layer[l];
           if (L.dep >= 0) {
-            // A operand = output of layer dep: its LAST slab must be through the epilogue.  That slab was issued
-            // (c_abs - last) slabs ago; if that is within the last NACC slabs its buffer has not been reused and we can
-            // wait on it, otherwise a later reuse of the buffer already proved it complete.
+            // A operand = output of layer dep: its chunks must be through their epilogues.  The two hidden groups finish out
+            // of order, so the last TWO chunks are checked; older ones precede them in their group's program order.  A chunk
+            // issued more than NACC chunks ago was already proven drained when its buffer was reused.
             const int last = plan.layer[L.dep].first_chunk + plan.layer[L.dep].n_chunks - 1;
-            const int back = c_abs - last;                       // >= 1
-            if (back <= NACC) {
-              int bb = b - back; if (bb < 0) bb += NACC;
-              if (seen[bb] < use[bb]) { mbar_wait(&sl->acc_free[bb], (use[bb] - 1) & 1, p.err_flag, 5); seen[bb] = use[bb]; tc_fence_after(); }
-            }
+            for (int cd = last; cd >= plan.layer[L.dep].first_chunk && cd >= last - 1; --cd)
+              if (c_abs - cd <= NACC) ensure_drained(cd % NACC, 5);
           }
           const uint32_t sbo = (uint32_t)(L.kp >> 3) * 128u;
           const int nk = L.kp >> 4;
           for (int c = 0; c < L.n_chunks; ++c, ++c_abs) {
             const ChunkSpec& ch = plan.chunk[L.first_chunk + c];
-            if (seen[b] < use[b]) {                                      // accumulator buffer still being drained?
-              mbar_wait(&sl->acc_free[b], (use[b] - 1) & 1, p.err_flag, 6);
-              seen[b] = use[b]; tc_fence_after();
-            }
+            ensure_drained(b, 6);                                         // accumulator buffer still being read by its last user?
             stamp(p, tile_it, c_abs, 3);
             mbar_wait(&sl->full[s], ring_par, p.err_flag, 3);
             tc_fence_after();
@@ -402,104 +458,172 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
               mma_ts<true>(d_addr, a_addr, desc_lo, desc_hi, idesc);
             }
             tc_commit(&sl->empty[s]);                                    // frees the ring slot when these MMAs retire
-            tc_commit(&sl->acc_full[b]);                                 // slab accumulator complete -> epilogue
+            const int sp = ch.special;
+#pragma unroll
+            for (int bb = 0; bb < NACC; ++bb) {
+              if (bb != b) continue;
+              if (sp < 0) { tc_commit(&sl->acc_full[bb]); ++hid_commits[bb]; owner[bb] = 0; }
+              else {
+                owner[bb] = 1 + sp;
+#pragma unroll
+                for (int k = 0; k < NSPECIAL; ++k) if (k == sp) { tc_commit(&sl->sp_full[k]); ++sp_commits[k]; }
+              }
+            }
             stamp(p, tile_it, c_abs, 5);
-            ++use[b];
             if (++b == NACC) b = 0;
             if (++s == p.stages) { s = 0; ring_par ^= 1u; }
           }
         }
       }
     }
-  } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3, hf = warp >> 2;
-    const int t = q * 32 + lane;                                          // trajectory row of the tile == TMEM lane
-    const int et = threadIdx.x;                                           // 0..255
+  } else if (warp >= GROUP_A_WARP0) {
+    // ===================== hidden-layer epilogue groups A (warps 8-11) and B (warps 12-15) =====================
+    const int grp = (warp - GROUP_A_WARP0) >> 2, q = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    const int S = p.S, A = p.A, O = S + 1;
-    float* my_o = st_o + t * p.OP;
-    // prefetch the first tile's states (cp.async, 4 B granules into the padded rows)
-    auto prefetch = [&](int tile, int buf) {
+    const bool lead = (threadIdx.x & (GROUP_THREADS - 1)) == 0;
+    uint32_t acc_par[NACC] = {0, 0, 0};
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      const int64_t row0 = (int64_t)tile * TILE_M;
+      const int t = q * 32 + lane;
+      const bool valid = t < n - (int)row0;
+      int b = 0;
+      for (int c = 0; c < plan.n_chunks; ++c) {
+        const ChunkSpec& ch = plan.chunk[c];
+        if (ch.special < 0) {
+          const bool mine = (ch.hid & 1) == grp;
+          if (mine && lead) stamp(p, tile_it, c, 0);
+          // Both groups observe EVERY phase of acc_full[b], their own chunks and the other group's: a parity wait is only
+          // sound when the waiter is at most one phase behind.  (The other group's chunk was issued before this group's next
+          // one, so this never delays useful work.)
+#pragma unroll
+          for (int bb = 0; bb < NACC; ++bb) if (bb == b) mbar_wait(&sl->acc_full[bb], acc_par[bb], p.err_flag, 4);
+          if (mine) {
+            const LayerSpec& L = plan.layer[ch.layer];
+            const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
+            tc_fence_after();
+            if (lead) stamp(p, tile_it, c, 1);
+            if (p.dump_layer == (int)ch.layer) {                          // debug hook: raw accumulator to global
+              for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+                uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
+                if (valid) for (int j = 0; j < 16; ++j) if (ch.n0 + c0 + j < L.n_real) p.dump_out[(row0 + t) * L.n_real + ch.n0 + c0 + j] = __uint_as_float(r[j]);
+              }
+            }
+            if (L.kind == HID_SILU) hidden_chunk<true>(lane_base, acc_col, L, ch.n0, ch.nc);
+            else hidden_chunk<false>(lane_base, acc_col, L, ch.n0, ch.nc);
+            tmem_st_wait(); tc_fence_before();
+#pragma unroll
+            for (int bb = 0; bb < NACC; ++bb) if (bb == b) mbar_arrive(&sl->acc_free[bb]);   // accumulator drained, activations visible
+            if (lead) stamp(p, tile_it, c, 2);
+          }
+#pragma unroll
+          for (int bb = 0; bb < NACC; ++bb) if (bb == b) acc_par[bb] ^= 1u;      // every hidden commit into b flips its phase, mine or not
+        }
+        if (++b == NACC) b = 0;
+      }
+    }
+  } else if (warp >= GROUP_C_WARP0) {
+    // ===================== group C (warps 4-7): output chunks, noise, hooks, stores, next tile's prologue =====================
+    const int q = warp & 3;
+    const int t = q * 32 + lane;                                          // trajectory row of the tile == TMEM lane
+    const int ct = threadIdx.x - GROUP_C_WARP0 * 32;                      // 0..127
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const int kp0 = plan.layer[0].kp;
+    const int first_model = plan.n_policy_chunks;                        // chunk index of trunk0's first chunk; layer index = that chunk's layer
+    const int kpm = plan.layer[plan.chunk[first_model].layer].kp;
+    const uint32_t xm_col = (uint32_t)plan.layer[plan.chunk[first_model].layer].a_col;
+    const uint32_t xp_col = (uint32_t)plan.layer[0].a_col;
+    // The policy input of tile i+1 is staged while tile i is still in its model phase when it fits the 8 spare TMEM columns
+    // (state_dim <= 15); wider inputs share columns with the log-var head's activations and are staged once those are dead.
+    const bool early_prologue = xp_col == TM_XP;
+
+    auto prefetch = [&](int tile, int buf) {                              // cp.async, 4 B granules into the padded rows
       const int64_t r0 = (int64_t)tile * TILE_M;
       const int rws = min(TILE_M, n - (int)r0);
       float* dst = st_s + buf * TILE_M * p.SP;
-      for (int i = et; i < rws * S; i += EPI_THREADS) { const int r = i / S, c = i - r * S; cp_async4(dst + r * p.SP + c, p.cur + r0 * S + i); }
+      for (int i = ct; i < rws * S; i += GROUP_THREADS) { const int r = i / S, c = i - r * S; cp_async4(dst + r * p.SP + c, p.cur + r0 * S + i); }
       cp_async_commit();
     };
-    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
+    // tile prologue: policy input [s, 1] -> TMEM, normalised state -> model-input row, policy noise -> smem
+    auto prologue = [&](int tile, int buf, uint32_t tile_it) {
+      if (ct == 0) stamp(p, tile_it, 0, 6);
+      cp_async_wait_all();
+      named_bar_sync(1, GROUP_THREADS);                                   // the tile's states landed (all of group C's copies)
+      const int rows = min(TILE_M, n - tile * TILE_M);
+      const float* my_s = st_s + buf * TILE_M * p.SP + t * p.SP;
+      float* my_o = st_o + buf * TILE_M * p.OP + t * p.OP;
+      write_input_row(lane_base, xp_col, my_s, kp0);
+      for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - sl->norm_mean[c]) * sl->norm_inv[c];          // src/dynamics.py:113
+      const int64_t id = t < rows ? (int64_t)p.ids[(int64_t)tile * TILE_M + t] : 0;
+      const float4 e4 = t < rows ? noise_get4(p.noise_p, id, 0, A) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(st_np + t * 4) = e4;
+      tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->tile_ready);
+      if (ct == 0) stamp(p, tile_it, 0, 7);
+    };
+
+    if ((int)blockIdx.x < n_tiles) { prefetch(blockIdx.x, 0); prologue(blockIdx.x, 0, 0); }
     uint32_t tile_it = 0;
-    int b = 0; uint32_t acc_par[NACC] = {0, 0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      const int buf = tile_it & 1;
       const int64_t row0 = (int64_t)tile * TILE_M;
       const int rows = min(TILE_M, n - (int)row0);
       const bool valid = t < rows;
       const int64_t row = row0 + t;
-      const int64_t id = valid ? (int64_t)p.ids[row] : 0;                // global trajectory id (noise key), fetched early
-      float* my_s = st_s + (tile_it & 1) * TILE_M * p.SP + t * p.SP;
-      // ---- E0: this tile's states have been prefetched; write the policy input [s, 1] into TMEM, normalise for the model ----
-      if (et == 0) stamp(p, tile_it, 0, 6);
-      cp_async_wait_all();
-      asm volatile("bar.sync 1, 256;" ::: "memory");                     // states landed; previous tile's readers of st_o are done
-      if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, (tile_it + 1) & 1);
-      if (hf == 0) {
-        write_input_row(lane_base, (uint32_t)plan.layer[0].a_col, my_s, plan.layer[0].kp, plan.layer[0].kp);
-      } else {
-        for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - sl->norm_mean[c]) * sl->norm_inv[c];          // src/dynamics.py:113
-      }
-      tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->tile_ready);
-      if (et == 0) stamp(p, tile_it, 0, 7);
-
-      for (int c = 0; c < plan.n_chunks; ++c) {
+      const int64_t id = valid ? (int64_t)p.ids[row] : 0;                // global trajectory id (noise key)
+      const float* my_s = st_s + buf * TILE_M * p.SP + t * p.SP;
+      float* my_o = st_o + buf * TILE_M * p.OP + t * p.OP;
+      const int next_tile = tile + (int)gridDim.x;
+      if (next_tile < n_tiles) prefetch(next_tile, buf ^ 1);            // buffer buf^1 was last read by the previous tile's diff-head epilogue
+      const uint32_t par = tile_it & 1;
+      int b = 0;
+      for (int c = 0; c < plan.n_chunks; ++c, b = (b + 1 == NACC ? 0 : b + 1)) {
         const ChunkSpec& ch = plan.chunk[c];
+        if (ch.special < 0) continue;
         const LayerSpec& L = plan.layer[ch.layer];
         const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
-        if (et == 0) stamp(p, tile_it, c, 0);
-        mbar_wait(&sl->acc_full[b], acc_par[b], p.err_flag, 4);
+        const int sp = ch.special;
+        if (ct == 0) stamp(p, tile_it, c, 0);
+        mbar_wait(&sl->sp_full[sp], par, p.err_flag, 7);
         tc_fence_after();
-        if (et == 0) stamp(p, tile_it, c, 1);
-        if (p.dump_layer == (int)ch.layer && hf == 0) {                  // debug hook: raw accumulator to global
+        if (ct == 0) stamp(p, tile_it, c, 1);
+        if (p.dump_layer == (int)ch.layer) {                              // debug hook: raw accumulator to global
           for (int c0 = 0; c0 < ch.nc; c0 += 16) {
             uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
             if (valid) for (int j = 0; j < 16; ++j) if (ch.n0 + c0 + j < L.n_real) p.dump_out[row * L.n_real + ch.n0 + c0 + j] = __uint_as_float(r[j]);
           }
         }
-        if (L.kind == HID_RELU || L.kind == HID_SILU) {
-          int c_begin = ch.n0, c_end = ch.n0 + ch.nc;
-          if ((ch.nc & 31) == 0) { const int cw = ch.nc >> 1; c_begin += hf * cw; c_end = c_begin + cw; }
-          else if (hf == 1) c_end = c_begin;                             // narrow slab: column half 0 does it all
-          if (L.kind == HID_SILU) hidden_slab<true>(lane_base, acc_col, L, ch.n0, c_begin, c_end, p, tile_it, c, et == 0);
-          else hidden_slab<false>(lane_base, acc_col, L, ch.n0, c_begin, c_end, p, tile_it, c, et == 0);
-          if (hf == 0 && ch.n0 + ch.nc == L.np && L.next_kp > L.np) {    // constant tail [np, next_kp): 1 at n_real, else 0
-            for (int e0 = L.np; e0 < L.next_kp; e0 += 16) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) pk[j] = pack_bf16((e0 + 2 * j) == L.n_real ? 1.f : 0.f, (e0 + 2 * j + 1) == L.n_real ? 1.f : 0.f);
-              tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(e0 >> 1), pk);
-            }
-          }
-        } else if (L.kind == OUT_POLICY) {
+        if (L.kind == OUT_POLICY) {
           // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
-          if (hf == 0) {
-            uint32_t r[16]; tmem_ld16(lane_base + acc_col, r); tmem_ld_wait();
-            const float4 e4 = valid ? noise_get4(p.noise_p, id, 0, A) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+          uint32_t r[16]; tmem_ld16(lane_base + acc_col, r); tmem_ld_wait();
+          const float4 e4 = *reinterpret_cast<const float4*>(st_np + t * 4);
+          const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+          const float mu4[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
+          float raw4[4] = {0.f, 0.f, 0.f, 0.f};                            // raw_j = out[A + j], statically indexed per A
+          if (A == 1) { raw4[0] = __uint_as_float(r[1]); }
+          else if (A == 2) { raw4[0] = __uint_as_float(r[2]); raw4[1] = __uint_as_float(r[3]); }
+          else if (A == 3) { raw4[0] = __uint_as_float(r[3]); raw4[1] = __uint_as_float(r[4]); raw4[2] = __uint_as_float(r[5]); }
+          else { raw4[0] = __uint_as_float(r[4]); raw4[1] = __uint_as_float(r[5]); raw4[2] = __uint_as_float(r[6]); raw4[3] = __uint_as_float(r[7]); }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < A) {
-                float mu = 0.f, raw = 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) { if (k == j) mu = __uint_as_float(r[k]); if (k == A + j) raw = __uint_as_float(r[k]); }
-                const float sd = __expf(-6.f + 10.f / (1.f + __expf(-raw)));
-                const float a = tanh_fast(fmaf(ev[j], sd, mu));
-                my_o[S + j] = a;
-                if (valid) p.actions[row * A + j] = a;
-              }
+          for (int j = 0; j < 4; ++j) {
+            if (j < A) {
+              const float sd = __expf(-6.f + __fdividef(10.f, 1.f + __expf(-raw4[j])));
+              const float a = tanh_fast(fmaf(ev[j], sd, mu4[j]));
+              my_o[S + j] = a;
+              if (valid) p.actions[row * A + j] = a;
             }
-            // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written during E0  (src/dynamics.py:113-114)
-            const int kpm = plan.layer[ch.layer + 1].kp;
-            write_input_row(lane_base, (uint32_t)plan.layer[ch.layer + 1].a_col, my_o, kpm, kpm);
           }
+          // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written by the prologue  (src/dynamics.py:113-114)
+          write_input_row(lane_base, xm_col, my_o, kpm);
+          tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
+          if (ct == 0) stamp(p, tile_it, c, 2);
+          // ---- off the critical path: this tile's model noise, then the next tile's prologue ----
+          if (p.NM > 0) {
+            for (int cg = 0; 4 * cg < O; ++cg) {
+              const float4 m4 = valid ? noise_get4(p.noise_m, id, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(st_nm + t * p.NM + 4 * cg) = m4;
+            }
+          }
+          if (early_prologue && next_tile < n_tiles) prologue(next_tile, buf ^ 1, tile_it + 1);
         } else if (L.kind == OUT_DIFF) {
           // ---- diff head: means = diffs + [s, 0]  (kept in shared memory)                   src/dynamics.py:118 ----
           for (int c0 = 0; c0 < ch.nc; c0 += 16) {
@@ -507,70 +631,84 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int cc = c0 + j;
-              if (cc < O && ((cc >> 2) & 1) == hf) my_o[cc] = __uint_as_float(r[j]) + (cc < S ? my_s[cc] : 0.f);
+              if (cc < O) my_o[cc] = __uint_as_float(r[j]) + (cc < S ? my_s[cc] : 0.f);
             }
           }
+          tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
+          if (ct == 0) stamp(p, tile_it, c, 2);
         } else {
           // ---- log-var head + Gaussian sample + hooks                                       src/dynamics.py:119-121,201-203 ----
           for (int c0 = 0; c0 < ch.nc; c0 += 16) {
             uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
+            if (c0 + 16 >= ch.nc) { tc_fence_before(); mbar_arrive(&sl->sp_free[sp]); }      // accumulator in registers: release it early
 #pragma unroll
             for (int jg = 0; jg < 4; ++jg) {
               const int cg = (c0 >> 2) + jg;
-              if ((cg & 1) == hf && 4 * cg < O) {
-                const float4 e4 = valid ? noise_get4(p.noise_m, id, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (4 * cg < O) {
+                float4 e4;
+                if (p.NM > 0) e4 = *reinterpret_cast<const float4*>(st_nm + t * p.NM + 4 * cg);
+                else e4 = valid ? noise_get4(p.noise_m, id, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const int cc = 4 * cg + k;
                   if (cc < O) {
-                    const float lv = soft_clamp_fast(__uint_as_float(r[4 * jg + k]), sl->min_lv[cc], sl->max_lv[cc]);
-                    my_o[cc] = fmaf(__expf(0.5f * lv), ev[k], my_o[cc]);          // sqrt(exp(lv)) = exp(lv/2)
+                    const float u = __expf(sl->lv_hi[cc] - __uint_as_float(r[4 * jg + k]));
+                    const float sd = sl->lv_s0[cc] * sqrtf(1.f + __fdividef(sl->lv_E[cc], 1.f + u));
+                    my_o[cc] = fmaf(sd, ev[k], my_o[cc]);
                   }
                 }
               }
             }
           }
-          asm volatile("bar.sync 2, 256;" ::: "memory");                 // both column halves of every row are in st_o
-          if (hf == 0 && valid) {
+          // wide policy inputs: the log-var head's MMAs are complete, its activations are dead -> stage the next tile now
+          if (!early_prologue && next_tile < n_tiles) prologue(next_tile, buf ^ 1, tile_it + 1);
+          if (valid) {
             HookOut ho;
             eval_hooks(p.env, [my_o](int d) { return my_o[d]; }, ho);
             p.rewards[row] = my_o[S]; p.done[row] = ho.done; p.viol[row] = ho.viol;
-            for (int cc = 0; cc < p.C; ++cc) p.cv[row * p.C + cc] = ho.cv[cc];
+#pragma unroll
+            for (int cc = 0; cc < DRPO_MAX_CON; ++cc) if (cc < p.C) p.cv[row * p.C + cc] = ho.cv[cc];
           }
-          for (int i = et; i < rows * S; i += EPI_THREADS) {             // coalesced store of the tile's next states
+          named_bar_sync(2, GROUP_THREADS);                              // every row of the tile is final in st_o
+          const float* so = st_o + buf * TILE_M * p.OP;
+          for (int i = ct; i < rows * S; i += GROUP_THREADS) {            // coalesced store of the tile's next states
             const int r = i / S, cc = i - r * S;
-            p.next_states[row0 * S + i] = st_o[r * p.OP + cc];
+            p.next_states[row0 * S + i] = so[r * p.OP + cc];
           }
-          if (hf == 0) my_o[S + A] = 1.f;                                // restore the bias slot if the reward column overwrote it (A == 0 never)
+          named_bar_sync(2, GROUP_THREADS);                              // st_o[buf] is rewritten two prologues from now by other threads
+          my_o[S + A] = 1.f;                                             // restore the bias slot if the reward column overwrote it (A == 0 never)
+          if (ct == 0) stamp(p, tile_it, c, 2);
         }
-        tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->acc_free[b]);   // accumulator drained, activations visible
-        if (et == 0) stamp(p, tile_it, c, 2);
-        acc_par[b] ^= 1u;
-        if (++b == NACC) b = 0;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, TM_COLS);
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static void add_layer(NetPlan& P, int n_real, int k_real, int kind, int a_col, int out_col, int dep, uint32_t& img_off) {
+static void add_layer(NetPlan& P, int n_real, int k_real, int kind, int a_col, int out_col, int dep, int special, int& hid, uint32_t& img_off) {
   const int l = P.n_layers++;
   LayerSpec& L = P.layer[l];
   L.n_real = n_real; L.k_real = k_real; L.np = round_up(n_real, 16); L.kp = round_up(k_real + 1, 16);
   L.kind = kind; L.a_col = a_col; L.out_col = out_col; L.first_chunk = P.n_chunks; L.n_chunks = 0; L.dep = dep;
   L.next_kp = (kind == HID_RELU || kind == HID_SILU) ? round_up(n_real + 1, 16) : 0;
-  for (int n0 = 0; n0 < L.np; n0 += NSLAB) {
+  // balanced chunks of <= NSLAB columns in units of 16 (208 -> 64,48,48,48; 256 -> 4 x 64)
+  const int units = L.np / 16, nch = (L.np + NSLAB - 1) / NSLAB;
+  int n0 = 0;
+  for (int i = 0; i < nch; ++i) {
+    const int u = units / nch + (i < units % nch ? 1 : 0);
     ChunkSpec& c = P.chunk[P.n_chunks++];
-    c.n0 = (uint16_t)n0; c.nc = (uint16_t)std::min(NSLAB, L.np - n0); c.layer = (uint16_t)l; c.pad = 0;
+    c.n0 = (uint16_t)n0; c.nc = (uint16_t)(16 * u); c.layer = (uint16_t)l;
+    c.special = (int8_t)special; c.hid = (uint8_t)(special < 0 ? hid++ : 0);
     c.offset = img_off + (uint32_t)n0 * L.kp * 2; c.bytes = (uint32_t)c.nc * L.kp * 2;
     P.max_chunk_bytes = std::max(P.max_chunk_bytes, c.bytes);
     ++L.n_chunks;
+    n0 += 16 * u;
   }
   img_off += (uint32_t)L.np * L.kp * 2;
 }
@@ -584,38 +722,53 @@ static int build_plan(const drpo_rollout_args& a, NetPlan& P) {
     set_error("bf16 rollout: dims outside the TMEM plan (S=%d A=%d actor hidden=%d model hidden=%d)", S, A, Hp, Hm);
     return DRPO_ERR_UNSUPPORTED;
   }
-  uint32_t off = 0;
-  add_layer(P, Hp, S, HID_RELU, TM_XP, TM_PA, -1, off);           // 0 actor L0
-  add_layer(P, Hp, Hp, HID_RELU, TM_PA, TM_PB, 0, off);           // 1 actor L1
-  add_layer(P, 2 * A, Hp, OUT_POLICY, TM_PB, 0, 1, off);          // 2 actor L2 -> policy head (writes the model input)
+  // policy input: the 8 spare columns when it fits (tile i+1 is staged during tile i's model phase), else the columns that are
+  // free during the policy phase only
+  const int xp = round_up(S + 1, 16) <= 16 ? (int)TM_XP : 464;
+  uint32_t off = 0; int hid = 0;
+  add_layer(P, Hp, S, HID_RELU, xp, TM_PA, -1, -1, hid, off);           // 0 actor L0
+  add_layer(P, Hp, Hp, HID_RELU, TM_PA, TM_PB, 0, -1, hid, off);        // 1 actor L1
+  add_layer(P, 2 * A, Hp, OUT_POLICY, TM_PB, 0, 1, 0, hid, off);        // 2 actor L2 -> policy head (writes the model input)
   P.policy_bytes = off; P.n_policy_chunks = P.n_chunks;
   off = 0;
-  add_layer(P, Hm, S + A, HID_SILU, TM_L1, TM_D1, 2, off);        // 3 trunk0: x_m lives in the (still unused) l1 region
-  add_layer(P, Hm, Hm, HID_SILU, TM_D1, TM_H2, 3, off);           // 4 trunk1 -> h2, kept for both heads
-  add_layer(P, Hm, Hm, HID_SILU, TM_H2, TM_D1, 4, off);           // 5 diff head hidden
-  add_layer(P, Hm, Hm, HID_SILU, TM_H2, TM_L1, 4, off);           // 6 log-var head hidden (independent of 5: no bubble)
-  add_layer(P, S + 1, Hm, OUT_DIFF, TM_D1, 0, 5, off);            // 7 diffs
-  add_layer(P, S + 1, Hm, OUT_LOGVAR, TM_L1, 0, 6, off);          // 8 log-vars
+  add_layer(P, Hm, S + A, HID_SILU, TM_L1, TM_D1, 2, -1, hid, off);     // 3 trunk0: x_m lives in the (still unused) l1 region
+  add_layer(P, Hm, Hm, HID_SILU, TM_D1, TM_H2, 3, -1, hid, off);        // 4 trunk1 -> h2, kept for both heads
+  add_layer(P, Hm, Hm, HID_SILU, TM_H2, TM_D1, 4, -1, hid, off);        // 5 diff head hidden
+  add_layer(P, Hm, Hm, HID_SILU, TM_H2, TM_L1, 4, -1, hid, off);        // 6 log-var head hidden (independent of 5: no bubble)
+  add_layer(P, S + 1, Hm, OUT_DIFF, TM_D1, 0, 5, 1, hid, off);          // 7 diffs
+  add_layer(P, S + 1, Hm, OUT_LOGVAR, TM_L1, 0, 6, 2, hid, off);        // 8 log-vars
   P.model_bytes = off;
-  return DRPO_OK;
-}
-
-// order of drpo_linear's handed to pack_net for the member net: trunk0, trunk1, diff0, lvar0, diff1, lvar1 (= layers 3..8)
-static int pack_net(const drpo_linear* lin, const LayerSpec* L, int count, uint8_t* img, void* stream) {
-  uint32_t off = 0;
-  for (int i = 0; i < count; ++i) {
-    DRPO_LAUNCH(pack_layer_kernel, grid_for((int64_t)L[i].np * L[i].kp), 256, 0, stream, lin[i].w, lin[i].b, L[i].n_real, L[i].k_real,
-                L[i].np, L[i].kp, reinterpret_cast<__nv_bfloat16*>(img + off));
-    off += (uint32_t)L[i].np * L[i].kp * 2;
+  // the accumulator rotation (chunk % NACC) and the group alternation (hid % 2) must repeat identically every tile, and
+  // each output layer must be exactly one chunk
+  if (P.n_chunks % NACC != 0 || hid % 2 != 0 || P.layer[2].n_chunks != 1 || P.layer[7].n_chunks != 1 || P.layer[8].n_chunks != 1) {
+    set_error("bf16 rollout: chunk plan (%d chunks, %d hidden) does not tile the accumulator rotation (actor hidden=%d model hidden=%d)",
+              P.n_chunks, hid, Hp, Hm);
+    return DRPO_ERR_UNSUPPORTED;
   }
   return DRPO_OK;
 }
 
-static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP) {
+// order of drpo_linear's handed to pack_net for the member net: trunk0, trunk1, diff0, lvar0, diff1, lvar1 (= layers 3..8)
+static int pack_net(const drpo_linear* lin, const NetPlan& P, int first_layer, int count, uint8_t* img, void* stream) {
+  uint32_t off = 0;
+  for (int i = 0; i < count; ++i) {
+    const LayerSpec& L = P.layer[first_layer + i];
+    PackChunks pc; pc.n = L.n_chunks;
+    for (int c = 0; c < L.n_chunks; ++c) pc.n0[c] = P.chunk[L.first_chunk + c].n0;
+    pc.n0[L.n_chunks] = L.np;
+    DRPO_LAUNCH(pack_layer_kernel, grid_for((int64_t)L.np * L.kp), 256, 0, stream, lin[i].w, lin[i].b, L.n_real, L.k_real,
+                L.np, L.kp, pc, reinterpret_cast<__nv_bfloat16*>(img + off));
+    off += (uint32_t)L.np * L.kp * 2;
+  }
+  return DRPO_OK;
+}
+
+static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP, int& NM) {
   SP = P.layer[0].kp | 1;                                  // state row [s, 1, 0..] padded to the first layer's K
   OP = P.layer[3].kp | 1;                                  // [norm s, a, 1, 0..] padded to trunk0's K; later [next state, reward]
+  NM = (S + 1) <= 16 ? round_up(S + 1, 4) : 0;             // staged model noise (wide states draw it inline)
   const uint32_t slot = (P.max_chunk_bytes + 1023u) & ~1023u;
-  return (int)(slot * stages + (size_t)TILE_M * (2 * SP + OP) * 4 + sizeof(SmemLayout) + 64);
+  return (int)(slot * stages + (size_t)TILE_M * (2 * SP + 2 * OP + 4 + NM) * 4 + sizeof(SmemLayout) + 64);
 }
 
 }  // namespace umma
@@ -652,23 +805,23 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
   // ---- pack the actor and every member this rollout uses into the UMMA layout (bf16, bias folded in) ----
   {
     drpo_linear pl[3] = {a.actor->l0, a.actor->l1, a.actor->l2};
-    if ((rc = pack_net(pl, &P.layer[0], 3, pol_img, stream))) return rc;
+    if ((rc = pack_net(pl, P, 0, 3, pol_img, stream))) return rc;
     bool used[64] = {false};
     for (int t = 0; t < H; ++t) used[a.member_idx_host[t]] = true;
     for (int m = 0; m < E; ++m) {
       if (!used[m]) continue;
       MemberNet mn = member_of(*a.ensemble, m);
       drpo_linear ml[6] = {mn.t0, mn.t1, mn.d0, mn.l0, mn.d1, mn.l1};       // plan order: 3 trunk0, 4 trunk1, 5 diff0, 6 lvar0, 7 diff1, 8 lvar1
-      if ((rc = pack_net(ml, &P.layer[3], 6, mem_img + (int64_t)m * align_up(P.model_bytes, 1024), stream))) return rc;
+      if ((rc = pack_net(ml, P, 3, 6, mem_img + (int64_t)m * align_up(P.model_bytes, 1024), stream))) return rc;
     }
   }
   int dev = 0, sms = 148, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int SP, OP, stages = MAX_STAGES;
-  while (stages > 2 && smem_bytes_for(P, S, stages, SP, OP) > max_smem) --stages;
-  const int smem = smem_bytes_for(P, S, stages, SP, OP);
+  int SP, OP, NM, stages = MAX_STAGES;
+  while (stages > 2 && smem_bytes_for(P, S, stages, SP, OP, NM) > max_smem) --stages;
+  const int smem = smem_bytes_for(P, S, stages, SP, OP, NM);
   if (smem > max_smem) { set_error("bf16 rollout: needs %d B of shared memory, device offers %d", smem, max_smem); return DRPO_ERR_UNSUPPORTED; }
   DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 
@@ -687,7 +840,7 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
     sp.norm_mean = a.ensemble->norm_mean; sp.norm_std = a.ensemble->norm_std; sp.min_lv = a.ensemble->min_log_var; sp.max_lv = a.ensemble->max_log_var;
     sp.noise_p = make_noise(a.eps_policy ? a.eps_policy + (int64_t)t * a.eps_batch_stride * A : nullptr, A, a.seed, TAG_ROLLOUT_POLICY, (uint32_t)t);
     sp.noise_m = make_noise(a.eps_model ? a.eps_model + (int64_t)t * a.eps_batch_stride * (S + 1) : nullptr, S + 1, a.seed, TAG_ROLLOUT_MODEL, (uint32_t)t);
-    sp.env = *a.env; sp.S = S; sp.A = A; sp.C = C; sp.SP = SP; sp.OP = OP; sp.stages = stages; sp.err_flag = err_flag;
+    sp.env = *a.env; sp.S = S; sp.A = A; sp.C = C; sp.SP = SP; sp.OP = OP; sp.NM = NM; sp.stages = stages; sp.err_flag = err_flag;
     sp.dump_layer = dump_layer; sp.dump_out = dump_out;
     DRPO_LAUNCH(rollout_step_umma_kernel, grid, NUM_THREADS, smem, stream, sp);
     DRPO_LAUNCH(rollout_store_kernel, grid_for(B * S), 256, 0, stream, a.virt, w.st, n_dev, cur, w.actions, w.next_states,
