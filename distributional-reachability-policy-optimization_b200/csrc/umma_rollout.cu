@@ -11,14 +11,17 @@
 //     (layer, chunk), and streamed from L2 into a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier);
 //   * bias rides in the GEMM: every activation tile carries a constant-1 column and the packed weights hold the bias in
 //     the matching K slot; the epilogue is activation (packed bf16x2 math) + TMEM store only.
-// Warp roles (512 threads):
-//   warp 0     MMA issuer (one elected lane) + TMEM allocator; warp 1 TMA producer; warps 2-3 idle;
-//   warps 4-7  group C: the three narrow output chunks (policy head, diff head, log-var head), the Philox noise, the
-//              env hooks, the global stores, and the NEXT tile's prologue (state prefetch, normalisation, policy input),
-//              so that the tail of tile i overlaps the first policy layers of tile i+1;
-//   warps 8-11 hidden-layer epilogue group A, warps 12-15 group B: the 24 hidden-layer chunks of a tile alternate between
-//              the two groups, so the fixed latencies of one group's chunk (barrier wake-up, tcgen05.ld, tcgen05.st,
-//              fence) hide behind the other group's MUFU work.
+// Warp roles (768 threads, one CTA per SM):
+//   warps 0-3   group C: the three narrow output chunks (policy head -> action + model input, diff head, log-var head ->
+//               Gaussian sample), the coalesced next-state store, and the NEXT tile's prologue (cp.async prefetch of states and
+//               noise, normalisation, policy input), so that the tail of tile i overlaps the first policy layers of tile i+1;
+//   warps 4-19  four hidden-layer epilogue groups: group pair (g>>1) takes every other hidden chunk, (g&1) picks the column
+//               half, so two chunks are always in their epilogue and the fixed latencies of one (barrier wake-up, tcgen05.ld,
+//               tcgen05.st, fence) hide behind the other's MUFU work;
+//   warp 20     idle; warp 21 TMA producer (weight chunks -> shared-memory ring);
+//   warps 22-23 two MMA issuers (one elected lane each) alternating chunks; warp 23 also owns the TMEM allocation.
+// The per-step Gaussian draws (Philox keyed by global trajectory id, or the injected parity tensors) are staged row-compact
+// by noise_stage_kernel; the env hooks run fused with the replay-buffer store in hooks_store_kernel.
 // Measured design inputs (tools/ubench_*.cu, profiles/): tcgen05.mma issues at the N/2-cycle hardware floor only from an
 // elect.sync branch (a `lane == 0` branch costs 63 cycles/MMA); tcgen05.ld moves ~3 KB/clk/SM; MUFU is 4 lanes/clk/SMSP and
 // tanh.approx.bf16x2 is two MUFU ops, which makes the SiLU epilogues MUFU-bound.
@@ -41,10 +44,12 @@ constexpr int NACC = 3;                    // accumulator buffers in TMEM
 constexpr int MAX_CHUNKS = 32;
 constexpr int MAX_LAYERS = 9;
 constexpr int GROUP_THREADS = 128;         // one epilogue group = 4 warps = the 128 TMEM lanes
-constexpr int EPI_THREADS = 3 * GROUP_THREADS;      // groups C (output chunks, prologue, tail), A and B (hidden chunks)
-constexpr int NUM_THREADS = EPI_THREADS + 128;      // warp 0 MMA issuer, warp 1 TMA producer, warps 2-3 idle (keep the groups 4-aligned)
-constexpr int MMA_WARP = 0, PRODUCER_WARP = 1;
-constexpr int GROUP_C_WARP0 = 4, GROUP_A_WARP0 = 8; // a warp reaches TMEM lanes 32*(warp%4)..; the SM's arbiter prefers high warp ids
+constexpr int N_HID_GROUPS = 4;            // hidden groups: pair (g>>1) takes every other hidden chunk, (g&1) picks the column half
+constexpr int EPI_THREADS = (1 + N_HID_GROUPS) * GROUP_THREADS;   // group C (output chunks, prologue) + the hidden groups
+constexpr int NUM_THREADS = EPI_THREADS + 128;      // + warp 20 idle, warp 21 TMA producer, warps 22-23 MMA issuers
+// a warp reaches TMEM lanes 32*(warp%4)..; the SM's arbiter prefers high warp ids, so the single-lane roles sit on top
+constexpr int GROUP_C_WARP0 = 0, GROUP_H_WARP0 = 4;
+constexpr int PRODUCER_WARP = NUM_THREADS / 32 - 3, MMA_WARP = NUM_THREADS / 32 - 1, MMA_WARP2 = NUM_THREADS / 32 - 2;
 constexpr int MAX_STAGES = 6;
 constexpr int NSPECIAL = 3;                // output chunks per tile: policy head, diff head, log-var head
 constexpr uint32_t TM_COLS = 512;
@@ -81,17 +86,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (fails the launch) after ~4 s of SM clocks instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+// bounded wait: a protocol bug traps (fails the launch) after ~2^26 polls (seconds) instead of hanging the GPU.  The slow path
+// is out of line (every wait site costs two instructions of the small instruction cache) and as lean as possible: a failed
+// try_wait returns after only ~40 ns, so a waiting warp re-issues the loop body every ~80 cycles and those instructions
+// compete with the working warps of its scheduler (the first profile spent half of all issue slots on wait loops).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int* err_flag, int code) {
 #pragma unroll 1
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) {
-      if (err_flag) atomicExch(err_flag, code);
-      __trap();
-    }
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity), "r"(0x989680u) : "memory");
+    if (ok) return;
   }
+  if (err_flag) atomicExch(err_flag, code);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  if (!ok) mbar_wait_slow(smem_u32(bar), parity, err_flag, code);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // one elected lane of a converged warp: unlike `lane == 0`, the compiler knows the branch is single-threaded, keeps the
@@ -147,6 +166,7 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // softplus / soft clamp with fast intrinsics (bf16-path tolerance)
 __device__ __forceinline__ float softplus_fast(float x) { return x > 15.f ? x : __logf(1.f + __expf(x)); }
@@ -230,6 +250,12 @@ struct NetPlan {
   uint32_t policy_bytes, model_bytes;     // image sizes; policy chunks index the actor image, model chunks the member image
   int n_policy_chunks;
   uint32_t max_chunk_bytes;
+  // Flattened per-chunk records, copied to shared memory at kernel start so that the per-chunk loops of the issuer and of the
+  // hidden groups read one 16-byte word instead of chasing the layer/chunk tables through the constant bank.
+  //   irec (issuer):  x = idesc, y = descriptor high word (SBO, version), z = a_col | nk << 16 | (special + 1) << 24,
+  //                   w = kA | kB << 8 | (bufA + 1) << 16 | (bufB + 1) << 20   (K-sliced start of a layer's first chunk, 0 = none)
+  //   erec (hidden):  x = n0 | nc << 16, y = out_col | kind << 16 | (hid & 1) << 24 | hidden << 25, z = n_real | np << 16, w = next_kp
+  uint4 irec[MAX_CHUNKS], erec[MAX_CHUNKS];
 };
 
 // Weight image of one layer: per chunk a contiguous block in the canonical K-major layout [n/8][k/8][8 rows][8 elems];
@@ -256,30 +282,34 @@ __global__ void pack_layer_kernel(const float* __restrict__ W, const float* __re
 struct StepParams {
   NetPlan plan;
   const uint8_t* policy_img; const uint8_t* model_img;
-  const float* cur; const int32_t* ids; const int* n_dev; int64_t n_max;
-  float *actions, *next_states, *rewards, *cv; uint8_t *done, *viol;
+  const float* cur; const int* n_dev; int64_t n_max;
+  const float* eps_p;                    // [n][4]   this step's policy noise, row-compact (noise_stage_kernel)
+  const float* eps_m;                    // [n][NMG] this step's model noise
+  float *actions, *next_states, *rewards;
   const float *norm_mean, *norm_std, *min_lv, *max_lv;
-  NoiseView noise_p, noise_m;
-  drpo_env_params env;
-  int S, A, C, SP, OP, NM, stages;
+  int S, A, SP, OP, NM, NMG, stages;
   int* err_flag;
   int dump_layer; float* dump_out;       // debug: dump the fp32 accumulator of one layer
 };
 
 struct SmemLayout {
-  uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_free[NACC], sp_full[NSPECIAL], sp_free[NSPECIAL], tile_ready;
-  uint32_t tmem_base, pad;
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_free[NACC], sp_full[NSPECIAL], sp_free[NSPECIAL], tile_ready, token[2];
+  uint32_t tmem_base, pad[3];
   // per-dim constants of the member, staged once per CTA: normaliser, and the log-var soft clamp folded into
   //   std = exp(lv/2) = s0 * sqrt(1 + E / (1 + exp(hi - x)))   with s0 = exp(lo/2), E = exp(hi - lo)      (src/dynamics.py:120-121,201)
   float norm_mean[64], norm_inv[64], lv_hi[64], lv_E[64], lv_s0[64];
+  uint4 irec[MAX_CHUNKS], erec[MAX_CHUNKS];
 };
 
-// debug timing (dump_layer == 100): CTA 0 stamps clock() for its first 4 tiles into dump_out viewed as uint32
+// debug timing (kDebug build, dump_layer == 100): CTA 0 stamps clock() for its first 4 tiles into dump_out viewed as uint32
 // [(tile*32 + chunk)*8 + k], k: 0 epilogue wait begin, 1 accumulator ready, 2 epilogue done, 3 mma deps ok, 4 weights ready,
 // 5 mma issued, 6 tile prologue begin (chunk 0 only), 7 tile prologue end
+template <bool kDebug>
 __device__ __forceinline__ void stamp(const StepParams& p, uint32_t tile_it, int chunk, int k) {
-  if (p.dump_layer == 100 && blockIdx.x == 0 && tile_it < 4)
-    reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + chunk) * 8 + k] = (uint32_t)clock();
+  if (kDebug) {
+    if (p.dump_layer == 100 && blockIdx.x == 0 && tile_it < 4)
+      reinterpret_cast<uint32_t*>(p.dump_out)[(tile_it * 32 + chunk) * 8 + k] = (uint32_t)clock();
+  }
 }
 
 // write one input row (k_real values + constant 1) as packed bf16 into a TMEM activation buffer
@@ -292,67 +322,72 @@ __device__ __forceinline__ void write_input_row(uint32_t lane_base, uint32_t col
   }
 }
 
-// 16 accumulator columns -> activation -> 8 packed bf16x2 words; `one` = element of this piece that must read 1.0 (the bias
-// slot of the consumer layer) or anything outside [0,16)
+// 16 accumulator columns -> activation -> 8 packed bf16x2 words
 template <bool kSilu>
-__device__ __forceinline__ void act_pack16(const uint32_t (&r)[16], uint32_t (&pk)[8], int one) {
+__device__ __forceinline__ void act_pack16(const uint32_t (&r)[16], uint32_t (&pk)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t x = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
     pk[j] = kSilu ? silu_bf16x2(x) : relu_bf16x2(x);
   }
-  if (one >= 0 && one < 16) {
+}
+// force element `one` (0..15) of a packed piece to 1.0: the bias slot of the consumer layer
+__device__ __forceinline__ void patch_one(uint32_t (&pk)[8], int one) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (one == 2 * j) pk[j] = (pk[j] & 0xFFFF0000u) | 0x00003F80u;
-      if (one == 2 * j + 1) pk[j] = (pk[j] & 0x0000FFFFu) | 0x3F800000u;
-    }
+  for (int j = 0; j < 8; ++j) {
+    if (one == 2 * j) pk[j] = (pk[j] & 0xFFFF0000u) | 0x00003F80u;
+    if (one == 2 * j + 1) pk[j] = (pk[j] & 0x0000FFFFu) | 0x3F800000u;
   }
 }
 
-// epilogue of one chunk (nc = 16, 32, 48 or 64 columns) of a hidden layer for one row:
-// ACC[acc_col + j] -> activation -> packed bf16 -> TMEM out_col + (n0 + j)/2.  All loads are issued before the single wait.
+// epilogue of one column half (hn = 16 or 32 columns starting at layer column h0) of a hidden-layer chunk, one row per thread:
+// ACC[acc_col + j] -> activation -> packed bf16 -> TMEM out_col + (h0 + j)/2.  Both loads are issued before the single wait.
 template <bool kSilu>
-__device__ __forceinline__ void hidden_chunk(uint32_t lane_base, uint32_t acc_col, const LayerSpec& L, int n0, int nc) {
-  uint32_t ra[16], rb[16], rc[16], rd[16];
+__device__ __forceinline__ void hidden_half(uint32_t lane_base, uint32_t acc_col, uint32_t out_col, int n_real, int np, int next_kp, int h0, int hn) {
+  uint32_t ra[16], rb[16];
   const uint32_t src = lane_base + acc_col;
   tmem_ld16(src, ra);
-  if (nc > 16) tmem_ld16(src + 16, rb);
-  if (nc > 32) tmem_ld16(src + 32, rc);
-  if (nc > 48) tmem_ld16(src + 48, rd);
+  if (hn > 16) tmem_ld16(src + 16, rb);
   tmem_ld_wait();
-  const int one = L.n_real - n0;                       // position of the consumer's bias slot relative to this chunk
-  const uint32_t dst = lane_base + (uint32_t)L.out_col + (uint32_t)(n0 >> 1);
-  uint32_t pk[8];
-  act_pack16<kSilu>(ra, pk, one);
-  tmem_st8(dst, pk);
-  if (nc > 16) { act_pack16<kSilu>(rb, pk, one - 16); tmem_st8(dst + 8, pk); }
-  if (nc > 32) { act_pack16<kSilu>(rc, pk, one - 32); tmem_st8(dst + 16, pk); }
-  if (nc > 48) { act_pack16<kSilu>(rd, pk, one - 48); tmem_st8(dst + 24, pk); }
-  if (n0 + nc == L.np && L.next_kp > L.np) {             // constant tail [np, next_kp): 1 at n_real, else 0
-    for (int e0 = L.np; e0 < L.next_kp; e0 += 16) {
+  const int one = n_real - h0;                         // position of the consumer's bias slot relative to this half
+  const uint32_t dst = lane_base + out_col + (uint32_t)(h0 >> 1);
+  uint32_t pa[8], pb[8];
+  act_pack16<kSilu>(ra, pa);
+  if (one >= 0 && one < 16) patch_one(pa, one);          // rare: only the piece that holds column n_real
+  tmem_st8(dst, pa);
+  if (hn > 16) {
+    act_pack16<kSilu>(rb, pb);
+    if (one >= 16 && one < 32) patch_one(pb, one - 16);
+    tmem_st8(dst + 8, pb);
+  }
+  if (h0 + hn == np && next_kp > np) {                   // rare: constant tail [np, next_kp): 1 at n_real, else 0
+    for (int e0 = np; e0 < next_kp; e0 += 16) {
       uint32_t t8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) t8[j] = pack_bf16((e0 + 2 * j) == L.n_real ? 1.f : 0.f, (e0 + 2 * j + 1) == L.n_real ? 1.f : 0.f);
-      tmem_st8(lane_base + (uint32_t)L.out_col + (uint32_t)(e0 >> 1), t8);
+      for (int j = 0; j < 8; ++j) t8[j] = pack_bf16((e0 + 2 * j) == n_real ? 1.f : 0.f, (e0 + 2 * j + 1) == n_real ? 1.f : 0.f);
+      tmem_st8(lane_base + out_col + (uint32_t)(e0 >> 1), t8);
     }
   }
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 
+template <bool kDebug>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const NetPlan& plan = p.plan;
-  // shared memory: [weight ring | raw states x2 | model input / next state rows x2 | policy noise | model noise | barriers, constants]
+  // shared memory: [weight ring | raw states x2 | model input / next state rows x2 | policy noise x2 | model noise x2 | barriers, constants]
   uint8_t* ring = smem_raw;
   const uint32_t slot_bytes = (plan.max_chunk_bytes + 1023u) & ~1023u;
   float* st_s = reinterpret_cast<float*>(ring + (size_t)slot_bytes * p.stages);      // [2][128][SP] raw states (fp32)
   float* st_o = st_s + 2 * TILE_M * p.SP;                                            // [2][128][OP] [norm s, a, 1, 0..] then [next state, reward]
-  float* st_np = st_o + 2 * TILE_M * p.OP;                                           // [128][4]  policy noise of the tile in its policy phase
-  float* st_nm = st_np + TILE_M * 4;                                                 // [128][NM] model noise of the tile in its model phase
-  SmemLayout* sl = reinterpret_cast<SmemLayout*>(st_nm + TILE_M * p.NM);
+  float* st_np = st_o + 2 * TILE_M * p.OP;                                           // [2][128][4]  policy noise
+  float* st_nm = st_np + 2 * TILE_M * 4;                                             // [2][128][NM] model noise (NM = 0: read from global)
+  SmemLayout* sl = reinterpret_cast<SmemLayout*>(st_nm + 2 * TILE_M * p.NM);
 
   const int n = (int)min((int64_t)*p.n_dev, p.n_max);
   const int n_tiles = (n + TILE_M - 1) / TILE_M;
@@ -360,19 +395,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&sl->full[s], 1); mbar_init(&sl->empty[s], 1); }
-    for (int b = 0; b < NACC; ++b) { mbar_init(&sl->acc_full[b], 1); mbar_init(&sl->acc_free[b], GROUP_THREADS); }
+    for (int b = 0; b < NACC; ++b) { mbar_init(&sl->acc_full[b], 1); mbar_init(&sl->acc_free[b], 2 * GROUP_THREADS); }
     for (int k = 0; k < NSPECIAL; ++k) { mbar_init(&sl->sp_full[k], 1); mbar_init(&sl->sp_free[k], GROUP_THREADS); }
     mbar_init(&sl->tile_ready, GROUP_THREADS);
+    mbar_init(&sl->token[0], 1); mbar_init(&sl->token[1], 1);
     fence_barrier_init();
   }
-  if (threadIdx.x >= NUM_THREADS - EPI_THREADS) {
+  if (threadIdx.x < EPI_THREADS) {
     // constants + the constant tails of the staging rows: [.., 1, 0, 0 ..] = bias slot and K padding of the two input layers
-    const int et0 = threadIdx.x - (NUM_THREADS - EPI_THREADS);
+    const int et0 = threadIdx.x;
     if (et0 < S) { sl->norm_mean[et0] = p.norm_mean[et0]; sl->norm_inv[et0] = 1.f / (p.norm_std[et0] + 1e-6f); }
     if (et0 <= S) {
       const float lo = p.min_lv[et0], hi = p.max_lv[et0];
       sl->lv_hi[et0] = hi; sl->lv_E[et0] = __expf(hi - lo); sl->lv_s0[et0] = __expf(0.5f * lo);
     }
+    if (et0 < MAX_CHUNKS) { sl->irec[et0] = plan.irec[et0]; sl->erec[et0] = plan.erec[et0]; }
     for (int i = et0; i < 2 * TILE_M * p.SP; i += EPI_THREADS) { const int c = i % p.SP; st_s[i] = c == S ? 1.f : 0.f; }
     for (int i = et0; i < 2 * TILE_M * p.OP; i += EPI_THREADS) { const int c = i % p.OP; st_o[i] = c == S + A ? 1.f : 0.f; }
   }
@@ -397,139 +434,158 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
         }
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer =====================
+  } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+    // ===================== two MMA issuers =====================
+    // The tensor pipe accepts only a few tcgen05.mma ahead of execution, so an issuing thread is blocked for the duration of its
+    // chunk and cannot overlap the per-chunk bookkeeping (barrier waits, record load, commits: ~500 cycles of latency) with it.
+    // Two issuers alternate chunks: while one is blocked feeding chunk g, the other clears the waits of chunk g+1.  A token
+    // keeps the ISSUE order equal to the chunk order (every in-order argument in this file relies on it), and both threads
+    // replay the complete (static) schedule so that each one knows the phase parity of every barrier it waits on.
     if (elect_one()) {
+      const uint32_t me = warp == MMA_WARP ? 0u : 1u;
       int s = 0; uint32_t ring_par = 0;      // weight ring slot + parity of its current use
-      // accumulator buffer b = chunk index % NACC (n_chunks is a multiple of NACC).  owner[b]: who drains the buffer's current
-      // contents (-1 nobody yet, 0 a hidden group via acc_free[b], 1+k group C via sp_free[k]).  commits/seen count the
-      // phases of each "free" barrier that were started / already observed by this thread (at most one outstanding).
-      int owner[NACC] = {-1, -1, -1};
-      uint32_t hid_commits[NACC] = {0, 0, 0}, hid_seen[NACC] = {0, 0, 0};
-      uint32_t sp_commits[NSPECIAL] = {0, 0, 0}, sp_seen[NSPECIAL] = {0, 0, 0};
-      auto ensure_drained = [&](int b, int code) {
-        // unrolled selects keep the small state arrays in registers
-#pragma unroll
-        for (int bb = 0; bb < NACC; ++bb) {
-          if (bb != b) continue;
-          if (owner[bb] == 0) {
-            if (hid_seen[bb] < hid_commits[bb]) { mbar_wait(&sl->acc_free[bb], (hid_commits[bb] - 1) & 1, p.err_flag, code); hid_seen[bb] = hid_commits[bb]; tc_fence_after(); }
-          } else if (owner[bb] > 0) {
-#pragma unroll
-            for (int k = 0; k < NSPECIAL; ++k)
-              if (owner[bb] == 1 + k && sp_seen[k] < sp_commits[k]) { mbar_wait(&sl->sp_free[k], (sp_commits[k] - 1) & 1, p.err_flag, code); sp_seen[k] = sp_commits[k]; tc_fence_after(); }
-          }
+      // Accumulator buffer b = chunk index % NACC (n_chunks is a multiple of NACC).  Who drains the buffer's current contents is
+      // own[b] (2 bits each: 0 the hidden groups via acc_free[b], 1+k group C via sp_free[k]).  Each "free" barrier has at most
+      // one phase outstanding: pend_* bit = a phase was started and not yet observed, par_* bit = parity of that phase.
+      uint32_t own = 0, pend_h = 0, par_h = 0, pend_s = 0, par_s = 0;
+      uint32_t g = 0;                        // global chunk counter: chunk g belongs to issuer (g & 1)
+      uint32_t tok_par = 0;                  // parity of the next phase of the OTHER issuer's token
+      auto ensure_drained = [&](int b, bool mine, int code) {
+        const uint32_t o = (own >> (2 * b)) & 3u;
+        if (o == 0) {
+          if ((pend_h >> b) & 1u) { if (mine) { mbar_wait(&sl->acc_free[b], (par_h >> b) & 1u, p.err_flag, code); tc_fence_after(); } pend_h ^= 1u << b; par_h ^= 1u << b; }
+        } else {
+          const int k = (int)o - 1;
+          if ((pend_s >> k) & 1u) { if (mine) { mbar_wait(&sl->sp_free[k], (par_s >> k) & 1u, p.err_flag, code); tc_fence_after(); } pend_s ^= 1u << k; par_s ^= 1u << k; }
         }
       };
+      const int n_chunks = plan.n_chunks;
       uint32_t tile_it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
         mbar_wait(&sl->tile_ready, tile_it & 1, p.err_flag, 2);
         tc_fence_after();
-        int c_abs = 0, b = 0;
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const LayerSpec& L = plan.layer[l];
-          if (L.dep >= 0) {
-            // A operand = output of layer dep: its chunks must be through their epilogues.  The two hidden groups finish out
-            // of order, so the last TWO chunks are checked; older ones precede them in their group's program order.  A chunk
-            // issued more than NACC chunks ago was already proven drained when its buffer was reused.
-            const int last = plan.layer[L.dep].first_chunk + plan.layer[L.dep].n_chunks - 1;
-            for (int cd = last; cd >= plan.layer[L.dep].first_chunk && cd >= last - 1; --cd)
-              if (c_abs - cd <= NACC) ensure_drained(cd % NACC, 5);
-          }
-          const uint32_t sbo = (uint32_t)(L.kp >> 3) * 128u;
-          const int nk = L.kp >> 4;
-          for (int c = 0; c < L.n_chunks; ++c, ++c_abs) {
-            const ChunkSpec& ch = plan.chunk[L.first_chunk + c];
-            ensure_drained(b, 6);                                         // accumulator buffer still being read by its last user?
-            stamp(p, tile_it, c_abs, 3);
+        int b = 0;
+        for (int c = 0; c < n_chunks; ++c, ++g) {
+          const uint4 rec = sl->irec[c];
+          const bool mine = (g & 1u) == me;
+          ensure_drained(b, mine, 6);                                     // accumulator buffer still being read by its last user?
+          const int sp = (int)((rec.z >> 24) & 0xFFu) - 1;
+          if (mine) {
+            if (me == 0) stamp<kDebug>(p, tile_it, c, 3);
             mbar_wait(&sl->full[s], ring_par, p.err_flag, 3);
             tc_fence_after();
-            stamp(p, tile_it, c_abs, 4);
             const uint32_t b_base = smem_u32(ring + (size_t)s * slot_bytes);
-            const uint32_t idesc = make_idesc(ch.nc);
+            const uint32_t idesc = rec.x, desc_hi = rec.y;
+            const uint32_t desc_lo = ((b_base & 0x3FFFFu) >> 4) | (8u << 16);   // LBO = 128 B (K-direction core-matrix stride)
+            const uint32_t a_addr = tmem + (rec.z & 0xFFFFu);
             const uint32_t d_addr = tmem + TM_ACC + (uint32_t)b * NSLAB;
-            const uint64_t bdesc = make_b_desc(b_base, 128u, sbo);
-            uint32_t desc_lo = (uint32_t)bdesc; const uint32_t desc_hi = (uint32_t)(bdesc >> 32);
-            uint32_t a_addr = tmem + (uint32_t)L.a_col;
-            mma_ts<false>(d_addr, a_addr, desc_lo, desc_hi, idesc);
-#pragma unroll 4
-            for (int k = 1; k < nk; ++k) {                              // one k-step = 2 core matrices = 256 B = +16 in the address field
-              desc_lo += 16u; a_addr += 8u;
-              mma_ts<true>(d_addr, a_addr, desc_lo, desc_hi, idesc);
+            const int nk = (int)((rec.z >> 16) & 0xFFu);
+            if (g > 0) { mbar_wait(&sl->token[me ^ 1u], tok_par, p.err_flag, 8); tok_par ^= 1u; }   // chunk g-1 has been issued
+            if (me == 0) stamp<kDebug>(p, tile_it, c, 4);
+            // back-to-back UTCHMMA for k-steps [lo, hi); one k-step = 2 core matrices = 256 B = +16 in the address field,
+            // +8 TMEM columns.  Fully unrolled with uniform predicates: a rolled loop issues an order of magnitude slower.
+            auto issue_range = [&](int lo, int hi) {
+#pragma unroll
+              for (int k = 0; k < 17; ++k) {
+                if (k >= lo && k < hi) {
+                  if (k == 0) mma_ts<false>(d_addr, a_addr, desc_lo, desc_hi, idesc);
+                  else mma_ts<true>(d_addr, a_addr + 8u * k, desc_lo + 16u * k, desc_hi, idesc);
+                }
+              }
+            };
+            if (rec.w == 0) {
+              issue_range(0, nk);
+            } else {
+              // First chunk of a layer whose A operand is still being produced: the producer layer's chunks drain out of order
+              // across the two group pairs, so its last TWO chunks are tracked (older ones precede them in their pair's program
+              // order and their buffers were reused since).  K-sliced start: k-steps that only read columns below chunk (last-1)
+              // issue at once, the rest wait for (last-1), then (last).
+              const int kB = min((int)((rec.w >> 8) & 0xFFu), nk), kA = min((int)(rec.w & 0xFFu), kB);
+              const int bufA = (int)((rec.w >> 16) & 0xFu) - 1, bufB = (int)((rec.w >> 20) & 0xFu) - 1;
+              issue_range(0, kA);
+              if (bufA >= 0) ensure_drained(bufA, true, 5);
+              issue_range(kA, kB);
+              if (bufB >= 0) ensure_drained(bufB, true, 5);
+              issue_range(kB, nk);
             }
             tc_commit(&sl->empty[s]);                                    // frees the ring slot when these MMAs retire
-            const int sp = ch.special;
-#pragma unroll
-            for (int bb = 0; bb < NACC; ++bb) {
-              if (bb != b) continue;
-              if (sp < 0) { tc_commit(&sl->acc_full[bb]); ++hid_commits[bb]; owner[bb] = 0; }
-              else {
-                owner[bb] = 1 + sp;
-#pragma unroll
-                for (int k = 0; k < NSPECIAL; ++k) if (k == sp) { tc_commit(&sl->sp_full[k]); ++sp_commits[k]; }
-              }
+            if (sp < 0) tc_commit(&sl->acc_full[b]); else tc_commit(&sl->sp_full[sp]);
+            mbar_arrive(&sl->token[me]);                                  // chunk g is issued: the other issuer may issue g+1
+            if (me == 0) stamp<kDebug>(p, tile_it, c, 5);
+          } else {
+            if (rec.w != 0) {                                             // replay the other issuer's K-sliced waits
+              const int bufA = (int)((rec.w >> 16) & 0xFu) - 1, bufB = (int)((rec.w >> 20) & 0xFu) - 1;
+              if (bufA >= 0) ensure_drained(bufA, false, 5);
+              if (bufB >= 0) ensure_drained(bufB, false, 5);
             }
-            stamp(p, tile_it, c_abs, 5);
-            if (++b == NACC) b = 0;
-            if (++s == p.stages) { s = 0; ring_par ^= 1u; }
           }
+          own &= ~(3u << (2 * b));
+          if (sp < 0) pend_h |= 1u << b;
+          else { pend_s |= 1u << sp; own |= (uint32_t)(1 + sp) << (2 * b); }
+          if (++b == NACC) b = 0;
+          if (++s == p.stages) { s = 0; ring_par ^= 1u; }
         }
       }
     }
-  } else if (warp >= GROUP_A_WARP0) {
-    // ===================== hidden-layer epilogue groups A (warps 8-11) and B (warps 12-15) =====================
-    const int grp = (warp - GROUP_A_WARP0) >> 2, q = warp & 3;
+  } else if (warp >= GROUP_H_WARP0 && warp < GROUP_H_WARP0 + 4 * N_HID_GROUPS) {
+    // ===================== hidden-layer epilogue groups (4 groups of 4 warps) =====================
+    const int grp = (warp - GROUP_H_WARP0) >> 2, q = warp & 3;
+    const int pair = grp >> 1, half = grp & 1;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    const bool lead = (threadIdx.x & (GROUP_THREADS - 1)) == 0;
-    uint32_t acc_par[NACC] = {0, 0, 0};
+    const bool lead = kDebug && (threadIdx.x & (GROUP_THREADS - 1)) == 0 && half == 0;
+    uint32_t par = 0;                                                     // bit b: phase parity of acc_full[b]
+    const int n_chunks_h = plan.n_chunks;
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-      const int64_t row0 = (int64_t)tile * TILE_M;
-      const int t = q * 32 + lane;
-      const bool valid = t < n - (int)row0;
       int b = 0;
-      for (int c = 0; c < plan.n_chunks; ++c) {
-        const ChunkSpec& ch = plan.chunk[c];
-        if (ch.special < 0) {
-          const bool mine = (ch.hid & 1) == grp;
-          if (mine && lead) stamp(p, tile_it, c, 0);
-          // Both groups observe EVERY phase of acc_full[b], their own chunks and the other group's: a parity wait is only
-          // sound when the waiter is at most one phase behind.  (The other group's chunk was issued before this group's next
+      for (int c = 0; c < n_chunks_h; ++c) {
+        const uint4 rec = sl->erec[c];
+        if ((rec.y >> 25) & 1u) {                                         // hidden-layer chunk
+          const bool mine = ((rec.y >> 24) & 1u) == (uint32_t)pair;
+          if (mine && lead) stamp<kDebug>(p, tile_it, c, 0);
+          // Every group observes EVERY phase of acc_full[b], its own chunks and the other pair's: a parity wait is only
+          // sound when the waiter is at most one phase behind.  (The other pair's chunk was issued before this pair's next
           // one, so this never delays useful work.)
-#pragma unroll
-          for (int bb = 0; bb < NACC; ++bb) if (bb == b) mbar_wait(&sl->acc_full[bb], acc_par[bb], p.err_flag, 4);
+          mbar_wait(&sl->acc_full[b], (par >> b) & 1u, p.err_flag, 4);
+          par ^= 1u << b;
           if (mine) {
-            const LayerSpec& L = plan.layer[ch.layer];
             const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
             tc_fence_after();
-            if (lead) stamp(p, tile_it, c, 1);
-            if (p.dump_layer == (int)ch.layer) {                          // debug hook: raw accumulator to global
-              for (int c0 = 0; c0 < ch.nc; c0 += 16) {
-                uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
-                if (valid) for (int j = 0; j < 16; ++j) if (ch.n0 + c0 + j < L.n_real) p.dump_out[(row0 + t) * L.n_real + ch.n0 + c0 + j] = __uint_as_float(r[j]);
+            if (lead) stamp<kDebug>(p, tile_it, c, 1);
+            const int n0 = (int)(rec.x & 0xFFFFu), nc = (int)(rec.x >> 16);
+            const uint32_t out_col = rec.y & 0xFFFFu;
+            const int n_real = (int)(rec.z & 0xFFFFu), np = (int)(rec.z >> 16), next_kp = (int)rec.w;
+            // column halves: 64 -> 32|32, 48 -> 32|16, 32 -> 16|16, 16 -> 16|0
+            const int w0 = (((nc >> 4) + 1) >> 1) << 4;
+            const int h0 = n0 + (half ? w0 : 0), hn = half ? nc - w0 : w0;
+            if (kDebug && p.dump_layer == (int)plan.chunk[c].layer) {     // debug hook: raw accumulator to global
+              const int64_t row0 = (int64_t)tile * TILE_M; const int t = q * 32 + lane;
+              for (int c0 = 0; c0 < hn; c0 += 16) {
+                uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)(h0 - n0 + c0), r); tmem_ld_wait();
+                if (t < n - (int)row0) for (int j = 0; j < 16; ++j) if (h0 + c0 + j < n_real) p.dump_out[(row0 + t) * n_real + h0 + c0 + j] = __uint_as_float(r[j]);
               }
             }
-            if (L.kind == HID_SILU) hidden_chunk<true>(lane_base, acc_col, L, ch.n0, ch.nc);
-            else hidden_chunk<false>(lane_base, acc_col, L, ch.n0, ch.nc);
-            tmem_st_wait(); tc_fence_before();
-#pragma unroll
-            for (int bb = 0; bb < NACC; ++bb) if (bb == b) mbar_arrive(&sl->acc_free[bb]);   // accumulator drained, activations visible
-            if (lead) stamp(p, tile_it, c, 2);
+            if (hn > 0) {
+              if (((rec.y >> 16) & 0xFFu) == HID_SILU) hidden_half<true>(lane_base, acc_col + (uint32_t)(h0 - n0), out_col, n_real, np, next_kp, h0, hn);
+              else hidden_half<false>(lane_base, acc_col + (uint32_t)(h0 - n0), out_col, n_real, np, next_kp, h0, hn);
+              tmem_st_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&sl->acc_free[b]);                                // accumulator drained, activations visible
+            if (lead) stamp<kDebug>(p, tile_it, c, 2);
           }
-#pragma unroll
-          for (int bb = 0; bb < NACC; ++bb) if (bb == b) acc_par[bb] ^= 1u;      // every hidden commit into b flips its phase, mine or not
         }
         if (++b == NACC) b = 0;
       }
     }
-  } else if (warp >= GROUP_C_WARP0) {
-    // ===================== group C (warps 4-7): output chunks, noise, hooks, stores, next tile's prologue =====================
+  } else if (warp < GROUP_C_WARP0 + 4) {
+    // ===================== group C (warps 0-3): output chunks, next tile's prologue =====================
     const int q = warp & 3;
     const int t = q * 32 + lane;                                          // trajectory row of the tile == TMEM lane
     const int ct = threadIdx.x - GROUP_C_WARP0 * 32;                      // 0..127
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int kp0 = plan.layer[0].kp;
-    const int first_model = plan.n_policy_chunks;                        // chunk index of trunk0's first chunk; layer index = that chunk's layer
+    const int first_model = plan.n_policy_chunks;                        // chunk index of trunk0's first chunk
     const int kpm = plan.layer[plan.chunk[first_model].layer].kp;
     const uint32_t xm_col = (uint32_t)plan.layer[plan.chunk[first_model].layer].a_col;
     const uint32_t xp_col = (uint32_t)plan.layer[0].a_col;
@@ -537,155 +593,202 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
     // (state_dim <= 15); wider inputs share columns with the log-var head's activations and are staged once those are dead.
     const bool early_prologue = xp_col == TM_XP;
 
-    auto prefetch = [&](int tile, int buf) {                              // cp.async, 4 B granules into the padded rows
-      const int64_t r0 = (int64_t)tile * TILE_M;
-      const int rws = min(TILE_M, n - (int)r0);
-      float* dst = st_s + buf * TILE_M * p.SP;
-      for (int i = ct; i < rws * S; i += GROUP_THREADS) { const int r = i / S, c = i - r * S; cp_async4(dst + r * p.SP + c, p.cur + r0 * S + i); }
-      cp_async_commit();
-    };
-    // tile prologue: policy input [s, 1] -> TMEM, normalised state -> model-input row, policy noise -> smem
-    auto prologue = [&](int tile, int buf, uint32_t tile_it) {
-      if (ct == 0) stamp(p, tile_it, 0, 6);
-      cp_async_wait_all();
-      named_bar_sync(1, GROUP_THREADS);                                   // the tile's states landed (all of group C's copies)
-      const int rows = min(TILE_M, n - tile * TILE_M);
-      const float* my_s = st_s + buf * TILE_M * p.SP + t * p.SP;
-      float* my_o = st_o + buf * TILE_M * p.OP + t * p.OP;
-      write_input_row(lane_base, xp_col, my_s, kp0);
-      for (int c = 0; c < S; ++c) my_o[c] = (my_s[c] - sl->norm_mean[c]) * sl->norm_inv[c];          // src/dynamics.py:113
-      const int64_t id = t < rows ? (int64_t)p.ids[(int64_t)tile * TILE_M + t] : 0;
-      const float4 e4 = t < rows ? noise_get4(p.noise_p, id, 0, A) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(st_np + t * 4) = e4;
-      tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->tile_ready);
-      if (ct == 0) stamp(p, tile_it, 0, 7);
-    };
-
-    if ((int)blockIdx.x < n_tiles) { prefetch(blockIdx.x, 0); prologue(blockIdx.x, 0, 0); }
+    // Program of group C: one prologue per tile (tile 0 before its chunks, tile i+1 inside tile i), three output epilogues per
+    // tile, one prefetch per tile.  A single loop with pending-work flags keeps one copy of each piece of code (instruction cache).
     uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    int tile = blockIdx.x;
+    int pf_tile = tile < n_tiles ? tile : -1, pf_buf = 0;                 // pending prefetch (cp.async of a tile's states and noise)
+    bool need_prologue = tile < n_tiles;                                  // pending prologue of `ptile` into buffer `pbuf`
+    int ptile = tile, pbuf = 0; uint32_t pit = 0;
+    int c = -1, b = NACC - 1;                                             // chunk cursor of the current tile (-1: before the first chunk)
+    while (tile < n_tiles) {
+      if (pf_tile >= 0) {
+        const int64_t r0 = (int64_t)pf_tile * TILE_M;
+        const int rws = min(TILE_M, n - (int)r0);
+        float* dst = st_s + pf_buf * TILE_M * p.SP;
+        for (int i = ct; i < rws * S; i += GROUP_THREADS) { const int r = i / S, cc = i - r * S; cp_async4(dst + r * p.SP + cc, p.cur + r0 * S + i); }
+        if (ct < rws) cp_async16(st_np + (pf_buf * TILE_M + ct) * 4, p.eps_p + (r0 + ct) * 4);
+        if (p.NM > 0) {
+          const int pieces = p.NMG >> 2;
+          for (int i = ct; i < rws * pieces; i += GROUP_THREADS) { const int r = i / pieces, cc = i - r * pieces; cp_async16(st_nm + (pf_buf * TILE_M + r) * p.NM + 4 * cc, p.eps_m + (r0 + r) * p.NMG + 4 * cc); }
+        }
+        cp_async_commit();
+        pf_tile = -1;
+      }
+      if (need_prologue) {
+        // ---- tile prologue: policy input [s, 1] -> TMEM, normalised state -> model-input row ----
+        if (ct == 0) stamp<kDebug>(p, pit, 0, 6);
+        cp_async_wait_all();
+        named_bar_sync(1, GROUP_THREADS);                                 // the tile's states and noise landed (all of group C's copies)
+        const float* ps = st_s + pbuf * TILE_M * p.SP + t * p.SP;
+        float* po = st_o + pbuf * TILE_M * p.OP + t * p.OP;
+        write_input_row(lane_base, xp_col, ps, kp0);
+        for (int cc = 0; cc < S; ++cc) po[cc] = (ps[cc] - sl->norm_mean[cc]) * sl->norm_inv[cc];        // src/dynamics.py:113
+        tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->tile_ready);
+        if (ct == 0) stamp<kDebug>(p, pit, 0, 7);
+        need_prologue = false;
+        if (ptile == tile && c < 0) {                                     // that was the first tile's own prologue: prefetch its successor
+          const int nt = tile + (int)gridDim.x;
+          if (nt < n_tiles) { pf_tile = nt; pf_buf = 1; }
+        }
+        continue;
+      }
+      // ---- advance to the tile's next output chunk ----
+      do { ++c; if (++b == NACC) b = 0; } while (c < plan.n_chunks && plan.chunk[c].special < 0);
+      if (c >= plan.n_chunks) {                                           // tile finished
+        tile += gridDim.x; ++tile_it; c = -1; b = NACC - 1;
+        const int nt = tile + (int)gridDim.x;
+        if (tile < n_tiles && nt < n_tiles) { pf_tile = nt; pf_buf = (tile_it & 1) ^ 1; }   // buffers were last read by the finished tile's epilogues
+        continue;
+      }
       const int buf = tile_it & 1;
       const int64_t row0 = (int64_t)tile * TILE_M;
       const int rows = min(TILE_M, n - (int)row0);
       const bool valid = t < rows;
       const int64_t row = row0 + t;
-      const int64_t id = valid ? (int64_t)p.ids[row] : 0;                // global trajectory id (noise key)
       const float* my_s = st_s + buf * TILE_M * p.SP + t * p.SP;
       float* my_o = st_o + buf * TILE_M * p.OP + t * p.OP;
       const int next_tile = tile + (int)gridDim.x;
-      if (next_tile < n_tiles) prefetch(next_tile, buf ^ 1);            // buffer buf^1 was last read by the previous tile's diff-head epilogue
-      const uint32_t par = tile_it & 1;
-      int b = 0;
-      for (int c = 0; c < plan.n_chunks; ++c, b = (b + 1 == NACC ? 0 : b + 1)) {
-        const ChunkSpec& ch = plan.chunk[c];
-        if (ch.special < 0) continue;
-        const LayerSpec& L = plan.layer[ch.layer];
-        const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
-        const int sp = ch.special;
-        if (ct == 0) stamp(p, tile_it, c, 0);
-        mbar_wait(&sl->sp_full[sp], par, p.err_flag, 7);
-        tc_fence_after();
-        if (ct == 0) stamp(p, tile_it, c, 1);
-        if (p.dump_layer == (int)ch.layer) {                              // debug hook: raw accumulator to global
-          for (int c0 = 0; c0 < ch.nc; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
-            if (valid) for (int j = 0; j < 16; ++j) if (ch.n0 + c0 + j < L.n_real) p.dump_out[row * L.n_real + ch.n0 + c0 + j] = __uint_as_float(r[j]);
+      const ChunkSpec& ch = plan.chunk[c];
+      const LayerSpec& L = plan.layer[ch.layer];
+      const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
+      const int sp = ch.special;
+      if (ct == 0) stamp<kDebug>(p, tile_it, c, 0);
+      mbar_wait(&sl->sp_full[sp], tile_it & 1, p.err_flag, 7);
+      tc_fence_after();
+      if (ct == 0) stamp<kDebug>(p, tile_it, c, 1);
+      if (kDebug && p.dump_layer == (int)ch.layer) {                      // debug hook: raw accumulator to global
+        for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+          uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
+          if (valid) for (int j = 0; j < 16; ++j) if (ch.n0 + c0 + j < L.n_real) p.dump_out[row * L.n_real + ch.n0 + c0 + j] = __uint_as_float(r[j]);
+        }
+      }
+      if (L.kind == OUT_POLICY) {
+        // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
+        uint32_t r[16]; tmem_ld16(lane_base + acc_col, r); tmem_ld_wait();
+        const float4 e4 = *reinterpret_cast<const float4*>(st_np + (buf * TILE_M + t) * 4);
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        const float mu4[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
+        float raw4[4] = {0.f, 0.f, 0.f, 0.f};                              // raw_j = out[A + j], statically indexed per A
+        if (A == 1) { raw4[0] = __uint_as_float(r[1]); }
+        else if (A == 2) { raw4[0] = __uint_as_float(r[2]); raw4[1] = __uint_as_float(r[3]); }
+        else if (A == 3) { raw4[0] = __uint_as_float(r[3]); raw4[1] = __uint_as_float(r[4]); raw4[2] = __uint_as_float(r[5]); }
+        else { raw4[0] = __uint_as_float(r[4]); raw4[1] = __uint_as_float(r[5]); raw4[2] = __uint_as_float(r[6]); raw4[3] = __uint_as_float(r[7]); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < A) {
+            const float sd = __expf(-6.f + __fdividef(10.f, 1.f + __expf(-raw4[j])));
+            const float a = tanh_fast(fmaf(ev[j], sd, mu4[j]));
+            my_o[S + j] = a;
+            if (valid) p.actions[row * A + j] = a;
           }
         }
-        if (L.kind == OUT_POLICY) {
-          // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
-          uint32_t r[16]; tmem_ld16(lane_base + acc_col, r); tmem_ld_wait();
-          const float4 e4 = *reinterpret_cast<const float4*>(st_np + t * 4);
-          const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-          const float mu4[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
-          float raw4[4] = {0.f, 0.f, 0.f, 0.f};                            // raw_j = out[A + j], statically indexed per A
-          if (A == 1) { raw4[0] = __uint_as_float(r[1]); }
-          else if (A == 2) { raw4[0] = __uint_as_float(r[2]); raw4[1] = __uint_as_float(r[3]); }
-          else if (A == 3) { raw4[0] = __uint_as_float(r[3]); raw4[1] = __uint_as_float(r[4]); raw4[2] = __uint_as_float(r[5]); }
-          else { raw4[0] = __uint_as_float(r[4]); raw4[1] = __uint_as_float(r[5]); raw4[2] = __uint_as_float(r[6]); raw4[3] = __uint_as_float(r[7]); }
+        // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written by the prologue  (src/dynamics.py:113-114)
+        write_input_row(lane_base, xm_col, my_o, kpm);
+        tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
+        if (ct == 0) stamp<kDebug>(p, tile_it, c, 2);
+        // off the critical path: the next tile's prologue
+        if (early_prologue && next_tile < n_tiles) { need_prologue = true; ptile = next_tile; pbuf = buf ^ 1; pit = tile_it + 1; }
+      } else if (L.kind == OUT_DIFF) {
+        // ---- diff head: means = diffs + [s, 0]  (kept in shared memory)                   src/dynamics.py:118 ----
+        for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+          uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r);
+          float sv[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < A) {
-              const float sd = __expf(-6.f + __fdividef(10.f, 1.f + __expf(-raw4[j])));
-              const float a = tanh_fast(fmaf(ev[j], sd, mu4[j]));
-              my_o[S + j] = a;
-              if (valid) p.actions[row * A + j] = a;
-            }
-          }
-          // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written by the prologue  (src/dynamics.py:113-114)
-          write_input_row(lane_base, xm_col, my_o, kpm);
-          tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
-          if (ct == 0) stamp(p, tile_it, c, 2);
-          // ---- off the critical path: this tile's model noise, then the next tile's prologue ----
-          if (p.NM > 0) {
-            for (int cg = 0; 4 * cg < O; ++cg) {
-              const float4 m4 = valid ? noise_get4(p.noise_m, id, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(st_nm + t * p.NM + 4 * cg) = m4;
-            }
-          }
-          if (early_prologue && next_tile < n_tiles) prologue(next_tile, buf ^ 1, tile_it + 1);
-        } else if (L.kind == OUT_DIFF) {
-          // ---- diff head: means = diffs + [s, 0]  (kept in shared memory)                   src/dynamics.py:118 ----
-          for (int c0 = 0; c0 < ch.nc; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
+          for (int j = 0; j < 16; ++j) sv[j] = (c0 + j < S) ? my_s[c0 + j] : 0.f;
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int cc = c0 + j;
-              if (cc < O) my_o[cc] = __uint_as_float(r[j]) + (cc < S ? my_s[cc] : 0.f);
-            }
-          }
-          tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
-          if (ct == 0) stamp(p, tile_it, c, 2);
-        } else {
-          // ---- log-var head + Gaussian sample + hooks                                       src/dynamics.py:119-121,201-203 ----
-          for (int c0 = 0; c0 < ch.nc; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r); tmem_ld_wait();
-            if (c0 + 16 >= ch.nc) { tc_fence_before(); mbar_arrive(&sl->sp_free[sp]); }      // accumulator in registers: release it early
-#pragma unroll
-            for (int jg = 0; jg < 4; ++jg) {
-              const int cg = (c0 >> 2) + jg;
-              if (4 * cg < O) {
-                float4 e4;
-                if (p.NM > 0) e4 = *reinterpret_cast<const float4*>(st_nm + t * p.NM + 4 * cg);
-                else e4 = valid ? noise_get4(p.noise_m, id, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int cc = 4 * cg + k;
-                  if (cc < O) {
-                    const float u = __expf(sl->lv_hi[cc] - __uint_as_float(r[4 * jg + k]));
-                    const float sd = sl->lv_s0[cc] * sqrtf(1.f + __fdividef(sl->lv_E[cc], 1.f + u));
-                    my_o[cc] = fmaf(sd, ev[k], my_o[cc]);
-                  }
-                }
-              }
-            }
-          }
-          // wide policy inputs: the log-var head's MMAs are complete, its activations are dead -> stage the next tile now
-          if (!early_prologue && next_tile < n_tiles) prologue(next_tile, buf ^ 1, tile_it + 1);
-          if (valid) {
-            HookOut ho;
-            eval_hooks(p.env, [my_o](int d) { return my_o[d]; }, ho);
-            p.rewards[row] = my_o[S]; p.done[row] = ho.done; p.viol[row] = ho.viol;
-#pragma unroll
-            for (int cc = 0; cc < DRPO_MAX_CON; ++cc) if (cc < p.C) p.cv[row * p.C + cc] = ho.cv[cc];
-          }
-          named_bar_sync(2, GROUP_THREADS);                              // every row of the tile is final in st_o
-          const float* so = st_o + buf * TILE_M * p.OP;
-          for (int i = ct; i < rows * S; i += GROUP_THREADS) {            // coalesced store of the tile's next states
-            const int r = i / S, cc = i - r * S;
-            p.next_states[row0 * S + i] = so[r * p.OP + cc];
-          }
-          named_bar_sync(2, GROUP_THREADS);                              // st_o[buf] is rewritten two prologues from now by other threads
-          my_o[S + A] = 1.f;                                             // restore the bias slot if the reward column overwrote it (A == 0 never)
-          if (ct == 0) stamp(p, tile_it, c, 2);
+          for (int j = 0; j < 16; ++j) if (c0 + j < O) my_o[c0 + j] = __uint_as_float(r[j]) + sv[j];
         }
+        tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
+        if (ct == 0) stamp<kDebug>(p, tile_it, c, 2);
+      } else {
+        // ---- log-var head + Gaussian sample                                              src/dynamics.py:119-121,201-203 ----
+        for (int c0 = 0; c0 < ch.nc; c0 += 16) {
+          uint32_t r[16]; tmem_ld16(lane_base + acc_col + (uint32_t)c0, r);
+          // loads first, math second, stores last: the shared-memory stores of one column never fence the next column's loads
+          float ev[16], res[16];
+#pragma unroll
+          for (int jg = 0; jg < 4; ++jg) {
+            const int cg = (c0 >> 2) + jg;
+            float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * cg < O) {
+              if (p.NM > 0) e4 = *reinterpret_cast<const float4*>(st_nm + (buf * TILE_M + t) * p.NM + 4 * cg);
+              else if (valid) e4 = *reinterpret_cast<const float4*>(p.eps_m + row * p.NMG + 4 * cg);
+            }
+            ev[4 * jg] = e4.x; ev[4 * jg + 1] = e4.y; ev[4 * jg + 2] = e4.z; ev[4 * jg + 3] = e4.w;
+          }
+          tmem_ld_wait();
+          if (c0 + 16 >= ch.nc) { tc_fence_before(); mbar_arrive(&sl->sp_free[sp]); }        // accumulator in registers: release it early
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int cc = min(c0 + j, O - 1);
+            const float u = __expf(sl->lv_hi[cc] - __uint_as_float(r[j]));
+            res[j] = fmaf(sl->lv_s0[cc] * sqrt_fast(1.f + __fdividef(sl->lv_E[cc], 1.f + u)), ev[j], my_o[cc]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j < O) my_o[c0 + j] = res[j];
+        }
+        if (valid) p.rewards[row] = my_o[S];
+        named_bar_sync(2, GROUP_THREADS);                                // every row of the tile is final in st_o
+        const float* so = st_o + buf * TILE_M * p.OP;
+        for (int i = ct; i < rows * S; i += GROUP_THREADS) {              // coalesced store of the tile's next states
+          const int r = i / S, cc = i - r * S;
+          p.next_states[row0 * S + i] = so[r * p.OP + cc];
+        }
+        named_bar_sync(2, GROUP_THREADS);                                // st_o[buf] is rewritten two prologues from now by other threads
+        my_o[S + A] = 1.f;                                               // restore the bias slot if the reward column overwrote it (A == 0 never)
+        if (ct == 0) stamp<kDebug>(p, tile_it, c, 2);
+        // wide policy inputs: the log-var head's MMAs are complete, its activations are dead -> stage the next tile now
+        if (!early_prologue && next_tile < n_tiles) { need_prologue = true; ptile = next_tile; pbuf = buf ^ 1; pit = tile_it + 1; }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem, TM_COLS);
+}
+
+// This step's noise, row-compact: Philox(seed, global trajectory id) or the injected draws gathered by trajectory id.
+__global__ void __launch_bounds__(256) noise_stage_kernel(const int32_t* __restrict__ ids, const int* n_dev, int64_t n_max, NoiseView np_, NoiseView nm_,
+                                                          int A, int O, int NMG, float* __restrict__ eps_p, float* __restrict__ eps_m) {
+  const int64_t n = min((int64_t)*n_dev, n_max);
+  const int pieces = 1 + (NMG >> 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * pieces; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pieces; const int c = (int)(i - r * pieces);
+    const int64_t id = ids[r];
+    if (c == 0) *reinterpret_cast<float4*>(eps_p + r * 4) = noise_get4(np_, id, 0, A);
+    else *reinterpret_cast<float4*>(eps_m + r * NMG + 4 * (c - 1)) = noise_get4(nm_, id, c - 1, O);
+  }
+}
+
+// check_done / check_violation / get_constraint_values of the step's next states (src/smbpo.py:238-240) fused with
+// buffer.extend: the step's rows go into the ring at (base + r) % capacity (src/sampling.py:128-145, src/smbpo.py:241-242,248).
+__global__ void __launch_bounds__(256) hooks_store_kernel(drpo_env_params env, drpo_buffer buf, const RolloutState* st, const int32_t* n_dev,
+                                                          const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ ns,
+                                                          const float* __restrict__ rew, uint8_t* __restrict__ done_out) {
+  const int64_t n = *n_dev, base = st->base, cap = buf.capacity;
+  const int S = buf.state_dim, A = buf.action_dim, C = buf.con_dim;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = t0; i < n * S; i += stride) {
+    const int64_t r = i / S; const int c = (int)(i - r * S); const int64_t slot = (base + r) % cap;
+    buf.states[slot * S + c] = s[i];
+    buf.next_states[slot * S + c] = ns[i];
+  }
+  for (int64_t i = t0; i < n * A; i += stride) {
+    const int64_t r = i / A; const int c = (int)(i - r * A);
+    buf.actions[((base + r) % cap) * A + c] = a[i];
+  }
+  for (int64_t r = t0; r < n; r += stride) {
+    const float* row = ns + r * S;
+    HookOut ho;
+    eval_hooks(env, [row](int d) { return row[d]; }, ho);
+    const int64_t slot = (base + r) % cap;
+    buf.rewards[slot] = rew[r]; buf.dones[slot] = ho.done; buf.violations[slot] = ho.viol;
+    done_out[r] = ho.done;
+#pragma unroll
+    for (int cc = 0; cc < DRPO_MAX_CON; ++cc) if (cc < C) buf.constraint_values[slot * C + cc] = ho.cv[cc];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -738,6 +841,32 @@ static int build_plan(const drpo_rollout_args& a, NetPlan& P) {
   add_layer(P, S + 1, Hm, OUT_DIFF, TM_D1, 0, 5, 1, hid, off);          // 7 diffs
   add_layer(P, S + 1, Hm, OUT_LOGVAR, TM_L1, 0, 6, 2, hid, off);        // 8 log-vars
   P.model_bytes = off;
+  for (int l = 0; l < P.n_layers; ++l) {
+    const LayerSpec& L = P.layer[l];
+    for (int c = 0; c < L.n_chunks; ++c) {
+      const int ci = L.first_chunk + c; const ChunkSpec& ch = P.chunk[ci];
+      const uint32_t sbo = (uint32_t)(L.kp >> 3) * 128u;
+      uint4 ir, er;
+      ir.x = make_idesc(ch.nc);
+      ir.y = ((sbo >> 4) & 0x3FFFu) | (1u << 14);                       // descriptor bits 32..45 = SBO, bit 46 = version 1
+      ir.z = (uint32_t)L.a_col | ((uint32_t)(L.kp >> 4) << 16) | ((uint32_t)(ch.special + 1) << 24);
+      ir.w = 0;
+      if (c == 0 && L.dep >= 0) {
+        const LayerSpec& D = P.layer[L.dep];
+        const int last = D.first_chunk + D.n_chunks - 1;
+        uint32_t kA = 0, kB = 0, bufA = 0, bufB = 0;
+        if (ci - last <= NACC) { bufB = 1 + last % NACC; kB = P.chunk[last].n0 >> 4; }
+        if (D.n_chunks > 1 && ci - (last - 1) <= NACC) { bufA = 1 + (last - 1) % NACC; kA = P.chunk[last - 1].n0 >> 4; }
+        if (!bufB) kB = kA;                                               // (cannot happen: last is younger than last-1)
+        ir.w = kA | (kB << 8) | (bufA << 16) | (bufB << 20);
+      }
+      er.x = (uint32_t)ch.n0 | ((uint32_t)ch.nc << 16);
+      er.y = (uint32_t)L.out_col | ((uint32_t)L.kind << 16) | ((uint32_t)(ch.hid & 1) << 24) | ((ch.special < 0 ? 1u : 0u) << 25);
+      er.z = (uint32_t)L.n_real | ((uint32_t)L.np << 16);
+      er.w = (uint32_t)L.next_kp;
+      P.irec[ci] = ir; P.erec[ci] = er;
+    }
+  }
   // the accumulator rotation (chunk % NACC) and the group alternation (hid % 2) must repeat identically every tile, and
   // each output layer must be exactly one chunk
   if (P.n_chunks % NACC != 0 || hid % 2 != 0 || P.layer[2].n_chunks != 1 || P.layer[7].n_chunks != 1 || P.layer[8].n_chunks != 1) {
@@ -763,12 +892,13 @@ static int pack_net(const drpo_linear* lin, const NetPlan& P, int first_layer, i
   return DRPO_OK;
 }
 
-static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP, int& NM) {
+static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP, int& NM, int& NMG) {
   SP = P.layer[0].kp | 1;                                  // state row [s, 1, 0..] padded to the first layer's K
   OP = P.layer[3].kp | 1;                                  // [norm s, a, 1, 0..] padded to trunk0's K; later [next state, reward]
-  NM = (S + 1) <= 16 ? round_up(S + 1, 4) : 0;             // staged model noise (wide states draw it inline)
+  NMG = round_up(S + 1, 4);                                // row length of the step's model-noise array in global memory
+  NM = (S + 1) <= 16 ? NMG + 4 : 0;                        // staged copy (+4: conflict-free float4 rows); wide states read global
   const uint32_t slot = (P.max_chunk_bytes + 1023u) & ~1023u;
-  return (int)(slot * stages + (size_t)TILE_M * (2 * SP + 2 * OP + 4 + NM) * 4 + sizeof(SmemLayout) + 64);
+  return (int)(slot * stages + (size_t)TILE_M * (2 * SP + 2 * OP + 2 * 4 + 2 * NM) * 4 + sizeof(SmemLayout) + 64);
 }
 
 }  // namespace umma
@@ -778,25 +908,39 @@ using namespace umma;
 int64_t umma_rollout_ws_bytes(const drpo_rollout_args& a) {
   NetPlan P;
   if (build_plan(a, P) != DRPO_OK) return 0;
-  return rollout_ws_bytes_fp32(a) + (int64_t)align_up(P.policy_bytes, 1024) + (int64_t)a.ensemble->ensemble_size * align_up(P.model_bytes, 1024) + 4096;
+  const int64_t noise_bytes = a.batch * (4 + round_up(a.ensemble->state_dim + 1, 4)) * 4 + 1024;
+  return rollout_ws_bytes_fp32(a) + noise_bytes + (int64_t)align_up(P.policy_bytes, 1024) +
+         (int64_t)a.ensemble->ensemble_size * align_up(P.model_bytes, 1024) + 4096;
 }
 
 int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_out) {
   NetPlan P; int rc;
   if ((rc = build_plan(a, P))) return rc;
-  const int64_t B = a.batch; const int S = a.ensemble->state_dim, A = a.ensemble->action_dim, C = a.env->con_dim;
+  const int64_t B = a.batch; const int S = a.ensemble->state_dim, A = a.ensemble->action_dim;
   const int H = dump_layer >= 0 ? 1 : a.horizon; void* stream = a.stream;
   if (dump_layer >= P.n_layers && dump_layer != 100) { set_error("debug dump: layer %d out of range", dump_layer); return DRPO_ERR_ARG; }
+  if (a.env->con_dim > DRPO_MAX_CON) { set_error("con_dim %d > %d", a.env->con_dim, DRPO_MAX_CON); return DRPO_ERR_ARG; }
+  int dev = 0, sms = 148, max_smem = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int SP, OP, NM, NMG, stages = MAX_STAGES;
+  while (stages > 2 && smem_bytes_for(P, S, stages, SP, OP, NM, NMG) > max_smem) --stages;
+  const int smem = smem_bytes_for(P, S, stages, SP, OP, NM, NMG);
+  if (smem > max_smem) { set_error("bf16 rollout: needs %d B of shared memory, device offers %d", smem, max_smem); return DRPO_ERR_UNSUPPORTED; }
+
   Arena ar(a.workspace, a.workspace_bytes);
   RolloutScratch w;
   w.curA = ar.take<float>(B * S); w.curB = ar.take<float>(B * S); w.actions = ar.take<float>(B * A);
-  w.next_states = ar.take<float>(B * S); w.rewards = ar.take<float>(B); w.cv = ar.take<float>(B * C);
-  w.done = ar.take<uint8_t>(B); w.viol = ar.take<uint8_t>(B);
+  w.next_states = ar.take<float>(B * S); w.rewards = ar.take<float>(B);
+  w.done = ar.take<uint8_t>(B);
   w.idsA = ar.take<int32_t>(B); w.idsB = ar.take<int32_t>(B); w.n_alive = ar.take<int32_t>(a.horizon + 2);
   const int nblocks = (int)((B + CBLK - 1) / CBLK);
   w.block_counts = ar.take<int32_t>(nblocks + 1);
   w.st = ar.take<RolloutState>(1);
   int* err_flag = ar.take<int>(4);
+  float* eps_p = ar.take<float>(B * 4);
+  float* eps_m = ar.take<float>(B * NMG);
   uint8_t* pol_img = ar.take<uint8_t>(align_up(P.policy_bytes, 1024));
   const int E = a.ensemble->ensemble_size;
   uint8_t* mem_img = ar.take<uint8_t>((int64_t)E * align_up(P.model_bytes, 1024));
@@ -815,15 +959,8 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
       if ((rc = pack_net(ml, P, 3, 6, mem_img + (int64_t)m * align_up(P.model_bytes, 1024), stream))) return rc;
     }
   }
-  int dev = 0, sms = 148, max_smem = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int SP, OP, NM, stages = MAX_STAGES;
-  while (stages > 2 && smem_bytes_for(P, S, stages, SP, OP, NM) > max_smem) --stages;
-  const int smem = smem_bytes_for(P, S, stages, SP, OP, NM);
-  if (smem > max_smem) { set_error("bf16 rollout: needs %d B of shared memory, device offers %d", smem, max_smem); return DRPO_ERR_UNSUPPORTED; }
-  DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 
   DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));
   DRPO_CUDA_OK(cudaMemcpyAsync(w.curA, a.initial_states, sizeof(float) * B * S, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -832,19 +969,21 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
   const int grid = (int)std::min<int64_t>(sms, (B + TILE_M - 1) / TILE_M);
   for (int t = 0; t < H; ++t) {
     const int* n_dev = w.n_alive + t;
+    // this step's Gaussian draws, keyed by global trajectory id (torch.normal in policy.act, randn_like in ensemble.sample)
+    NoiseView np_ = make_noise(a.eps_policy ? a.eps_policy + (int64_t)t * a.eps_batch_stride * A : nullptr, A, a.seed, TAG_ROLLOUT_POLICY, (uint32_t)t);
+    NoiseView nm_ = make_noise(a.eps_model ? a.eps_model + (int64_t)t * a.eps_batch_stride * (S + 1) : nullptr, S + 1, a.seed, TAG_ROLLOUT_MODEL, (uint32_t)t);
+    DRPO_LAUNCH(noise_stage_kernel, grid_for(B * (1 + NMG / 4)), 256, 0, stream, ids, n_dev, B, np_, nm_, A, S + 1, NMG, eps_p, eps_m);
     StepParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.plan = P; sp.policy_img = pol_img; sp.model_img = mem_img + (int64_t)a.member_idx_host[t] * align_up(P.model_bytes, 1024);
-    sp.cur = cur; sp.ids = ids; sp.n_dev = n_dev; sp.n_max = B;
-    sp.actions = w.actions; sp.next_states = w.next_states; sp.rewards = w.rewards; sp.cv = w.cv; sp.done = w.done; sp.viol = w.viol;
+    sp.cur = cur; sp.n_dev = n_dev; sp.n_max = B; sp.eps_p = eps_p; sp.eps_m = eps_m;
+    sp.actions = w.actions; sp.next_states = w.next_states; sp.rewards = w.rewards;
     sp.norm_mean = a.ensemble->norm_mean; sp.norm_std = a.ensemble->norm_std; sp.min_lv = a.ensemble->min_log_var; sp.max_lv = a.ensemble->max_log_var;
-    sp.noise_p = make_noise(a.eps_policy ? a.eps_policy + (int64_t)t * a.eps_batch_stride * A : nullptr, A, a.seed, TAG_ROLLOUT_POLICY, (uint32_t)t);
-    sp.noise_m = make_noise(a.eps_model ? a.eps_model + (int64_t)t * a.eps_batch_stride * (S + 1) : nullptr, S + 1, a.seed, TAG_ROLLOUT_MODEL, (uint32_t)t);
-    sp.env = *a.env; sp.S = S; sp.A = A; sp.C = C; sp.SP = SP; sp.OP = OP; sp.NM = NM; sp.stages = stages; sp.err_flag = err_flag;
+    sp.S = S; sp.A = A; sp.SP = SP; sp.OP = OP; sp.NM = NM; sp.NMG = NMG; sp.stages = stages; sp.err_flag = err_flag;
     sp.dump_layer = dump_layer; sp.dump_out = dump_out;
-    DRPO_LAUNCH(rollout_step_umma_kernel, grid, NUM_THREADS, smem, stream, sp);
-    DRPO_LAUNCH(rollout_store_kernel, grid_for(B * S), 256, 0, stream, a.virt, w.st, n_dev, cur, w.actions, w.next_states,
-                w.rewards, w.done, w.viol, w.cv);
+    if (dump_layer >= 0) { DRPO_LAUNCH(rollout_step_umma_kernel<true>, grid, NUM_THREADS, smem, stream, sp); }
+    else { DRPO_LAUNCH(rollout_step_umma_kernel<false>, grid, NUM_THREADS, smem, stream, sp); }
+    DRPO_LAUNCH(hooks_store_kernel, grid_for(B * S), 256, 0, stream, *a.env, a.virt, w.st, n_dev, cur, w.actions, w.next_states, w.rewards, w.done);
     DRPO_LAUNCH(compact_count_kernel, nblocks, CBLK, 0, stream, w.done, n_dev, w.block_counts);
     DRPO_LAUNCH(compact_scan_kernel, 1, CBLK, 0, stream, w.block_counts, nblocks, w.n_alive, t, w.st, a.step_counts);
     DRPO_LAUNCH(compact_scatter_kernel, nblocks, CBLK, 0, stream, w.done, n_dev, w.block_counts, w.next_states, ids, nxt, ids_n, S);

@@ -43,6 +43,43 @@ __host__ __device__ inline uint32_t make_idesc(int n) { return (1u << 4) | (1u <
 
 // variant: 0 lane==0 branch; 1 elect.sync branch; 2 whole-warp loop + predicated mma; 3 elect branch, 16 MMAs fully unrolled per outer iteration
 // ROT: number of accumulators rotated through (compile time).  issuers: 1 or 2 warps (warp 8 and 9) issuing concurrently.
+// queue-depth probe: issue `reps` x 16 MMAs back to back (unrolled), then stamp: after the issue loop, after commit, after completion
+__global__ void __launch_bounds__(320, 1) queue_probe(int n, int reps, uint32_t* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u + (i & 7);
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (warp == 8) {
+    const uint32_t idesc = make_idesc(n);
+    const uint64_t bdesc = make_desc(smem_u32(smem), 128u, 16 * 128u * 2);
+    const uint32_t dhi = (uint32_t)(bdesc >> 32), dlo0 = (uint32_t)bdesc;
+    if (elect_one()) {
+      const uint32_t t0 = clock();
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) mma_ts(tmem + 128, tmem + 8u * k, dlo0 + 16u * k, dhi, idesc, (r > 0 || k > 0) ? 1u : 0u);
+      }
+      const uint32_t t1 = clock();
+      tc_commit(&bar[0]);
+      const uint32_t t2 = clock();
+      mbar_wait(&bar[0], 0);
+      const uint32_t t3 = clock();
+      out[0] = t1 - t0; out[1] = t2 - t0; out[2] = t3 - t0;
+    }
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 template <int VARIANT, int ROT>
 __global__ void __launch_bounds__(320, 1) issue_bench(int n, int outer, int issuers, uint32_t* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -166,6 +203,15 @@ template <int OP> void run_alu(const char* name) {
 
 int main() {
   cudaMalloc(&d, 256);
+  cudaFuncSetAttribute(queue_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int n : {16, 64}) for (int reps : {1, 2, 4, 8}) {
+    cudaMemset(d, 0, 256);
+    queue_probe<<<1, 320, 64 * 1024>>>(n, reps, d);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("probe failed\n"); return 1; }
+    cudaMemcpy(h, d, 256, cudaMemcpyDeviceToHost);
+    printf("queue probe n=%d: %d MMAs: issue loop done at %u cycles, commit returned at %u, completion seen at %u (exec floor %d)\n", n, 16 * reps, h[0], h[1], h[2], 16 * reps * n / 2);
+  }
+  if (getenv("PROBE_ONLY")) return 0;
   for (int n : {16, 64, 128}) { run_issue<0, 1>(n, 1); run_issue<1, 1>(n, 1); run_issue<2, 1>(n, 1); run_issue<3, 1>(n, 1); }
   for (int n : {16, 64}) { run_issue<1, 2>(n, 1); run_issue<3, 2>(n, 1); run_issue<3, 4>(n, 1); }
   for (int n : {16, 64, 128}) { run_issue<1, 1>(n, 2); run_issue<3, 1>(n, 2); }
