@@ -10,6 +10,15 @@
 namespace drpo {
 static thread_local char g_err[1024] = "";
 int64_t g_launch_count = 0;
+thread_local int g_gemm_mode = 0;
+cublasHandle_t gemm_cublas_handle() {
+  static cublasHandle_t h = nullptr;
+  if (!h) {
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) { h = nullptr; return nullptr; }
+    cublasSetMathMode(h, CUBLAS_TF32_TENSOR_OP_MATH);
+  }
+  return h;
+}
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
@@ -283,8 +292,12 @@ int drpo_critic_step(const drpo_critic_args* a) {
     const drpo_batch& b = a->batch;
     DRPO_CHECK_ARG(b.obs && b.act && b.next_obs && b.rew && b.done && b.cv, "drpo_critic_step: NULL batch tensor");
   }
-  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32, "drpo_critic_step: only DRPO_PREC_FP32 is implemented");
-  return critic_step_fp32(*a);
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16, "drpo_critic_step: unknown precision %d", a->precision);
+  // DRPO_PREC_BF16 = tensor-core mode: the dense contractions run as TF32 tensor-op GEMMs, everything else is unchanged
+  g_gemm_mode = a->precision == DRPO_PREC_BF16 ? 1 : 0;
+  rc = critic_step_fp32(*a);
+  g_gemm_mode = 0;
+  return rc;
 }
 
 int64_t drpo_multiplier_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
@@ -302,8 +315,11 @@ int drpo_multiplier_step(const drpo_multiplier_args* a) {
   DRPO_CHECK_ARG(a->lam.l0.in_dim == a->state_dim + 1 && a->lam.l2.out_dim == 1, "drpo_multiplier_step: multiplier dims disagree");
   DRPO_CHECK_ARG(a->params && a->grads && a->adam_m && a->adam_v && a->losses, "drpo_multiplier_step: NULL arena");
   DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_multiplier_step: bad phases");
-  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32, "drpo_multiplier_step: only DRPO_PREC_FP32 is implemented");
-  return multiplier_step_fp32(*a);
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16, "drpo_multiplier_step: unknown precision %d", a->precision);
+  g_gemm_mode = a->precision == DRPO_PREC_BF16 ? 1 : 0;
+  rc = multiplier_step_fp32(*a);
+  g_gemm_mode = 0;
+  return rc;
 }
 
 }  // extern "C"

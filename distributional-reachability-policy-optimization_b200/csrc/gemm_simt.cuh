@@ -129,10 +129,104 @@ static inline int launch_gemm(const GemmArgs& g, void* stream) {
   return DRPO_OK;
 }
 
+// ---- tensor-core mode (DRPO_PREC_BF16 for the critic / multiplier steps) ---------------------------------------------
+// The plain dense contractions of the critic step go to cuBLAS TF32 tensor-op GEMMs (a library GEMM: the baseline a
+// hand-written tcgen05 critic kernel has to beat); bias + activation, activation-gradient masks and
+// bias gradients (column sums) run as the fused elementwise kernels below.
+}  // namespace drpo
+#include <cublas_v2.h>
+namespace drpo {
+
+extern thread_local int g_gemm_mode;            // 0 = fp32 FMA kernels, 1 = cuBLAS TF32 (set per C-ABI call)
+cublasHandle_t gemm_cublas_handle();            // lazily created, one per process (defined in drpo_api.cu)
+
+#define DRPO_CUBLAS_OK(expr)                                                      \
+  do {                                                                             \
+    cublasStatus_t _s = (expr);                                                    \
+    if (_s != CUBLAS_STATUS_SUCCESS) {                                             \
+      ::drpo::set_error("%s failed: cublas status %d (%s:%d)", #expr, (int)_s, __FILE__, __LINE__); \
+      return DRPO_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+static __global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ Y, int64_t ldy, const float* __restrict__ bias, int M, int N, int act) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N; const int n = (int)(i - m * N);
+    float* y = Y + m * ldy + n;
+    *y = apply_act(*y + (bias ? bias[n] : 0.f), act);
+  }
+}
+static __global__ void __launch_bounds__(256) act_mask_kernel(float* __restrict__ dX, int64_t ldx, const float* __restrict__ saved, int64_t lds, int M, int N, int mode) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N; const int n = (int)(i - m * N);
+    const float mk = saved[m * lds + n];
+    dX[m * ldx + n] *= (mode == 1) ? (mk > 0.f ? 1.f : 0.f) : (1.f - mk * mk);
+  }
+}
+// db[n] = sum_m dY[m,n]: each block sums a slab of rows with float4 loads (a row segment of N floats is one coalesced run),
+// fixed summation order, fp32 partials [slab][N]; one small reducer finishes
+static __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dY, int64_t ldy, int M, int N, int rows_per_block, float* __restrict__ partial) {
+  __shared__ float4 sm[256];
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  const bool vec = (N % 4 == 0) && (ldy % 4 == 0) && N <= 1024;
+  if (vec) {
+    const int n4 = N >> 2, lanes = 256 / n4;                    // row lanes per block (N = 256 -> 4)
+    const int c = threadIdx.x % n4, r = threadIdx.x / n4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < lanes)
+      for (int m = m0 + r; m < m1; m += lanes) {
+        const float4 v = *reinterpret_cast<const float4*>(dY + (int64_t)m * ldy + 4 * c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (r == 0) {
+      for (int k = 1; k < lanes; ++k) { const float4 v = sm[k * n4 + c]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+      *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.y * N + 4 * c) = s;
+    }
+  } else {
+    for (int n = threadIdx.x; n < N; n += 256) {
+      float s = 0.f;
+      for (int m = m0; m < m1; ++m) s += dY[(int64_t)m * ldy + n];
+      partial[(int64_t)blockIdx.y * N + n] = s;
+    }
+  }
+}
+static __global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * N + n];
+  db[n] = s;
+}
+static inline unsigned ew_grid(int64_t work) { int64_t g = (work + 255) / 256; if (g < 1) g = 1; if (g > 148 * 16) g = 148 * 16; return (unsigned)g; }
+
+// row-major C[m,n] (+)= op over row-major operands, expressed in cuBLAS' column-major terms
+static inline int tc_gemm(cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const float* A, int64_t lda, const float* B, int64_t ldb,
+                          float* C, int64_t ldc, float beta, void* stream) {
+  cublasHandle_t h = gemm_cublas_handle();
+  if (!h) { set_error("cuBLAS handle could not be created"); return DRPO_ERR_CUDA; }
+  DRPO_CUBLAS_OK(cublasSetStream(h, (cudaStream_t)stream));
+  const float alpha = 1.f;
+  DRPO_CUBLAS_OK(cublasGemmEx(h, ta, tb, m, n, k, &alpha, A, CUDA_R_32F, (int)lda, B, CUDA_R_32F, (int)ldb, &beta, C, CUDA_R_32F, (int)ldc,
+                              CUBLAS_COMPUTE_32F_FAST_TF32, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
+  ++g_launch_count;
+  return DRPO_OK;
+}
+
 // ---- convenience wrappers -------------------------------------------------------------------------------------
 // Y[M,N] = act(X[M,K] W[N,K]^T + b)
 static inline int linear_fwd(const float* X, int64_t ldx, const drpo_linear& L, float* Y, int64_t ldy, int M, int act,
                              const int* m_dev, void* stream) {
+  if (g_gemm_mode == 1 && !m_dev && M > 0) {
+    // Y^T[N,M] = W[K,N]^T X^T[K,M] in column-major terms
+    int rc = tc_gemm(CUBLAS_OP_T, CUBLAS_OP_N, L.out_dim, M, L.in_dim, L.w, L.in_dim, X, ldx, Y, ldy, 0.f, stream);
+    if (rc) return rc;
+    if (L.b || act != ACT_NONE) DRPO_LAUNCH(bias_act_kernel, ew_grid((int64_t)M * L.out_dim), 256, 0, stream, Y, ldy, L.b, M, L.out_dim, act);
+    return DRPO_OK;
+  }
   GemmArgs g = gemm_args();
   g.A = X; g.a_sm = ldx; g.a_sk = 1;
   g.B = L.w; g.b_sk = 1; g.b_sn = L.in_dim;
@@ -142,6 +236,13 @@ static inline int linear_fwd(const float* X, int64_t ldx, const drpo_linear& L, 
 // dX[M,K] = (dY[M,N] W[N,K]) * act'(saved)   (+ beta*dX)
 static inline int linear_bwd_data(const float* dY, int64_t ldy, const drpo_linear& L, float* dX, int64_t lddx, int M,
                                   const float* saved, int64_t ldsaved, int mask_mode, float beta, void* stream) {
+  if (g_gemm_mode == 1 && M > 0 && (beta == 0.f || mask_mode <= 1)) {
+    // dX^T[K,M] = W[K,N] dY^T[N,M]; with beta = 1 the accumulated term already carries the same 0/1 relu mask (idempotent)
+    int rc = tc_gemm(CUBLAS_OP_N, CUBLAS_OP_N, L.in_dim, M, L.out_dim, L.w, L.in_dim, dY, ldy, dX, lddx, beta, stream);
+    if (rc) return rc;
+    if (mask_mode) DRPO_LAUNCH(act_mask_kernel, ew_grid((int64_t)M * L.in_dim), 256, 0, stream, dX, lddx, saved, ldsaved, M, L.in_dim, mask_mode);
+    return DRPO_OK;
+  }
   GemmArgs g = gemm_args();
   g.A = dY; g.a_sm = ldy; g.a_sk = 1;
   g.B = L.w; g.b_sk = L.in_dim; g.b_sn = 1;
@@ -152,6 +253,19 @@ static inline int linear_bwd_data(const float* dY, int64_t ldy, const drpo_linea
 // dW[N,K] = dY[M,N]^T X[M,K],  db[N] = column sums of dY ; split-K over the batch with a deterministic reduction
 static inline int linear_bwd_weight(const float* dY, int64_t ldy, const float* X, int64_t ldx, int M, int n_out, int k_in,
                                     float* dW, float* db, float* partial, int64_t partial_floats, void* stream) {
+  if (g_gemm_mode == 1 && M > 0) {
+    // dW^T[K,N] = X^T[K,M] dY[M,N]  (contraction over the batch), db = column sums of dY
+    int rc = tc_gemm(CUBLAS_OP_N, CUBLAS_OP_T, k_in, n_out, M, X, ldx, dY, ldy, dW, k_in, 0.f, stream);
+    if (rc) return rc;
+    if (db) {
+      int nb = (M + 127) / 128;                                         // ~128 rows per block: 512 blocks at B = 64k
+      while ((int64_t)nb * n_out > partial_floats && nb > 1) nb = (nb + 1) / 2;
+      const int rows = (M + nb - 1) / nb;
+      DRPO_LAUNCH(colsum_partial_kernel, dim3(1, nb), 256, 0, stream, dY, ldy, M, n_out, rows, partial);
+      DRPO_LAUNCH(colsum_final_kernel, (n_out + 127) / 128, 128, 0, stream, partial, nb, n_out, db);
+    }
+    return DRPO_OK;
+  }
   GemmArgs g = gemm_args();
   g.A = dY; g.a_sm = 1; g.a_sk = ldy;
   g.B = X; g.b_sk = ldx; g.b_sn = 1;

@@ -34,7 +34,8 @@ enum { DRPO_OK = 0, DRPO_ERR_ARG = -1, DRPO_ERR_CUDA = -2, DRPO_ERR_WORKSPACE = 
 
 /* arithmetic mode of the dense layers */
 enum { DRPO_PREC_FP32 = 0,   /* fp32 FMA path, parity <= 1e-5 relative vs the reference */
-       DRPO_PREC_BF16 = 1 }; /* bf16 tcgen05/TMEM path, fp32 accumulate, parity <= 2e-2 */
+       DRPO_PREC_BF16 = 1 }; /* tensor-core path, fp32 accumulate, parity <= 2e-2: drpo_rollout = fused bf16 tcgen05/TMEM
+                                kernel; drpo_critic_step / drpo_multiplier_step = TF32 tensor-op GEMMs (cuBLAS), fp32 elsewhere */
 
 /* ------------------------------------------------------------------------------------------------------------
  * Env hooks: check_done / check_violation / get_constraint_values

@@ -349,3 +349,37 @@ def test_buffer_gather_matches_reference_assembly():
     want = O.preprocess_batch([c.cpu() for c in comb], 2.0, 2.0, 10.0, 0.5)
     for a, b, n in zip(got, want, O.COMPONENTS):
         assert torch.equal(a.cpu(), b), n
+
+
+@pytest.mark.parametrize("S,A,C,B", [(51, 2, 1, 4096), (12, 2, 2, 1000)])
+def test_critic_and_multiplier_tensor_mode_vs_oracle(S, A, C, B):
+    """Tensor-core mode of the SSAC steps (PREC_BF16: TF32 tensor-op GEMMs, fp32 everywhere else) against the fp32 oracle
+    within the 2e-2 the north star allows for the reduced-precision GEMM path; losses much tighter."""
+    import drpo_b200
+    w = O.make_ssac_weights(61, S, A, C)
+    solver = make_ssac(w, S, A, C, B)
+    solver.precision = drpo_b200.PREC_BF16
+    wo = {k: v.clone() for k, v in w.items()}
+    g = torch.Generator().manual_seed(62)
+    obs = torch.randn(B, S, generator=g); act = torch.rand(B, A, generator=g) * 2 - 1
+    nobs = obs + 0.1 * torch.randn(B, S, generator=g); rew = torch.randn(B, generator=g)
+    done = torch.rand(B, generator=g) < 0.1; viol = torch.rand(B, generator=g) < 0.1
+    cv = (torch.randn(B, generator=g) - 0.5) if C == 1 else (torch.randn(B, C, generator=g) - 0.5)
+    batch = [obs, act, nobs, rew, done, viol, cv]
+    noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g), torch.randn(*cv.shape, generator=g))
+    lq, lc, aux = O.critic_update(wo, batch, noise, O.SSACHyper(), 0.0, O.AdamState(), 3e-4)
+    glq, glc = solver.update_critic(*[to_dev(b) for b in batch], noise=tuple(to_dev(n) for n in noise))
+    assert_close(glq, lq, 5e-3, "loss_q (tf32)"); assert_close(glc, lc, 5e-3, "loss_c (tf32)")
+    assert_close(solver._losses[2], aux["grad_norm_q"], 2e-2, "grad norm Q (tf32)")
+    assert_close(solver._losses[3], aux["grad_norm_c"], 2e-2, "grad norm Qc (tf32)")
+    off, grad = 0, solver.critic_optimizer.grad
+    for k in [k for k in w if k.startswith(("critic.", "constraint_critic."))]:
+        n = w[k].numel()
+        # tf32 products summed over the batch: entries that cancel to ~0 carry the largest relative error
+        assert_close(grad[off:off + n].view(w[k].shape), aux["grads_raw"][k], 2e-2, f"grad {k} (tf32)", max_outlier_frac=1e-2)
+        assert_close(grad[off:off + n].view(w[k].shape), aux["grads_raw"][k], 2e-1, f"grad {k} (tf32, outlier bound)")
+        off += n
+    eps = torch.randn(B, A, generator=g)
+    lm, _ = O.multiplier_update(wo, obs, eps, O.SSACHyper(), C, O.AdamState(), 3e-4)
+    glm = solver.update_multiplier(to_dev(obs), eps=to_dev(eps))
+    assert_close(glm, lm, 2e-2, "multiplier loss (tf32)")
