@@ -27,6 +27,9 @@ import torch  # noqa: E402
 HORIZON = 10
 DEFAULT_B0 = {"quadrotor": 1_000_000, "cartpole-move": 100_000, "safetygym-point-synthetic": 400_000, "point-robot": 100_000}
 CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload, from the
+# `ncu --set full` capture summarised in profiles/r1_rollout.md (null when no capture exists for the workload)
+TRAFFIC_BYTES_PER_LAUNCH = {}
 
 
 def flops_per_transition(S, A):
@@ -52,23 +55,49 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled directly
+    (a sample costs ~0.1 ms); nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flag = lambda name: "Active" if (r & getattr(n, name, 0)) else "Not Active"
+        return [str(sm), str(mx), f"{pw:.2f}", flag("nvmlClocksEventReasonHwSlowdown") if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else flag("nvmlClocksThrottleReasonHwSlowdown"),
+                flag("nvmlClocksEventReasonHwThermalSlowdown") if hasattr(n, "nvmlClocksEventReasonHwThermalSlowdown") else flag("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                flag("nvmlClocksEventReasonSwThermalSlowdown") if hasattr(n, "nvmlClocksEventReasonSwThermalSlowdown") else flag("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                flag("nvmlClocksEventReasonSwPowerCap") if hasattr(n, "nvmlClocksEventReasonSwPowerCap") else flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)        # NVML queries take driver locks: keep them sparse so that they do not perturb the launches
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -82,12 +111,13 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        num = lambda x: x.replace(".", "").isdigit()
+        sm = sorted(float(r[0]) for r in self.rows if num(r[0]))
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()) if self.rows else None,
-                "samples": len(self.rows), "reasons": reasons}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if num(self.rows[0][1]) else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if num(r[2])) if self.rows else None,
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi", "reasons": reasons}
 
 
 def build_alg(workload, B0, device, precision):
@@ -144,6 +174,9 @@ def run_ours(args):
         view = alg.rollout(alg.actor, initial_states=dev_init, member_idx=members)
         return view.step_counts.to("cpu", non_blocking=False)                  # D2H of the step's result
 
+    t_pre = time.perf_counter()                       # untimed pre-warm: bring the SM clocks up before the W warm-up steps
+    while time.perf_counter() - t_pre < 0.5:
+        step_device(); torch.cuda.synchronize()
     for _ in range(args.warmup):
         view = step_device()
     barrier()
@@ -187,17 +220,36 @@ def run_ours(args):
         dist.all_reduce(te)
     e2e_value = int(te) / (float(ms_e) * 1e-3)
 
-    # ---- roofline of the dominant kernel (measured live: CUDA events around the rollout's launches) ---------------
+    # ---- roofline of the dominant kernel: rollout_step_umma_kernel, one launch per rollout step.  Its launches are bracketed
+    #      by CUDA events on the launching stream (drpo_timing_enable) over K more steps of the same workload ----------------
     pk = peaks()
-    per_gpu_tr_per_step = transitions / world / args.steps
-    flops = flops_per_transition(S, A) * per_gpu_tr_per_step
     step_ms = ms_total / args.steps
-    kern = alg.last_kernel_stats() if hasattr(alg, "last_kernel_stats") else None
-    achieved_tf = flops / (step_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " (sustained)",
-                "kernel": "whole rollout step (policy+member GEMM chain + epilogues)" if kern is None else kern,
-                "algorithmic_flops_per_transition": flops_per_transition(S, A)}
+    import ctypes
+    rows_launched, kt, kn = 0, ctypes.c_double(0.0), ctypes.c_int64(0)
+    lib.drpo_timing_enable(1)
+    for _ in range(args.steps):
+        v = step_device()
+        rows_launched += int(v.step_counts[:-1].sum())               # alive rows of every step = rows each launch processed
+    torch.cuda.synchronize()
+    _lib.check(lib.drpo_timing_read(ctypes.byref(kt), ctypes.byref(kn)), "drpo_timing_read")
+    lib.drpo_timing_enable(0)
+    if kn.value > 0 and precision == drpo_b200.PREC_BF16:
+        avg_ms = kt.value / kn.value
+        flops_per_launch = flops_per_transition(S, A) * rows_launched / kn.value
+        achieved_tf = flops_per_launch / (avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(workload),
+                    "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                    "kernel": "rollout_step_umma_kernel (policy + ensemble-member GEMM chain + epilogues), one launch per rollout step",
+                    "avg_launch_ms": round(avg_ms, 4), "launches_timed": int(kn.value), "kernel_share_of_step": round(kt.value / (step_ms * args.steps), 3),
+                    "algorithmic_flops_per_transition": flops_per_transition(S, A), "rows_per_launch": round(rows_launched / kn.value, 1)}
+    else:
+        per_gpu_tr_per_step = transitions / world / args.steps
+        achieved_tf = flops_per_transition(S, A) * per_gpu_tr_per_step / (step_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                    "kernel": "whole rollout step (fp32 path: GEMM + elementwise kernel chain)",
+                    "algorithmic_flops_per_transition": flops_per_transition(S, A)}
 
     out = {
         "metric": "model_rollout_transitions_per_s", "value": value, "unit": "transitions/s", "n_gpus": world,
@@ -220,7 +272,7 @@ def run_ours(args):
         out["critic"] = bench_critic(args, device, world, rank, pk)
     # ---- CPU baseline (oracle port) on rank 0, N=1 only --------------------------------------------------------------
     if world == 1 and not args.skip_cpu:
-        out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=2)
+        out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=5)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -122,6 +122,9 @@ SYMBOLS = [
     ("drpo_last_error", C.c_char_p, []),
     ("drpo_abi_version", C.c_int, []),
     ("drpo_launch_count", C.c_int64, []),
+    ("drpo_kernel_status", C.c_int, []),
+    ("drpo_timing_enable", None, [C.c_int32]),
+    ("drpo_timing_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     ("drpo_philox_normal", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     ("drpo_hooks_eval", C.c_int, [C.POINTER(EnvParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drpo_ensemble_workspace_bytes", C.c_int64, [C.POINTER(Ensemble), C.c_int64]),
@@ -172,6 +175,14 @@ def load():
 def check(rc, what):
     if rc != 0:
         raise RuntimeError(f"{what} failed (code {rc}): {load().drpo_last_error().decode()}")
+
+
+def check_kernel_status(what):
+    """Raise if the last bf16 rollout reported an in-kernel wait time-out (blocking; call where the host synchronises anyway)."""
+    lib = load()
+    code = lib.drpo_kernel_status()
+    if code != 0:
+        raise RuntimeError(f"{what}: {lib.drpo_last_error().decode()}")
 
 
 def ptr(t):

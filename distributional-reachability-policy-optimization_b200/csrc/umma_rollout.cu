@@ -28,6 +28,8 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "hooks.cuh"
@@ -915,6 +917,35 @@ static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP,
 
 using namespace umma;
 
+static thread_local int* g_last_err_flag = nullptr;
+static thread_local int g_timing_on = 0;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* g_timing_events = nullptr;
+
+int umma_kernel_status() {
+  if (!g_last_err_flag) return 0;
+  int code = 0;
+  if (cudaMemcpy(&code, g_last_err_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("drpo_kernel_status: cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError())); return DRPO_ERR_CUDA; }
+  if (code) set_error("bf16 rollout kernel: an in-kernel wait timed out (code %d): pipeline protocol bug, results invalid", code);
+  return code;
+}
+void umma_timing_enable(int on) {
+  g_timing_on = on;
+  if (!g_timing_events) g_timing_events = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
+  for (auto& e : *g_timing_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  g_timing_events->clear();
+}
+int umma_timing_read(double* total_ms, int64_t* launches) {
+  double t = 0; int64_t n = 0;
+  if (g_timing_events)
+    for (auto& e : *g_timing_events) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(e.second) != cudaSuccess || cudaEventElapsedTime(&ms, e.first, e.second) != cudaSuccess) { set_error("drpo_timing_read: event query failed"); return DRPO_ERR_CUDA; }
+      t += ms; ++n;
+    }
+  *total_ms = t; *launches = n;
+  return DRPO_OK;
+}
+
 int64_t umma_rollout_ws_bytes(const drpo_rollout_args& a) {
   NetPlan P;
   if (build_plan(a, P) != DRPO_OK) return 0;
@@ -973,6 +1004,7 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
   DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 
   DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));
+  g_last_err_flag = err_flag;
   DRPO_CUDA_OK(cudaMemcpyAsync(w.curA, a.initial_states, sizeof(float) * B * S, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   DRPO_LAUNCH(rollout_init_kernel, grid_for(B), 256, 0, stream, w.idsA, B, a.traj_id_offset, w.n_alive, w.st, a.virt.pointer);
   float* cur = w.curA; float* nxt = w.curB; int32_t* ids = w.idsA; int32_t* ids_n = w.idsB;
@@ -991,8 +1023,11 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
     sp.norm_mean = a.ensemble->norm_mean; sp.norm_std = a.ensemble->norm_std; sp.min_lv = a.ensemble->min_log_var; sp.max_lv = a.ensemble->max_log_var;
     sp.S = S; sp.A = A; sp.SP = SP; sp.OP = OP; sp.NM = NM; sp.NMG = NMG; sp.stages = stages; sp.err_flag = err_flag;
     sp.dump_layer = dump_layer; sp.dump_out = dump_out;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{};
+    if (g_timing_on) { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); cudaEventRecord(ev.first, (cudaStream_t)stream); }
     if (dump_layer >= 0) { DRPO_LAUNCH(rollout_step_umma_kernel<true>, grid, NUM_THREADS, smem, stream, sp); }
     else { DRPO_LAUNCH(rollout_step_umma_kernel<false>, grid, NUM_THREADS, smem, stream, sp); }
+    if (g_timing_on) { cudaEventRecord(ev.second, (cudaStream_t)stream); g_timing_events->push_back(ev); }
     DRPO_LAUNCH(hooks_store_kernel, grid_for(B * S), 256, 0, stream, *a.env, a.virt, w.st, n_dev, cur, w.actions, w.next_states, w.rewards, w.done);
     DRPO_LAUNCH(compact_count_kernel, nblocks, CBLK, 0, stream, w.done, n_dev, w.block_counts);
     DRPO_LAUNCH(compact_scan_kernel, 1, CBLK, 0, stream, w.block_counts, nblocks, w.n_alive, t, w.st, a.step_counts);

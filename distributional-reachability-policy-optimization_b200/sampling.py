@@ -95,13 +95,26 @@ class RolloutView:
     COMPONENT_NAMES = ConstraintSafetySampleBuffer.COMPONENT_NAMES
 
     def __init__(self, ring, start_pointer, step_counts):
-        self.ring, self.start, self.step_counts = ring, int(start_pointer), step_counts   # step_counts: device int32 [H+1]
+        # both stay on the device until somebody asks: the rollout itself never synchronises with the host
+        self.ring, self._start, self.step_counts = ring, start_pointer, step_counts      # step_counts: device int32 [H+1]
+
+    @property
+    def start(self):
+        return int(self._start)
+
+    def _check(self):
+        from . import _lib
+        _lib.check_kernel_status("drpo_rollout")
 
     def __len__(self):
-        return int(self.step_counts[-1])
+        n = int(self.step_counts[-1])
+        self._check()
+        return n
 
     def counts(self):
-        return [int(c) for c in self.step_counts[:-1].tolist()]
+        c = [int(c) for c in self.step_counts[:-1].tolist()]
+        self._check()
+        return c
 
     def get(self, *names, device=None, as_dict=False):
         if len(names) == 0:

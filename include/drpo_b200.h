@@ -296,6 +296,15 @@ int drpo_qc_forward(const drpo_qc* qc, const float* states, const float* actions
 /* misc */
 const char* drpo_last_error(void);
 int drpo_abi_version(void);
+/* Blocking check of the last drpo_rollout(DRPO_PREC_BF16) launch sequence of this thread: 0 = ok, else the code of the first
+ * in-kernel wait that timed out (a protocol bug: the kernel reports it and runs to completion instead of hanging the GPU;
+ * the results of that rollout are invalid).  Synchronises the device; message via drpo_last_error(). */
+int drpo_kernel_status(void);
+/* Measurement aid (bench.py's roofline): while enabled, every launch of the fused rollout step kernel is bracketed by CUDA
+ * events on the caller's stream; drpo_timing_read synchronises them and returns their summed duration and count since
+ * the last drpo_timing_enable call. */
+void drpo_timing_enable(int32_t on);
+int drpo_timing_read(double* total_ms_host, int64_t* launches_host);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t drpo_launch_count(void);
 
