@@ -29,7 +29,7 @@ DEFAULT_B0 = {"quadrotor": 1_000_000, "cartpole-move": 100_000, "safetygym-point
 CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload, from the
 # `ncu --set full` capture summarised in profiles/r1_rollout.md (null when no capture exists for the workload)
-TRAFFIC_BYTES_PER_LAUNCH = {}
+TRAFFIC_BYTES_PER_LAUNCH = {"quadrotor": 164961024}
 
 
 def flops_per_transition(S, A):

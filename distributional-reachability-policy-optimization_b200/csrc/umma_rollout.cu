@@ -93,21 +93,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // try_wait returns after only ~40 ns, so a waiting warp re-issues the loop body every ~80 cycles and those instructions
 // compete with the working warps of its scheduler (the first profile spent half of all issue slots on wait loops).
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int* err_flag, int code) {
-  const long long t0 = clock64();
+  long long t0 = 0;
 #pragma unroll 1
-  for (;;) {
+  for (uint32_t it = 0;; ++it) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar_addr), "r"(parity), "r"(0x989680u) : "memory");
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
     if (ok) return;
-    // ~0.5 s of SM clocks without progress is a protocol bug; once one wait of the launch failed the others give up after 1 ms
-    const long long dt = clock64() - t0;
-    if (dt > 1000000000ll || (dt > 2000000ll && *(volatile int*)err_flag)) break;
+    // A failed try_wait returns after ~40 ns, so a waiting warp would re-issue this loop every ~80 cycles on the scheduler it
+    // shares with working warps (the profile of an earlier version spent 65% of all issued instructions here).  Short waits
+    // (the pipeline's hand-offs) poll back to back; long ones (output group between its chunks, idle groups at a layer
+    // boundary, the producer) back off with a short sleep.
+    if (it >= 8) __nanosleep(64);
+    if ((it & 63) == 63) {
+      // ~0.5 s of SM clocks without progress is a protocol bug; once one wait of the launch failed the others give up after 1 ms
+      if (t0 == 0) t0 = clock64();
+      const long long dt = clock64() - t0;
+      if (dt > 1000000000ll || (dt > 2000000ll && *(volatile int*)err_flag)) break;
+    }
   }
   // A protocol bug must fail loudly but must not hang the GPU (and a trap would hide which wait failed): record and report
   // the first failing wait, then let every warp run to completion; the results are garbage and the host checks err_flag.
