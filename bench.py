@@ -136,6 +136,10 @@ def build_alg(workload, B0, device, precision):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     import drpo_b200
     from drpo_b200 import _lib, synthetic
@@ -273,10 +277,13 @@ def run_ours(args):
     # ---- CPU baseline (oracle port) on rank 0, N=1 only --------------------------------------------------------------
     if world == 1 and not args.skip_cpu:
         out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=5)
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(json_fd, 1)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
 
 
 def bench_critic(args, device, world, rank, pk):
