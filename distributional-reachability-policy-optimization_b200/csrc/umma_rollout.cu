@@ -127,6 +127,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   if (!ok) mbar_wait_slow(smem_u32(bar), parity, err_flag, code);
 }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity, int* err_flag, int code) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  if (!ok) mbar_wait_slow(addr, parity, err_flag, code);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // one elected lane of a converged warp: unlike `lane == 0`, the compiler knows the branch is single-threaded, keeps the
 // tcgen05.mma operands in uniform registers and emits back-to-back UTCHMMA (measured: 9-32 cycles/MMA instead of 63)
@@ -150,6 +156,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_addr(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -308,7 +317,9 @@ struct StepParams {
 };
 
 struct SmemLayout {
-  uint64_t full[MAX_STAGES], empty[MAX_STAGES], hid_full[4], acc_free[NACC], sp_full[NSPECIAL], sp_free[NSPECIAL], tile_ready, token[2];
+  // full_bar: [0..3] hid_full[pair][slot] (accumulator full -> the pair that drains it), [4..6] sp_full[k] (-> group C)
+  // free_bar: [0..2] acc_free[b] (hidden chunk drained and stored), [3..5] sp_free[k] (output chunk fully done)
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], full_bar[4 + NSPECIAL], free_bar[NACC + NSPECIAL], tile_ready, token[2];
   uint32_t tmem_base, pad[3];
   // per-dim constants of the member, staged once per CTA: normaliser, and the log-var soft clamp folded into
   //   std = exp(lv/2) = s0 * sqrt(1 + E / (1 + exp(hi - x)))   with s0 = exp(lo/2), E = exp(hi - lo)      (src/dynamics.py:120-121,201)
@@ -410,9 +421,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&sl->full[s], 1); mbar_init(&sl->empty[s], 1); }
-    for (int b = 0; b < NACC; ++b) mbar_init(&sl->acc_free[b], 2 * GROUP_THREADS);
-    for (int k = 0; k < 4; ++k) mbar_init(&sl->hid_full[k], 1);
-    for (int k = 0; k < NSPECIAL; ++k) { mbar_init(&sl->sp_full[k], 1); mbar_init(&sl->sp_free[k], GROUP_THREADS); }
+    for (int k = 0; k < 4 + NSPECIAL; ++k) mbar_init(&sl->full_bar[k], 1);
+    for (int b = 0; b < NACC; ++b) mbar_init(&sl->free_bar[b], 2 * GROUP_THREADS);
+    for (int k = 0; k < NSPECIAL; ++k) mbar_init(&sl->free_bar[NACC + k], GROUP_THREADS);
     mbar_init(&sl->tile_ready, GROUP_THREADS);
     mbar_init(&sl->token[0], 1); mbar_init(&sl->token[1], 1);
     fence_barrier_init();
@@ -461,18 +472,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
       const uint32_t me = warp == MMA_WARP ? 0u : 1u;
       int s = 0; uint32_t ring_par = 0;      // weight ring slot + parity of its current use
       // Accumulator buffer b = chunk index % NACC (n_chunks is a multiple of NACC).  Who drains the buffer's current contents is
-      // own[b] (2 bits each: 0 the hidden groups via acc_free[b], 1+k group C via sp_free[k]).  Each "free" barrier has at most
-      // one phase outstanding: pend_* bit = a phase was started and not yet observed, par_* bit = parity of that phase.
-      uint32_t own = 0, pend_h = 0, par_h = 0, pend_s = 0, par_s = 0, hcnt = 0;   // hcnt: per-pair count of hidden chunks issued (8 bits each)
+      // own (2 bits per buffer: 0 the hidden groups -> free_bar[b], 1+k group C -> free_bar[NACC+k]).  Each free barrier has at
+      // most one phase outstanding: pend bit = a phase was started and not yet observed, par bit = its parity (bit = barrier id).
+      // The code of this loop is kept small on purpose (one instantiation of every wait and of the unrolled MMA sequence): it
+      // is the pipeline's serial section, and its instruction footprint competes with 23 other warps for a 32 KB L1.5 I-cache.
+      uint32_t own = 0, pend = 0, par = 0, hcnt = 0;      // hcnt: per-pair count of hidden chunks issued (8 bits each)
       uint32_t g = 0;                        // global chunk counter: chunk g belongs to issuer (g & 1)
       uint32_t tok_par = 0;                  // parity of the next phase of the OTHER issuer's token
-      auto ensure_drained = [&](int b, bool mine, int code) {
+      const uint32_t free_base = smem_u32(&sl->free_bar[0]), full_base = smem_u32(&sl->full_bar[0]);
+      auto drain = [&](int b, bool mine) {
         const uint32_t o = (own >> (2 * b)) & 3u;
-        if (o == 0) {
-          if ((pend_h >> b) & 1u) { if (mine) { mbar_wait(&sl->acc_free[b], (par_h >> b) & 1u, p.err_flag, code); tc_fence_after(); } pend_h ^= 1u << b; par_h ^= 1u << b; }
-        } else {
-          const int k = (int)o - 1;
-          if ((pend_s >> k) & 1u) { if (mine) { mbar_wait(&sl->sp_free[k], (par_s >> k) & 1u, p.err_flag, code); tc_fence_after(); } pend_s ^= 1u << k; par_s ^= 1u << k; }
+        const uint32_t id = o == 0 ? (uint32_t)b : NACC - 1 + o;
+        if ((pend >> id) & 1u) {
+          if (mine) { mbar_wait_addr(free_base + 8u * id, (par >> id) & 1u, p.err_flag, 6); tc_fence_after(); }
+          pend ^= 1u << id; par ^= 1u << id;
         }
       };
       const int n_chunks = plan.n_chunks;
@@ -484,9 +497,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
         for (int c = 0; c < n_chunks; ++c, ++g) {
           const uint4 rec = sl->irec[c];
           const bool mine = (g & 1u) == me;
-          ensure_drained(b, mine, 6);                                     // accumulator buffer still being read by its last user?
+          drain(b, mine);                                                 // accumulator buffer still being read by its last user?
           const int sp = (int)((rec.z >> 24) & 0x3Fu) - 1;
           const uint32_t pr = (rec.z >> 30) & 1u;                         // group pair that drains a hidden chunk
+          // First chunk of a layer whose A operand is still being produced: the producer layer's chunks drain out of order across
+          // the two group pairs, so its last TWO chunks are tracked (older ones precede them in their pair's program order and
+          // their buffers were reused since).  K-sliced start: k-steps that only read columns below chunk (last-1) issue at
+          // once, the rest wait for (last-1), then (last).
+          const int bufA = (int)((rec.w >> 16) & 0xFu) - 1, bufB = (int)((rec.w >> 20) & 0xFu) - 1;
           if (mine) {
             if (me == 0) stamp<kDebug>(p, tile_it, c, 3);
             mbar_wait(&sl->full[s], ring_par, p.err_flag, 3);
@@ -497,10 +515,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
             const uint32_t a_addr = tmem + (rec.z & 0xFFFFu);
             const uint32_t d_addr = tmem + TM_ACC + (uint32_t)b * NSLAB;
             const int nk = (int)((rec.z >> 16) & 0xFFu);
+            const int kB = min((int)((rec.w >> 8) & 0xFFu), nk), kA = min((int)(rec.w & 0xFFu), kB);
             if (g > 0) { mbar_wait(&sl->token[me ^ 1u], tok_par, p.err_flag, 8); tok_par ^= 1u; }   // chunk g-1 has been issued
             if (me == 0) stamp<kDebug>(p, tile_it, c, 4);
             // back-to-back UTCHMMA for k-steps [lo, hi); one k-step = 2 core matrices = 256 B = +16 in the address field,
-            // +8 TMEM columns.  Fully unrolled with uniform predicates: a rolled loop issues an order of magnitude slower.
+            // +8 TMEM columns.  Fully unrolled with compile-time-simple uniform predicates: the issue cost per MMA is very
+            // sensitive to the code shape (a rolled loop, or run-time range bounds inside a rolled segment loop, issue an order
+            // of magnitude slower than this).
             auto issue_range = [&](int lo, int hi) {
 #pragma unroll
               for (int k = 0; k < 17; ++k) {
@@ -513,35 +534,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
             if (rec.w == 0) {
               issue_range(0, nk);
             } else {
-              // First chunk of a layer whose A operand is still being produced: the producer layer's chunks drain out of order
-              // across the two group pairs, so its last TWO chunks are tracked (older ones precede them in their pair's program
-              // order and their buffers were reused since).  K-sliced start: k-steps that only read columns below chunk (last-1)
-              // issue at once, the rest wait for (last-1), then (last).
-              const int kB = min((int)((rec.w >> 8) & 0xFFu), nk), kA = min((int)(rec.w & 0xFFu), kB);
-              const int bufA = (int)((rec.w >> 16) & 0xFu) - 1, bufB = (int)((rec.w >> 20) & 0xFu) - 1;
               issue_range(0, kA);
-              if (bufA >= 0) ensure_drained(bufA, true, 5);
+              if (bufA >= 0) drain(bufA, true);
               issue_range(kA, kB);
-              if (bufB >= 0) ensure_drained(bufB, true, 5);
+              if (bufB >= 0) drain(bufB, true);
               issue_range(kB, nk);
             }
             tc_commit(&sl->empty[s]);                                    // frees the ring slot when these MMAs retire
             // "accumulator full" goes to the pair that drains this chunk: slot = parity of the pair's own chunk count, so each
             // pair observes every phase of its two barriers, in order, and nobody else waits on them (a parity wait is only
             // sound while the waiter is at most one phase behind)
-            if (sp < 0) tc_commit(&sl->hid_full[2 * pr + ((hcnt >> (8 * pr)) & 1u)]); else tc_commit(&sl->sp_full[sp]);
+            tc_commit_addr(full_base + 8u * (sp < 0 ? 2u * pr + ((hcnt >> (8 * pr)) & 1u) : 4u + (uint32_t)sp));
             mbar_arrive(&sl->token[me]);                                  // chunk g is issued: the other issuer may issue g+1
             if (me == 0) stamp<kDebug>(p, tile_it, c, 5);
           } else {
-            if (rec.w != 0) {                                             // replay the other issuer's K-sliced waits
-              const int bufA = (int)((rec.w >> 16) & 0xFu) - 1, bufB = (int)((rec.w >> 20) & 0xFu) - 1;
-              if (bufA >= 0) ensure_drained(bufA, false, 5);
-              if (bufB >= 0) ensure_drained(bufB, false, 5);
-            }
+            if (bufA >= 0) drain(bufA, false);                            // replay the other issuer's K-sliced waits
+            if (bufB >= 0) drain(bufB, false);
           }
           own &= ~(3u << (2 * b));
-          if (sp < 0) { pend_h |= 1u << b; hcnt = (hcnt & ~(0xFFu << (8 * pr))) | ((((hcnt >> (8 * pr)) + 1u) & 0xFFu) << (8 * pr)); }
-          else { pend_s |= 1u << sp; own |= (uint32_t)(1 + sp) << (2 * b); }
+          if (sp < 0) { pend |= 1u << b; hcnt = (hcnt & ~(0xFFu << (8 * pr))) | ((((hcnt >> (8 * pr)) + 1u) & 0xFFu) << (8 * pr)); }
+          else { pend |= 1u << (NACC + sp); own |= (uint32_t)(1 + sp) << (2 * b); }
           if (++b == NACC) b = 0;
           if (++s == p.stages) { s = 0; ring_par ^= 1u; }
         }
@@ -565,7 +577,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
           if (mine) {
             if (lead) stamp<kDebug>(p, tile_it, c, 0);
             // the pair's m-th chunk arrives on hid_full[pair][m & 1] as phase m >> 1: this pair sees every phase, in order
-            mbar_wait(&sl->hid_full[2 * pair + (m & 1u)], (m >> 1) & 1u, p.err_flag, 4);
+            mbar_wait(&sl->full_bar[2 * pair + (m & 1u)], (m >> 1) & 1u, p.err_flag, 4);
             ++m;
             const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
             tc_fence_after();
@@ -589,7 +601,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
               tmem_st_wait();
             }
             tc_fence_before();
-            mbar_arrive(&sl->acc_free[b]);                                // accumulator drained, activations visible
+            mbar_arrive(&sl->free_bar[b]);                                // accumulator drained, activations visible
             if (lead) stamp<kDebug>(p, tile_it, c, 2);
           }
         }
@@ -672,7 +684,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
       const uint32_t acc_col = TM_ACC + (uint32_t)b * NSLAB;
       const int sp = ch.special;
       if (ct == 0) stamp<kDebug>(p, tile_it, c, 0);
-      mbar_wait(&sl->sp_full[sp], tile_it & 1, p.err_flag, 7);
+      mbar_wait(&sl->full_bar[4 + sp], tile_it & 1, p.err_flag, 7);
       tc_fence_after();
       if (ct == 0) stamp<kDebug>(p, tile_it, c, 1);
       if (kDebug && p.dump_layer == (int)ch.layer) {                      // debug hook: raw accumulator to global
@@ -703,7 +715,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
         }
         // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written by the prologue  (src/dynamics.py:113-114)
         write_input_row(lane_base, xm_col, my_o, kpm);
-        tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
+        tmem_st_wait(); tc_fence_before(); mbar_arrive(&sl->free_bar[NACC + sp]);
         if (ct == 0) stamp<kDebug>(p, tile_it, c, 2);
         // off the critical path: the next tile's prologue
         if (early_prologue && next_tile < n_tiles) { need_prologue = true; ptile = next_tile; pbuf = buf ^ 1; pit = tile_it + 1; }
@@ -718,7 +730,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
 #pragma unroll
           for (int j = 0; j < 16; ++j) if (c0 + j < O) my_o[c0 + j] = __uint_as_float(r[j]) + sv[j];
         }
-        tc_fence_before(); mbar_arrive(&sl->sp_free[sp]);
+        tc_fence_before(); mbar_arrive(&sl->free_bar[NACC + sp]);
         if (ct == 0) stamp<kDebug>(p, tile_it, c, 2);
       } else {
         // ---- log-var head + Gaussian sample                                              src/dynamics.py:119-121,201-203 ----
@@ -737,7 +749,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_step_umma_kernel(const
             ev[4 * jg] = e4.x; ev[4 * jg + 1] = e4.y; ev[4 * jg + 2] = e4.z; ev[4 * jg + 3] = e4.w;
           }
           tmem_ld_wait();
-          if (c0 + 16 >= ch.nc) { tc_fence_before(); mbar_arrive(&sl->sp_free[sp]); }        // accumulator in registers: release it early
+          if (c0 + 16 >= ch.nc) { tc_fence_before(); mbar_arrive(&sl->free_bar[NACC + sp]); }        // accumulator in registers: release it early
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int cc = min(c0 + j, O - 1);
