@@ -104,8 +104,11 @@ static __global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint
                                                                const float* __restrict__ ns, const int32_t* __restrict__ ids,
                                                                float* __restrict__ cur_next, int32_t* __restrict__ ids_next, int S) {
   __shared__ int warp_off[CBLK / 32];
+  __shared__ int dst_row[CBLK];                 // destination row of every kept row of this block, -1 for dropped rows
   const int n = *n_dev;
-  const int64_t r = (int64_t)blockIdx.x * CBLK + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * CBLK;
+  if (r0 >= n) return;
+  const int64_t r = r0 + threadIdx.x;
   const bool keep = r < n && !done[r];
   const unsigned b = __ballot_sync(0xffffffffu, keep);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -118,10 +121,17 @@ static __global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint
     warp_off[threadIdx.x] = incl - v;
   }
   __syncthreads();
-  if (keep) {
-    const int64_t pos = (int64_t)block_offsets[blockIdx.x] + warp_off[w] + __popc(b & ((1u << lane) - 1u));
-    for (int c = 0; c < S; ++c) cur_next[pos * S + c] = ns[r * S + c];
-    ids_next[pos] = ids[r];
+  const int pos = keep ? block_offsets[blockIdx.x] + warp_off[w] + __popc(b & ((1u << lane) - 1u)) : -1;
+  dst_row[threadIdx.x] = pos;
+  if (keep) ids_next[pos] = ids[r];
+  __syncthreads();
+  // element-parallel copy: consecutive threads read consecutive floats of the block's rows (coalesced) and write the kept
+  // rows' floats, which are contiguous in the destination as well (order-preserving compaction)
+  const int rows = (int)min((int64_t)CBLK, (int64_t)n - r0);
+  for (int i = threadIdx.x; i < rows * S; i += CBLK) {
+    const int rr = i / S, c = i - rr * S;
+    const int d = dst_row[rr];
+    if (d >= 0) cur_next[(int64_t)d * S + c] = ns[r0 * S + i];
   }
 }
 

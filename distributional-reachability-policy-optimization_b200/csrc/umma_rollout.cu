@@ -935,14 +935,17 @@ static int smem_bytes_for(const NetPlan& P, int S, int stages, int& SP, int& OP,
 
 using namespace umma;
 
-static thread_local int* g_last_err_flag = nullptr;
+// status word of the last bf16 rollout: the device-side error flag is copied at the end of the rollout's stream work into a
+// 4-byte pinned host word owned by the library (the only allocation it ever makes), so that a later check never touches a
+// caller workspace that may have been freed
+static int* g_status_host = nullptr;
 static thread_local int g_timing_on = 0;
 static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* g_timing_events = nullptr;
 
 int umma_kernel_status() {
-  if (!g_last_err_flag) return 0;
-  int code = 0;
-  if (cudaMemcpy(&code, g_last_err_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("drpo_kernel_status: cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError())); return DRPO_ERR_CUDA; }
+  if (!g_status_host) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("drpo_kernel_status: %s", cudaGetErrorString(cudaGetLastError())); return DRPO_ERR_CUDA; }
+  const int code = *(volatile int*)g_status_host;
   if (code) set_error("bf16 rollout kernel: an in-kernel wait timed out (code %d): pipeline protocol bug, results invalid", code);
   return code;
 }
@@ -1022,7 +1025,7 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
   DRPO_CUDA_OK(cudaFuncSetAttribute(rollout_step_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 
   DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));
-  g_last_err_flag = err_flag;
+  if (!g_status_host) { DRPO_CUDA_OK(cudaMallocHost((void**)&g_status_host, sizeof(int))); *g_status_host = 0; }
   DRPO_CUDA_OK(cudaMemcpyAsync(w.curA, a.initial_states, sizeof(float) * B * S, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   DRPO_LAUNCH(rollout_init_kernel, grid_for(B), 256, 0, stream, w.idsA, B, a.traj_id_offset, w.n_alive, w.st, a.virt.pointer);
   float* cur = w.curA; float* nxt = w.curB; int32_t* ids = w.idsA; int32_t* ids_n = w.idsB;
@@ -1054,6 +1057,7 @@ int umma_rollout_impl(const drpo_rollout_args& a, int dump_layer, float* dump_ou
     int32_t* ti = ids; ids = ids_n; ids_n = ti;
   }
   DRPO_LAUNCH(rollout_finish_kernel, 1, 1, 0, stream, a.virt.pointer, w.st, a.step_counts, H);
+  DRPO_CUDA_OK(cudaMemcpyAsync(g_status_host, err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return DRPO_OK;
 }
 

@@ -11,7 +11,8 @@
  *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are contiguous row-major fp32,
  *     masks are uint8 (torch.bool storage), nn.Linear weights are [out,in] (y = x W^T + b) exactly as in the
  *     reference state_dict, so checkpoints interchange;
- *   - the library owns no memory: parameters, replay buffers and workspaces are allocated by the caller (PyTorch);
+ *   - the library owns no memory (but one 4-byte pinned status word, see drpo_kernel_status): parameters, replay buffers
+ *     and workspaces are allocated by the caller (PyTorch);
  *     `*_workspace_bytes` tells how much scratch a call needs;
  *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no call synchronises,
  *     allocates or frees, so every call is CUDA-graph capturable;
