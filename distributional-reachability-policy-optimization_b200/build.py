@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
             subprocess.run(cmd, check=True)
         objs.append(o)
     if force or not _newer(OUT, objs):
-        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcuda", "-lcublas"]
+        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcuda", "-lcublas", "-lcublasLt"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

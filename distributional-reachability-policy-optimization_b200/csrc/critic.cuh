@@ -161,6 +161,7 @@ static inline int mlp3_bwd(const drpo_mlp3& net, const Mlp3Grads& g, const float
 }
 
 constexpr int64_t PARTIAL_FLOATS = 16 * 256 * 320;
+constexpr int64_t LT_WORKSPACE_BYTES = 32ll << 20;      // scratch lent to cuBLASLt in tensor-core mode
 constexpr int LOSS_BLOCKS = 296;
 
 static inline int64_t critic_ws_bytes(int64_t B, int S, int A, int C, int H) {
@@ -174,7 +175,7 @@ static inline int64_t critic_ws_bytes(int64_t B, int S, int A, int C, int H) {
             + 2 * B + 2 * B * C                   // dq1,dq2,dmean,dls
             + 3 * B * H                           // dhA, dhB, dt2
             + PARTIAL_FLOATS;
-  return f * 4 + (LOSS_BLOCKS * 2 + 2 * 1184 + 8) * 8 + 64 * 256;
+  return f * 4 + (LOSS_BLOCKS * 2 + 2 * 1184 + 8) * 8 + 64 * 256 + LT_WORKSPACE_BYTES;
 }
 
 static inline drpo_mlp3 const_view(const drpo_mlp3& n) { return n; }
@@ -198,6 +199,7 @@ static inline int critic_step_fp32(const drpo_critic_args& a) {
   float* partial = ar.take<float>(PARTIAL_FLOATS);
   double* loss_part = ar.take<double>(LOSS_BLOCKS * 2); double* nrm_part = ar.take<double>(2 * 1184);
   float* coef = ar.take<float>(4);
+  g_lt_workspace = ar.take<char>(LT_WORKSPACE_BYTES); g_lt_workspace_bytes = (size_t)LT_WORKSPACE_BYTES;
   if (!ar.ok()) { set_error("drpo_critic_step: workspace too small (%lld needed, %lld given)", (long long)ar.off, (long long)a.workspace_bytes); return DRPO_ERR_WORKSPACE; }
   const int64_t n_all = a.n_params_q + a.n_params_qc;
 
@@ -318,7 +320,7 @@ static __global__ void __launch_bounds__(256) mult_loss_kernel(const float* __re
 static inline int64_t mult_ws_bytes(int64_t B, int S, int A, int C, int H) {
   int64_t f = B * (S + A) * 2 + 2 * B * A + 2 * B * H + B * 2 * A + 4 * B * H + 2 * B * C + 2 * B * C + B * (S + 1) + 3 * B
             + 2 * B * H + B + 2 * B * H + PARTIAL_FLOATS;
-  return f * 4 + (LOSS_BLOCKS * 2 + 2 * 1184 + 8) * 8 + 64 * 256;
+  return f * 4 + (LOSS_BLOCKS * 2 + 2 * 1184 + 8) * 8 + 64 * 256 + LT_WORKSPACE_BYTES;
 }
 
 static inline int multiplier_step_fp32(const drpo_multiplier_args& a) {
@@ -337,6 +339,7 @@ static inline int multiplier_step_fp32(const drpo_multiplier_args& a) {
   float* partial = ar.take<float>(PARTIAL_FLOATS);
   double* loss_part = ar.take<double>(LOSS_BLOCKS * 2); double* nrm_part = ar.take<double>(2 * 1184);
   float* coef = ar.take<float>(4);
+  g_lt_workspace = ar.take<char>(LT_WORKSPACE_BYTES); g_lt_workspace_bytes = (size_t)LT_WORKSPACE_BYTES;
   if (!ar.ok()) { set_error("drpo_multiplier_step: workspace too small (%lld needed, %lld given)", (long long)ar.off, (long long)a.workspace_bytes); return DRPO_ERR_WORKSPACE; }
   NoiseView none = make_noise(nullptr, 0, 0, 0, 0);
   if (a.phases & 1) {

@@ -11,6 +11,7 @@ namespace drpo {
 static thread_local char g_err[1024] = "";
 int64_t g_launch_count = 0;
 thread_local int g_gemm_mode = 0;
+thread_local void* g_lt_workspace = nullptr; thread_local size_t g_lt_workspace_bytes = 0;
 cublasHandle_t gemm_cublas_handle() {
   static cublasHandle_t h = nullptr;
   if (!h) {

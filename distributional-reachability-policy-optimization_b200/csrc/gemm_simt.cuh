@@ -3,6 +3,8 @@
 // strides so that  Y = X W^T (forward),  dX = dY W (backward-data)  and  dW = dY^T X (backward-weight, split-K
 // over the batch) are the same kernel.  64x64x16 tiles, 256 threads, 4x4 outputs per thread.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace drpo {
@@ -135,6 +137,7 @@ static inline int launch_gemm(const GemmArgs& g, void* stream) {
 // bias gradients (column sums) run as the fused elementwise kernels below.
 }  // namespace drpo
 #include <cublas_v2.h>
+#include <cublasLt.h>
 namespace drpo {
 
 extern thread_local int g_gemm_mode;            // 0 = fp32 FMA kernels, 1 = cuBLAS TF32 (set per C-ABI call)
@@ -216,11 +219,74 @@ static inline int tc_gemm(cublasOperation_t ta, cublasOperation_t tb, int m, int
   return DRPO_OK;
 }
 
+// Forward layer with the bias (+ReLU) fused into the GEMM epilogue through cuBLASLt: Y^T[N,M] = W[K,N]^T X^T[K,M] (+ b, relu).
+// One heuristic query per distinct (N, M, K, ld, epilogue) shape, cached for the life of the process.
+struct LtPlan { int n, m, k; int64_t ldx, ldy; int epi; uint32_t al; cublasLtMatmulDesc_t desc; cublasLtMatrixLayout_t a, b, c; cublasLtMatmulAlgo_t algo; bool ok; };
+extern thread_local void* g_lt_workspace; extern thread_local size_t g_lt_workspace_bytes;   // lent by the caller per C-ABI call
+static inline int tc_linear_fwd_lt(const float* X, int64_t ldx, const drpo_linear& L, float* Y, int64_t ldy, int M, int act, void* stream, bool* handled) {
+  static std::vector<LtPlan> plans;
+  *handled = false;
+  if (act != ACT_NONE && act != ACT_RELU) return DRPO_OK;
+  const int epi = (act == ACT_RELU) ? (L.b ? 2 : 1) : (L.b ? 3 : 0);   // 0 none, 1 relu, 2 relu+bias, 3 bias
+  if (epi == 0) return DRPO_OK;
+  cublasLtHandle_t lt = (cublasLtHandle_t)gemm_cublas_handle();
+  if (!lt) return DRPO_OK;
+  // the parameters live at arbitrary 4-byte offsets of the flat arena: the kernel choice must know the real alignments
+  auto align_of = [](const void* p) -> uint32_t { const uintptr_t v = (uintptr_t)p; uint32_t a = 256; while (a > 4 && (v & (a - 1))) a >>= 1; return a; };
+  const uint32_t alW = align_of(L.w), alX = align_of(X), alY = align_of(Y), alB = L.b ? align_of(L.b) : 256;
+  const uint32_t al = alW | (alX << 8) | (alY << 16) | ((alB >= 16 ? 16u : alB) << 24);
+  LtPlan* P = nullptr;
+  for (auto& q : plans) if (q.n == L.out_dim && q.m == M && q.k == L.in_dim && q.ldx == ldx && q.ldy == ldy && q.epi == epi && q.al == al) { P = &q; break; }
+  if (!P) {
+    LtPlan q{}; q.n = L.out_dim; q.m = M; q.k = L.in_dim; q.ldx = ldx; q.ldy = ldy; q.epi = epi; q.al = al; q.ok = false;
+    cublasOperation_t ta = CUBLAS_OP_T, tb = CUBLAS_OP_N;
+    const cublasLtEpilogue_t e = epi == 1 ? CUBLASLT_EPILOGUE_RELU : (epi == 2 ? CUBLASLT_EPILOGUE_RELU_BIAS : CUBLASLT_EPILOGUE_BIAS);
+    bool good = cublasLtMatmulDescCreate(&q.desc, CUBLAS_COMPUTE_32F_FAST_TF32, CUDA_R_32F) == CUBLAS_STATUS_SUCCESS;
+    good = good && cublasLtMatmulDescSetAttribute(q.desc, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta)) == CUBLAS_STATUS_SUCCESS;
+    good = good && cublasLtMatmulDescSetAttribute(q.desc, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb)) == CUBLAS_STATUS_SUCCESS;
+    good = good && cublasLtMatmulDescSetAttribute(q.desc, CUBLASLT_MATMUL_DESC_EPILOGUE, &e, sizeof(e)) == CUBLAS_STATUS_SUCCESS;
+    // A = W stored [K,N] column-major (ld K), B = X^T stored [K,M] (ld ldx), C = Y^T stored [N,M] (ld ldy)
+    good = good && cublasLtMatrixLayoutCreate(&q.a, CUDA_R_32F, L.in_dim, L.out_dim, L.in_dim) == CUBLAS_STATUS_SUCCESS;
+    good = good && cublasLtMatrixLayoutCreate(&q.b, CUDA_R_32F, L.in_dim, M, ldx) == CUBLAS_STATUS_SUCCESS;
+    good = good && cublasLtMatrixLayoutCreate(&q.c, CUDA_R_32F, L.out_dim, M, ldy) == CUBLAS_STATUS_SUCCESS;
+    if (good) {
+      cublasLtMatmulPreference_t pref; cublasLtMatmulHeuristicResult_t res{}; int found = 0;
+      size_t wsb = g_lt_workspace_bytes;
+      if (cublasLtMatmulPreferenceCreate(&pref) == CUBLAS_STATUS_SUCCESS) {
+        cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &wsb, sizeof(wsb));
+        cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_A_BYTES, &alW, sizeof(alW));
+        cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_B_BYTES, &alX, sizeof(alX));
+        cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_C_BYTES, &alY, sizeof(alY));
+        cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_D_BYTES, &alY, sizeof(alY));
+        // the bias pointer's alignment takes part in the heuristic: set a representative one
+        const void* bias = L.b;
+        if (epi >= 2) cublasLtMatmulDescSetAttribute(q.desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias));
+        if (cublasLtMatmulAlgoGetHeuristic(lt, q.desc, q.a, q.b, q.c, q.c, pref, 1, &res, &found) == CUBLAS_STATUS_SUCCESS && found > 0) { q.algo = res.algo; q.ok = true; }
+        cublasLtMatmulPreferenceDestroy(pref);
+      }
+    }
+    plans.push_back(q);
+    P = &plans.back();
+  }
+  if (!P->ok) return DRPO_OK;                              // no fused kernel for this shape: the caller falls back to GEMM + bias_act
+  const void* bias = L.b;
+  if (epi >= 2) DRPO_CUBLAS_OK(cublasLtMatmulDescSetAttribute(P->desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)));
+  const float alpha = 1.f, beta = 0.f;
+  DRPO_CUBLAS_OK(cublasLtMatmul(lt, P->desc, &alpha, L.w, P->a, X, P->b, &beta, Y, P->c, Y, P->c, &P->algo, g_lt_workspace, g_lt_workspace_bytes, (cudaStream_t)stream));
+  ++g_launch_count;
+  *handled = true;
+  return DRPO_OK;
+}
+
 // ---- convenience wrappers -------------------------------------------------------------------------------------
 // Y[M,N] = act(X[M,K] W[N,K]^T + b)
 static inline int linear_fwd(const float* X, int64_t ldx, const drpo_linear& L, float* Y, int64_t ldy, int M, int act,
                              const int* m_dev, void* stream) {
   if (g_gemm_mode == 1 && !m_dev && M > 0) {
+    bool handled = false;
+    int rc0 = tc_linear_fwd_lt(X, ldx, L, Y, ldy, M, act, stream, &handled);
+    if (rc0) return rc0;
+    if (handled) return DRPO_OK;
     // Y^T[N,M] = W[K,N]^T X^T[K,M] in column-major terms
     int rc = tc_gemm(CUBLAS_OP_T, CUBLAS_OP_N, L.out_dim, M, L.in_dim, L.w, L.in_dim, X, ldx, Y, ldy, 0.f, stream);
     if (rc) return rc;

@@ -211,25 +211,37 @@ class FusedAdam:
         self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_count = sd["step"]; self.param_groups[0]["lr"] = sd["lr"]
 
 
-def _flatten_into_arena(params):
-    """Move parameters into one flat fp32 tensor; each nn.Parameter becomes a view of it (state_dict order)."""
-    n = sum(p.numel() for p in params)
-    arena = torch.empty(n, dtype=torch.float32, device=params[0].device)
-    off = 0
+ARENA_ALIGN = 64      # floats (256 B): every parameter starts on the alignment the tensor-core GEMM kernels are chosen for
+
+
+def _arena_offsets(params):
+    offs, off = [], 0
     for p in params:
+        off = (off + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+        offs.append(off)
+        off += p.numel()
+    return offs, (off + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+
+
+def _flatten_into_arena(params):
+    """Move parameters into one flat fp32 tensor; each nn.Parameter becomes a view of it (state_dict order).  The gaps that
+    align each parameter are zeros and stay zeros (zero gradient, zero weight decay), so norms, Adam and EMA are unaffected."""
+    offs, n = _arena_offsets(params)
+    arena = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+    for p, off in zip(params, offs):
         k = p.numel()
         arena[off:off + k].copy_(p.data.reshape(-1))
         p.data = arena[off:off + k].view(p.shape)
-        off += k
     return arena
 
 
 def _arena_ok(arena, params):
-    off = 0
-    for p in params:
+    offs, n = _arena_offsets(params)
+    if arena.numel() != n:
+        return False
+    for p, off in zip(params, offs):
         if p.data_ptr() != arena.data_ptr() + 4 * off or not p.is_contiguous():
             return False
-        off += p.numel()
     return True
 
 
@@ -334,8 +346,10 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self._critic_arena = _flatten_into_arena(self._critic_params())
         self._target_arena = _flatten_into_arena(self._target_params())
         self._mult_arena = _flatten_into_arena(list(self.multiplier.parameters()))
-        self._n_q = sum(p.numel() for p in self.critic.parameters())
-        self._n_qc = sum(p.numel() for p in self.constraint_critic.parameters())
+        # the two clip groups are contiguous (padded) ranges of the critic arena: [Q1 | Q2] then [Qc]
+        offs, total = _arena_offsets(self._critic_params())
+        self._n_q = offs[len(list(self.critic.parameters()))]
+        self._n_qc = total - self._n_q
         self._structs = None
 
     def _ensure_arenas(self):
@@ -353,6 +367,14 @@ class SSAC(Configurable, BasePolicy, nn.Module):
                 qc=self.constraint_critic.as_struct(), qct=self.constraint_critic_target.as_struct(),
                 lam=_mlp3_struct(self.multiplier.lam))
         return self._structs
+
+    def critic_arena_views(self, arena):
+        """name -> view of ``arena`` (the critic parameter / gradient / Adam arena), in state_dict order of critic.* then
+        constraint_critic.* (the arena aligns every parameter to ARENA_ALIGN floats)."""
+        named = [(f"critic.{k}", p) for k, p in self.critic.named_parameters()] + \
+                [(f"constraint_critic.{k}", p) for k, p in self.constraint_critic.named_parameters()]
+        offs, _ = _arena_offsets([p for _, p in named])
+        return {k: arena[o:o + p.numel()].view(p.shape) for (k, p), o in zip(named, offs)}
 
     def invalidate_structs(self):
         """Call after replacing parameter storage by hand (``load_state_dict`` copies in place and needs nothing)."""

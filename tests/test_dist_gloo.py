@@ -51,15 +51,13 @@ class _OracleLib:
             lq, lc, _ = O.critic_losses(w, self.stash["batch"], self.stash["noise"], O.SSACHyper(), float(solver.log_alpha))
             (lq + lc).backward()
             scale = args.batch_size / args.global_batch_size          # losses / gradients are normalised by the GLOBAL batch
-            flat = torch.cat([w[k].grad.reshape(-1) for k in names]) * scale
-            solver.critic_optimizer.grad.copy_(flat)
+            gviews = solver.critic_arena_views(solver.critic_optimizer.grad)
+            for k in names:
+                gviews[k].copy_(w[k].grad * scale)
             solver._losses[0], solver._losses[1] = float(lq) * scale, float(lc) * scale
         if args.phases & 2:
-            g, off, grads = solver.critic_optimizer.grad, 0, {}
-            for k in names:
-                n = sd[k].numel()
-                grads[k] = g[off:off + n].view(sd[k].shape).clone()
-                off += n
+            gviews = solver.critic_arena_views(solver.critic_optimizer.grad)
+            grads = {k: gviews[k].clone() for k in names}
             O.clip_grad_norm([grads[k] for k in names if k.startswith("critic.")], 5.0)
             O.clip_grad_norm([grads[k] for k in names if k.startswith("constraint_critic.")], 5.0)
             with torch.no_grad():

@@ -302,11 +302,9 @@ def test_critic_update_vs_oracle(S, A, C, B):
     assert_close(glq, lq, RTOL, "loss_q"); assert_close(glc, lc, RTOL, "loss_c")
     assert_close(solver._losses[2], aux["grad_norm_q"], 2e-5, "grad norm Q"); assert_close(solver._losses[3], aux["grad_norm_c"], 2e-5, "grad norm Qc")
     # raw gradients: the arena layout is state_dict order of critic then constraint_critic
-    off, grad = 0, solver.critic_optimizer.grad
+    gviews = solver.critic_arena_views(solver.critic_optimizer.grad)
     for k in [k for k in w if k.startswith(("critic.", "constraint_critic."))]:
-        n = w[k].numel()
-        assert_close(grad[off:off + n].view(w[k].shape), aux["grads_raw"][k], 5e-5, f"grad {k}")
-        off += n
+        assert_close(gviews[k], aux["grads_raw"][k], 5e-5, f"grad {k}")
     sd = solver.state_dict()
     for k in wo:
         if k.startswith(("critic", "constraint_critic")):
@@ -372,13 +370,11 @@ def test_critic_and_multiplier_tensor_mode_vs_oracle(S, A, C, B):
     assert_close(glq, lq, 5e-3, "loss_q (tf32)"); assert_close(glc, lc, 5e-3, "loss_c (tf32)")
     assert_close(solver._losses[2], aux["grad_norm_q"], 2e-2, "grad norm Q (tf32)")
     assert_close(solver._losses[3], aux["grad_norm_c"], 2e-2, "grad norm Qc (tf32)")
-    off, grad = 0, solver.critic_optimizer.grad
+    gviews = solver.critic_arena_views(solver.critic_optimizer.grad)
     for k in [k for k in w if k.startswith(("critic.", "constraint_critic."))]:
-        n = w[k].numel()
         # tf32 products summed over the batch: entries that cancel to ~0 carry the largest relative error
-        assert_close(grad[off:off + n].view(w[k].shape), aux["grads_raw"][k], 2e-2, f"grad {k} (tf32)", max_outlier_frac=1e-2)
-        assert_close(grad[off:off + n].view(w[k].shape), aux["grads_raw"][k], 2e-1, f"grad {k} (tf32, outlier bound)")
-        off += n
+        assert_close(gviews[k], aux["grads_raw"][k], 2e-2, f"grad {k} (tf32)", max_outlier_frac=1e-2)
+        assert_close(gviews[k], aux["grads_raw"][k], 2e-1, f"grad {k} (tf32, outlier bound)")
     eps = torch.randn(B, A, generator=g)
     lm, _ = O.multiplier_update(wo, obs, eps, O.SSACHyper(), C, O.AdamState(), 3e-4)
     glm = solver.update_multiplier(to_dev(obs), eps=to_dev(eps))
