@@ -161,6 +161,20 @@ static __global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict_
   }
 }
 static __global__ void __launch_bounds__(256) act_mask_kernel(float* __restrict__ dX, int64_t ldx, const float* __restrict__ saved, int64_t lds, int M, int N, int mode) {
+  if ((N & 3) == 0 && (ldx & 3) == 0 && (lds & 3) == 0) {             // float4 path: rows are 16-byte aligned
+    const int n4 = N >> 2;
+    const int64_t total = (int64_t)M * n4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t m = i / n4; const int c = (int)(i - m * n4);
+      float4* px = reinterpret_cast<float4*>(dX + m * ldx) + c;
+      const float4 mk = *(reinterpret_cast<const float4*>(saved + m * lds) + c);
+      float4 v = *px;
+      if (mode == 1) { v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f; }
+      else { v.x *= 1.f - mk.x * mk.x; v.y *= 1.f - mk.y * mk.y; v.z *= 1.f - mk.z * mk.z; v.w *= 1.f - mk.w * mk.w; }
+      *px = v;
+    }
+    return;
+  }
   const int64_t total = (int64_t)M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / N; const int n = (int)(i - m * N);
@@ -197,12 +211,20 @@ static __global__ void __launch_bounds__(256) colsum_partial_kernel(const float*
     }
   }
 }
-static __global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ db) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// second stage: block = 32 columns x 8 partial-lanes, fixed summation order
+static __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ db) {
+  __shared__ float sm[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * N + n];
-  db[n] = s;
+  if (n < N) for (int b = w; b < nblocks; b += 8) s += partial[(int64_t)b * N + n];
+  sm[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    db[n] = t;
+  }
 }
 static inline unsigned ew_grid(int64_t work) { int64_t g = (work + 255) / 256; if (g < 1) g = 1; if (g > 148 * 16) g = 148 * 16; return (unsigned)g; }
 
@@ -328,7 +350,7 @@ static inline int linear_bwd_weight(const float* dY, int64_t ldy, const float* X
       while ((int64_t)nb * n_out > partial_floats && nb > 1) nb = (nb + 1) / 2;
       const int rows = (M + nb - 1) / nb;
       DRPO_LAUNCH(colsum_partial_kernel, dim3(1, nb), 256, 0, stream, dY, ldy, M, n_out, rows, partial);
-      DRPO_LAUNCH(colsum_final_kernel, (n_out + 127) / 128, 128, 0, stream, partial, nb, n_out, db);
+      DRPO_LAUNCH(colsum_final_kernel, (n_out + 31) / 32, 256, 0, stream, partial, nb, n_out, db);
     }
     return DRPO_OK;
   }
