@@ -86,6 +86,7 @@ class ClockSampler:
                 flag("nvmlClocksEventReasonSwPowerCap") if hasattr(n, "nvmlClocksEventReasonSwPowerCap") else flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def _run(self):
+        self._stop.wait(0.02)              # let the host queue some launches first: one NVML query stalls the launching thread for ms
         while not self._stop.is_set():
             try:
                 if self.nvml is not None:
@@ -97,7 +98,7 @@ class ClockSampler:
                         self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.05)        # NVML queries take driver locks: keep them sparse so that they do not perturb the launches
+            self._stop.wait(0.25)        # NVML queries take driver locks that stall kernel launches for milliseconds: keep them sparse
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -409,7 +410,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="quadrotor", choices=list(DEFAULT_B0))
