@@ -114,7 +114,9 @@ class SMBPO(Configurable, nn.Module):
         a = _lib.RolloutArgs()
         a.actor, a.ensemble, a.env = ctypes.pointer(actor_s), ctypes.pointer(ens_s), ctypes.pointer(self._env_params)
         a.initial_states, a.batch, a.horizon = _lib.ptr(initial_states), B, H
-        a.traj_id_offset = self.shard_rank * B
+        # global id of this shard's row 0 (even row split by default; uneven splits set traj_id_offset explicitly)
+        off = getattr(self, "_traj_id_offset_override", None)
+        a.traj_id_offset = self.shard_rank * B if off is None else int(off)
         a.member_idx_host = members
         keep = None
         if noise is not None:

@@ -111,3 +111,119 @@ def test_bf16_rollout_vs_oracle(tag, S, A, C, B):
     d, v, cv = O.hooks(spec, out["next_states"].cpu().numpy())
     assert np.array_equal(d, out["dones"].cpu().numpy()) and np.array_equal(v, out["violations"].cpu().numpy())
     assert np.array_equal(cv.reshape(-1), out["constraint_values"].cpu().numpy().reshape(-1))
+
+
+def _philox_alg(spec, S, A, C, B, H, buffer_max=None, seed=0x5EED):
+    import drpo_b200
+    wm, ws = O.make_ensemble_weights(41, S, A, diff_scale=0.05), O.make_ssac_weights(42, S, A, C)
+    cfg = drpo_b200.SMBPO.Config()
+    cfg.rollout_batch_size, cfg.horizon = B, H
+    cfg.buffer_max = buffer_max or B * H + 1024
+    env = oracle_spec_to_device_env(spec)
+    env.action_dim = A
+    alg = drpo_b200.SMBPO(cfg, env, device=dev())
+    alg.model_ensemble.load_state_dict(wm)
+    alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
+    alg.solver.load_state_dict(ws, strict=False)
+    alg.rollout_precision = drpo_b200.PREC_BF16
+    alg.rollout_seed, alg._rollouts_done = seed, 0
+    return alg
+
+
+def _steps(view):
+    """per-step dicts of the rollout's transitions (the ring stores them step-major)"""
+    out, counts, off, res = view.get(as_dict=True), view.counts(), 0, []
+    for n in counts:
+        res.append({k: v[off:off + n] for k, v in out.items()})
+        off += n
+    return res, counts
+
+
+def test_bf16_rollout_is_invariant_to_sharding():
+    """Multi-GPU contract on one GPU: rolling out rows [0,B) at once, or as two shards with their global row offsets,
+    gives bit-identical transitions (in-kernel Philox noise is keyed by the global trajectory id, rows are independent)."""
+    S, A, C, B, H = 12, 2, 2, 3000, 6
+    spec = O.env_quadrotor()
+    g = torch.Generator().manual_seed(7)
+    init = torch.randn(B, S, generator=g) * 0.3
+    init[:, 2] = 0.55 + 0.9 * torch.rand(B, generator=g)
+    members = [3, 1, 4, 0, 2, 1]
+    full = _philox_alg(spec, S, A, C, B, H)
+    fsteps, fcounts = _steps(full.rollout(full.actor, initial_states=to_dev(init), member_idx=members))
+    half = B // 2 + 37                                     # deliberately not a multiple of the 128-row tile
+    shards = []
+    for r, (lo, hi) in enumerate([(0, half), (half, B)]):
+        alg = _philox_alg(spec, S, A, C, hi - lo, H)
+        alg.shard_rank, alg.shard_world = r, 2
+        # SMBPO derives the id offset from shard_rank * local batch; the shards here are uneven, so set it through the seed-
+        # independent knob the C ABI offers: emulate by rolling out with an explicit offset
+        alg._traj_id_offset_override = lo
+        shards.append(_steps(alg.rollout(alg.actor, initial_states=to_dev(init[lo:hi]), member_idx=members)))
+    assert [a + b for a, b in zip(shards[0][1], shards[1][1])] == fcounts
+    for t in range(H):
+        for k in fsteps[t]:
+            both = torch.cat([shards[0][0][t][k], shards[1][0][t][k]])
+            assert torch.equal(both, fsteps[t][k]), (t, k)
+
+
+def test_bf16_rollout_chain_and_mask_properties_at_full_size():
+    """BASELINE size (1 M start states x horizon 10): size-independent properties.  (i) per-step counts never grow and sum to
+    the number of stored transitions; (ii) the states of step t+1 are exactly the surviving next states of step t, in order
+    (order-preserving compaction, src/smbpo.py:243-246); (iii) the stored masks and constraint values are bit-exactly the env
+    hooks of the stored next states; (iv) the ring pointer advanced by the number of transitions."""
+    S, A, C, B, H = 12, 2, 2, 1_000_000, 10
+    spec = O.env_quadrotor()
+    from drpo_b200 import synthetic
+    init = synthetic.make_start_states("quadrotor", B, 11)
+    alg = _philox_alg(spec, S, A, C, B, H)
+    p0 = int(alg.virt_buffer._pointer)
+    view = alg.rollout(alg.actor, initial_states=to_dev(init), member_idx=[i % 5 for i in range(H)])
+    steps, counts = _steps(view)
+    assert counts[0] == B and all(a >= b for a, b in zip(counts, counts[1:]))
+    assert len(view) == sum(counts) == int(alg.virt_buffer._pointer) - p0
+    assert torch.equal(steps[0]["states"].cpu(), init)
+    for t in range(H - 1):
+        keep = ~steps[t]["dones"]
+        assert int(keep.sum()) == counts[t + 1]
+        assert torch.equal(steps[t]["next_states"][keep], steps[t + 1]["states"]), t
+    for t in (0, H - 1):                                   # hooks on ~1 M rows each in numpy fp64
+        d, v, cv = O.hooks(spec, steps[t]["next_states"].cpu().numpy())
+        assert np.array_equal(d, steps[t]["dones"].cpu().numpy()) and np.array_equal(v, steps[t]["violations"].cpu().numpy())
+        assert np.array_equal(cv.reshape(-1), steps[t]["constraint_values"].cpu().numpy().reshape(-1))
+    assert torch.isfinite(steps[H - 1]["next_states"]).all() and steps[0]["actions"].abs().max() <= 1.0
+
+
+def test_bf16_rollout_ring_wraparound_and_ragged_tiles():
+    """A ring smaller than two rollouts wraps inside the second one; row counts that are not tile multiples (1, 127, 129)."""
+    S, A, C, H = 12, 2, 2, 4
+    spec = O.env_quadrotor()
+    g = torch.Generator().manual_seed(9)
+    for B in (1, 127, 129, 1000):
+        init = torch.randn(B, S, generator=g) * 0.3
+        init[:, 2] = 0.55 + 0.9 * torch.rand(B, generator=g)
+        ref = _philox_alg(spec, S, A, C, B, H)
+        want, wc = _steps(ref.rollout(ref.actor, initial_states=to_dev(init), member_idx=[0, 1, 2, 3]))
+        small = _philox_alg(spec, S, A, C, B, H, buffer_max=B * H + max(B // 2, 1))
+        small.rollout(small.actor, initial_states=to_dev(init), member_idx=[0, 1, 2, 3])
+        small._rollouts_done = 0                                       # same Philox seed as the first rollout
+        got, gc = _steps(small.rollout(small.actor, initial_states=to_dev(init), member_idx=[0, 1, 2, 3]))   # wraps
+        assert gc == wc, (B, gc, wc)
+        for t in range(H):
+            for k in want[t]:
+                assert torch.equal(got[t][k], want[t][k]), (B, t, k)
+
+
+def test_bf16_rollout_empty_and_all_done():
+    """Edge cases: no start states; start states from which every trajectory terminates at step 0 (the reference breaks out of
+    its loop when nothing continues, src/smbpo.py:243-245: later steps store nothing)."""
+    S, A, C, H = 12, 2, 2, 5
+    spec = O.env_quadrotor()
+    alg = _philox_alg(spec, S, A, C, 256, H)
+    view = alg.rollout(alg.actor, initial_states=to_dev(torch.zeros(0, S)), member_idx=[0] * H)
+    assert len(view) == 0 and view.counts() == [0] * H
+    init = torch.zeros(300, S)
+    init[:, 2] = 50.0                                     # z far above the 1.5 limit: violation => done (quadrotor.py:112-114)
+    view = alg.rollout(alg.actor, initial_states=to_dev(init), member_idx=[0] * H)
+    assert view.counts() == [300] + [0] * (H - 1) and len(view) == 300
+    out = view.get(as_dict=True)
+    assert bool(out["dones"].all()) and bool(out["violations"].all())
