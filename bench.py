@@ -230,13 +230,13 @@ def run_ours(args):
     pk = peaks()
     step_ms = ms_total / args.steps
     import ctypes
-    rows_launched, kt, kn = 0, ctypes.c_double(0.0), ctypes.c_int64(0)
+    rows_launched, kt, kn, ksat = 0, ctypes.c_double(0.0), ctypes.c_int64(0), ctypes.c_double(0.0)
     lib.drpo_timing_enable(1)
     for _ in range(args.steps):
         v = step_device()
         rows_launched += int(v.step_counts[:-1].sum())               # alive rows of every step = rows each launch processed
     torch.cuda.synchronize()
-    _lib.check(lib.drpo_timing_read(ctypes.byref(kt), ctypes.byref(kn)), "drpo_timing_read")
+    _lib.check(lib.drpo_timing_read(ctypes.byref(kt), ctypes.byref(kn), ctypes.byref(ksat)), "drpo_timing_read")
     lib.drpo_timing_enable(0)
     if kn.value > 0 and precision == drpo_b200.PREC_BF16:
         avg_ms = kt.value / kn.value
@@ -248,6 +248,14 @@ def run_ours(args):
                     "kernel": "rollout_step_umma_kernel (policy + ensemble-member GEMM chain + epilogues), one launch per rollout step",
                     "avg_launch_ms": round(avg_ms, 4), "launches_timed": int(kn.value), "kernel_share_of_step": round(kt.value / (step_ms * args.steps), 3),
                     "algorithmic_flops_per_transition": flops_per_transition(S, A), "rows_per_launch": round(rows_launched / kn.value, 1)}
+        # the step's HBM-bound satellites (hooks + ring store, order-preserving compaction): algorithmic bytes per row =
+        # read 4(2S+A+1) + write record 4(2S+A+1+C)+2 + done flag 1 (store), read done 1 + 4S + id 4, write survivors 4S+4 (compaction)
+        sat_bytes_row = (4 * (2 * S + A + 1) + 4 * (2 * S + A + 1 + C) + 2 + 1) + (1 + 4 * S + 4 + 4 * S + 4)
+        if ksat.value > 0:
+            sat_gbs = sat_bytes_row * rows_launched / (ksat.value * 1e-3) / 1e9
+            roofline["elementwise"] = {"bound": "hbm", "kernels": "hooks_store_kernel + compact_count/scan/scatter", "achieved": round(sat_gbs, 1),
+                                       "peak": pk["hbm"], "unit": "GB/s", "frac": round(sat_gbs / pk["hbm"], 4),
+                                       "avg_ms_per_step": round(ksat.value / kn.value, 4), "algorithmic_bytes_per_row": sat_bytes_row}
     else:
         per_gpu_tr_per_step = transitions / world / args.steps
         achieved_tf = flops_per_transition(S, A) * per_gpu_tr_per_step / (step_ms * 1e-3) / 1e12

@@ -124,7 +124,7 @@ SYMBOLS = [
     ("drpo_launch_count", C.c_int64, []),
     ("drpo_kernel_status", C.c_int, []),
     ("drpo_timing_enable", None, [C.c_int32]),
-    ("drpo_timing_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    ("drpo_timing_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     ("drpo_philox_normal", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     ("drpo_hooks_eval", C.c_int, [C.POINTER(EnvParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drpo_ensemble_workspace_bytes", C.c_int64, [C.POINTER(Ensemble), C.c_int64]),

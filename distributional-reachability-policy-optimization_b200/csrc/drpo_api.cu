@@ -41,9 +41,9 @@ int drpo_abi_version(void) { return DRPO_ABI_VERSION; }
 int64_t drpo_launch_count(void) { return g_launch_count; }
 int drpo_kernel_status(void) { return umma_kernel_status(); }
 void drpo_timing_enable(int32_t on) { umma_timing_enable(on); }
-int drpo_timing_read(double* total_ms_host, int64_t* launches_host) {
+int drpo_timing_read(double* total_ms_host, int64_t* launches_host, double* satellites_ms_host) {
   DRPO_CHECK_ARG(total_ms_host && launches_host, "drpo_timing_read: NULL output");
-  return umma_timing_read(total_ms_host, launches_host);
+  return umma_timing_read(total_ms_host, launches_host, satellites_ms_host);
 }
 
 int drpo_philox_normal(float* out, int64_t n, int32_t cols, const int32_t* row_ids, uint64_t seed, uint32_t stream_tag,

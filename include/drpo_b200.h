@@ -302,10 +302,11 @@ int drpo_abi_version(void);
  * the results of that rollout are invalid).  Synchronises the device; message via drpo_last_error(). */
 int drpo_kernel_status(void);
 /* Measurement aid (bench.py's roofline): while enabled, every launch of the fused rollout step kernel is bracketed by CUDA
- * events on the caller's stream; drpo_timing_read synchronises them and returns their summed duration and count since
- * the last drpo_timing_enable call. */
+ * events on the caller's stream, and a third event follows the step's HBM-bound satellites (hooks + ring store, compaction);
+ * drpo_timing_read synchronises them and returns the summed kernel duration, the launch count and (optional) the summed
+ * duration of the satellites since the last drpo_timing_enable call. */
 void drpo_timing_enable(int32_t on);
-int drpo_timing_read(double* total_ms_host, int64_t* launches_host);
+int drpo_timing_read(double* total_ms_host, int64_t* launches_host, double* satellites_ms_host);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t drpo_launch_count(void);
 
