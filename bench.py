@@ -280,6 +280,7 @@ def run_ours(args):
         "roofline": roofline,
     }
 
+    _lib.check_kernel_status("bench rollout")        # a pipeline-protocol time-out inside the fused kernel would invalidate the numbers
     # ---- SSAC critic updates/s (second half of the metric) -------------------------------------------------------------
     if not args.skip_critic:
         out["critic"] = bench_critic(args, device, world, rank, pk)
