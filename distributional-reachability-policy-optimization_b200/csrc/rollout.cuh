@@ -128,6 +128,17 @@ static __global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint
   // element-parallel copy: consecutive threads read consecutive floats of the block's rows (coalesced) and write the kept
   // rows' floats, which are contiguous in the destination as well (order-preserving compaction)
   const int rows = (int)min((int64_t)CBLK, (int64_t)n - r0);
+  if ((S & 3) == 0) {                                     // 16-byte rows: float4 copies
+    const int S4 = S >> 2;
+    const float4* src = reinterpret_cast<const float4*>(ns) + r0 * S4;
+    float4* dst = reinterpret_cast<float4*>(cur_next);
+    for (int i = threadIdx.x; i < rows * S4; i += CBLK) {
+      const int rr = i / S4, c = i - rr * S4;
+      const int d = dst_row[rr];
+      if (d >= 0) dst[(int64_t)d * S4 + c] = src[i];
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < rows * S; i += CBLK) {
     const int rr = i / S, c = i - rr * S;
     const int d = dst_row[rr];
