@@ -308,7 +308,8 @@ def bench_critic(args, device, world, rank, pk):
     cfg.constraint_critic_cfg.std_ratio = 1.0
     solver = drpo_b200.SSAC(cfg, S, A, C, HORIZON, 100, 1000, 10, 5.0, device=device)
     solver.load_state_dict(synthetic.make_ssac_weights(43567, S, A, C), strict=False)
-    solver.precision = {"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16}[args.precision]   # bf16 = tensor-core mode (TF32 GEMMs)
+    cprec = os.environ.get("DRPO_BENCH_CRITIC_PRECISION", args.precision)       # fp32 | bf16 (fused tcgen05 kernels) | tf32 (cuBLAS)
+    solver.precision = {"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16, "tf32": drpo_b200.PREC_TF32}[cprec]
     solver.data_parallel = world > 1
     full = synthetic.make_critic_batch(CRITIC_WORKLOAD, Bg, 49283)
     batch = [t[rank * B:(rank + 1) * B].to(device) for t in full]
@@ -334,7 +335,8 @@ def bench_critic(args, device, world, rank, pk):
     ach = fl * ups / 1e12 / world
     res = {"metric": "ssac_critic_updates_per_s", "value": ups, "unit": "updates/s", "samples_per_s": ups * Bg,
            "global_batch": Bg, "per_gpu_batch": B, "scaling": "strong", "ms_per_update": float(ms) / n,
-           "dtype": "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer" if args.precision == "bf16" else "f32",
+           "dtype": {"bf16": "bf16 (fused tcgen05 forward/loss/dX kernel + tcgen05 dW kernel), fp32 accumulate/optimizer",
+                     "tf32": "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer", "fp32": "f32"}[cprec],
            "gpu_launches": int(lib.drpo_launch_count() - l0), "loss_q": float(lq), "loss_c": float(lc),
            "roofline": {"bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                         "frac": round(ach / pk["tensor_sustained"], 5), "traffic": None,

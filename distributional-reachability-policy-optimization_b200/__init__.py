@@ -12,4 +12,4 @@ from .policy import SquashedGaussianPolicy                              # noqa: 
 from .ssac import SSAC, ConstraintCritic, CriticEnsemble, MLPMultiplier  # noqa: F401
 from .smbpo import SMBPO                                                # noqa: F401
 
-PREC_FP32, PREC_BF16 = _lib.PREC_FP32, _lib.PREC_BF16
+PREC_FP32, PREC_BF16, PREC_TF32 = _lib.PREC_FP32, _lib.PREC_BF16, _lib.PREC_TF32

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdrpo_sm100.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 ENV_POINT_ROBOT, ENV_BOUNDED, ENV_TRACKING = 0, 1, 2
 MAX_ACTIVE, MAX_DONE_DIMS, MAX_HAZARDS, MAX_CON = 4, 4, 4, 8
 
@@ -142,6 +142,8 @@ SYMBOLS = [
     ("drpo_debug_rollout_layer", C.c_int, [C.POINTER(RolloutArgs), C.c_int32, C.c_void_p]),
     ("drpo_critic_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_critic_step", C.c_int, [C.POINTER(CriticArgs)]),
+    ("drpo_debug_critic_rows", C.c_int, [C.c_void_p]),
+    ("drpo_debug_critic_dw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drpo_multiplier_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_multiplier_step", C.c_int, [C.POINTER(MultiplierArgs)]),
     ("drpo_qc_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32]),

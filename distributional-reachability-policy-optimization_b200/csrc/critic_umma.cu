@@ -1,0 +1,1009 @@
+// DRPO_PREC_BF16 critic step (SSAC.update_critic, src/ssac.py:437-456): the forward of all nine passes, the targets, the
+// losses and the dX half of the backward pass run in ONE persistent tcgen05 kernel per update; the dW half is a second
+// tcgen05 kernel (split-K over the batch); a table-driven reduce kernel assembles the flat gradient arena.
+//
+//   critic_fused_kernel   one CTA per SM, 128 batch rows per tile.  Per tile, 24 dense "ops" (one nn.Linear each, the Qc
+//       trunk back-propagation being one op with two K parts) run as tcgen05.mma (bf16 x bf16 -> fp32) into four 64-column
+//       TMEM accumulators; four epilogue groups (one per accumulator / 64-column slab, thread = batch row) apply bias + ReLU,
+//       keep the activation in TMEM as the next op's A operand (TS-mode MMA), evaluate the narrow heads (policy mean/log-std,
+//       Q, Qc mean/log-std) with CUDA-core dot products, and - once the row's targets are known - turn the per-row loss
+//       gradients into dH tiles that feed the transposed-weight MMAs.  Weights (forward and transposed images, packed once
+//       per update) stream through a shared-memory ring by TMA bulk copies.  What leaves the SM: the activations and
+//       activation gradients the dW kernel needs (bf16, "octet" layout below), per-CTA column sums (bias / head-weight
+//       gradients, warp-shuffle butterflies + shared-memory accumulators) and the two loss partials.
+//   critic_dw_kernel      dW[out,in] = sum_rows dH[row,out] * H[row,in]: both operands are read straight from the octet
+//       layout as MN-major UMMA operands (K = batch rows), 256 x N fp32 accumulated in TMEM, one partial per CTA.
+//   critic_grad_reduce_kernel   sums the split-K partials / per-CTA column sums into the gradient arena.
+//
+// Octet layout of a saved [rows, F] bf16 matrix: element (r, f) at ((f / 8) * rows_padded + r) * 8 + f % 8, i.e. one
+// [rows, 8] panel per 8 features.  The fused kernel's threads (one per row) write 16-byte vectors that are contiguous across
+// a warp, and a 64-row slab of one panel is a contiguous 1 KB block = 8 no-swizzle MN-major core matrices.
+#include <cuda_bf16.h>
+
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "critic.cuh"
+#include "critic_umma_api.h"
+#include "tc05.cuh"
+
+namespace drpo {
+namespace cu {
+
+using namespace tc;
+
+constexpr int HID = 256;                   // hidden width of every SSAC net (src/ssac.py:18-21)
+constexpr int TILE = 128;                  // batch rows per tile = TMEM lanes
+constexpr int NGROUPS = 4;                 // epilogue groups = 64-column slabs = accumulators
+constexpr int EPI_THREADS = NGROUPS * 128;
+constexpr int F_THREADS = EPI_THREADS + 64;   // + warp 16 TMA producer, warp 17 MMA issuer (owns the TMEM allocation)
+constexpr int MAX_OPS = 24;
+constexpr int MAXO = 4;                    // widest CUDA-core head: 2*action_dim <= 4, con_dim <= 4
+constexpr uint32_t CHUNK_BYTES = 64 * HID * 2;   // one ring stage: 64 output columns x K=256 bf16
+constexpr uint32_t TM_ACC = 0, TM_R0 = 256, TM_R1 = 384;
+
+enum ASrc { A_XS0 = 0, A_XS1 = 1, A_R0 = 2, A_R1 = 3 };
+
+struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t pad; };
+
+struct FusedParams {
+  FOp op[MAX_OPS];
+  int n_ops;
+  const uint8_t* wimg;
+  const float* ctab; int ctab_floats;
+  // offsets (floats) into ctab
+  int bias_off[MAX_OPS];                   // [256] bias of forward op i
+  int hw_actor[2], hb_actor[2];            // head weights [2A][256] / bias [2A]: actor, actor_safe
+  int hw_qt[2], hb_qt[2], hw_q[2], hb_q[2];
+  int hw_ctm, hb_ctm, hw_ctl, hb_ctl;      // target Qc mean / log-std heads [C][256]
+  int hw_cm, hb_cm, hw_cl, hb_cl;          // online Qc heads
+  // batch
+  const float *obs, *act, *next_obs, *rew, *cv; const uint8_t* done;
+  NoiseView n_actor, n_safe, n_qc;
+  const float* log_alpha;
+  float gamma, one_minus_gamma, td_bound, inv_bg, inv_bgc;
+  int64_t B, Bpad; int S, A, C, D, Kx, stages, n_tiles;
+  // saved activations (octet layout, Bpad rows)
+  __nv_bfloat16 *x_sa, *q_h1[2], *q_dh2[2], *q_dh1[2], *c_t1, *c_t2, *c_dm1, *c_dl1, *c_dt2, *c_dt1;
+  float* gacc_out; int nv;                 // [grid][nv*256] per-CTA column sums
+  double* loss_part;                       // [grid][2]
+  int* err_flag;
+  float* dbg;                              // optional [B,16] per-row intermediates (tests)
+};
+
+// slots of the per-CTA column-sum accumulators (each 256 floats)
+__host__ __device__ inline int slot_q_w2(int i) { return 3 * i; }
+__host__ __device__ inline int slot_q_b1(int i) { return 3 * i + 1; }
+__host__ __device__ inline int slot_q_b0(int i) { return 3 * i + 2; }
+constexpr int SLOT_C_BM0 = 6, SLOT_C_BL0 = 7, SLOT_C_BT1 = 8, SLOT_C_BT0 = 9, SLOT_SCAL = 10, SLOT_C_WM = 11;
+__host__ __device__ inline int slot_c_wm(int c) { return SLOT_C_WM + c; }
+__host__ __device__ inline int slot_c_wl(int c, int C) { return SLOT_C_WM + C + c; }
+__host__ __device__ inline int n_slots(int C) { return SLOT_C_WM + 2 * C; }
+// scalars inside SLOT_SCAL: [0,1] dL/d q_i bias, [2..2+C) mean-head bias, [2+C..2+2C) log-std-head bias
+
+struct FusedSmem {
+  uint64_t full[6], empty[6], acc_full[NGROUPS], acc_free[NGROUPS], act_ready;
+  uint32_t tmem_base, pad[3];
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight images: 256 x kp bf16 per image, four 64-column chunks, each in the canonical K-major no-swizzle layout
+//   [n/8][k/8][8 rows][8 elems];  transposed images hold W^T (the backward op's B operand)
+// ---------------------------------------------------------------------------------------------------------------
+struct PackEntry { const float* W; int n_real, k_real, kp, transposed; int64_t dst; };
+struct PackTable { PackEntry e[28]; int n; };
+__global__ void pack_images_kernel(PackTable t, __nv_bfloat16* __restrict__ img) {
+  const PackEntry e = t.e[blockIdx.y];
+  const int total = HID * e.kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / e.kp, k = i - n * e.kp;
+    float v = 0.f;
+    if (n < e.n_real && k < e.k_real) v = e.transposed ? e.W[(int64_t)k * e.n_real + n] : e.W[(int64_t)n * e.k_real + k];
+    const int c = n >> 6, nin = n & 63;
+    const int64_t idx = (int64_t)c * 64 * e.kp + ((int64_t)(nin >> 3) * (e.kp >> 3) + (k >> 3)) * 64 + (nin & 7) * 8 + (k & 7);
+    img[e.dst + idx] = __float2bfloat16_rn(v);
+  }
+}
+// constant table: gathers biases / head weights (fp32) into one contiguous block
+struct CopyEntry { const float* src; int n; int dst; };
+struct CopyTable { CopyEntry e[48]; int n; };
+__global__ void gather_ctab_kernel(CopyTable t, float* __restrict__ out) {
+  const CopyEntry e = t.e[blockIdx.x];
+  for (int i = threadIdx.x; i < e.n; i += blockDim.x) out[e.dst + i] = e.src[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+
+// column sums over the 32 rows of a warp: v[j] = this row's value of column j; returns the sum of column `lane`
+__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
+  float w[16];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float keep = b4 ? v[i + 16] : v[i], send = b4 ? v[i] : v[i + 16];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = b3 ? w[i + 8] : w[i], send = b3 ? w[i] : w[i + 8];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = b2 ? w[i + 4] : w[i], send = b2 ? w[i] : w[i + 4];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = b1 ? w[i + 2] : w[i], send = b1 ? w[i] : w[i + 2];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float keep = b0 ? w[1] : w[0], send = b0 ? w[0] : w[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// per-thread view of the fused kernel's epilogue state
+struct Epi {
+  FusedSmem* sm;
+  const float* ctab;        // shared-memory copy of the constant table
+  float* gacc;              // shared-memory column-sum accumulators [nv][256]
+  float4* hp;               // head partials [4 groups][128 rows] (float4 = up to MAXO outputs)
+  uint32_t tm;              // TMEM base + this warp's lane offset
+  int g, row, lane;         // epilogue group (64-column slab), row within the tile, lane
+  int64_t grow, Bpad;       // global row, padded row count
+  bool valid;
+  uint32_t it;              // global index of the op whose epilogue runs next (parity of the per-op barriers)
+  int* err;
+};
+
+__device__ __forceinline__ void epi_wait_acc(Epi& e) {
+  mbar_wait(&e.sm->acc_full[e.g], e.it & 1, e.err, 100 + e.g);
+  tc_fence_after();
+}
+__device__ __forceinline__ void epi_free_acc(Epi& e) {
+  tc_fence_before();
+  mbar_arrive(&e.sm->acc_free[e.g]);
+}
+// all of this op's MMAs (every chunk) have completed: the op's A regions may be overwritten
+__device__ __forceinline__ void epi_wait_all_mma(Epi& e) {
+  mbar_wait(&e.sm->acc_full[NGROUPS - 1], e.it & 1, e.err, 110);
+  tc_fence_after();
+}
+__device__ __forceinline__ void epi_op_done(Epi& e) {      // this thread's TMEM / shared writes for the next op are complete
+  tmem_st_wait();
+  tc_fence_before();
+  mbar_arrive(&e.sm->act_ready);
+}
+// 16-byte panels of 32 packed columns -> global octet layout
+__device__ __forceinline__ void save_octets(const Epi& e, __nv_bfloat16* base, int half, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int oct = e.g * 8 + half * 4 + o;
+    uint4 v = make_uint4(pk[4 * o], pk[4 * o + 1], pk[4 * o + 2], pk[4 * o + 3]);
+    *reinterpret_cast<uint4*>(base + ((int64_t)oct * e.Bpad + e.grow) * 8) = v;
+  }
+}
+__device__ __forceinline__ void add_colsum(const Epi& e, int slot, int half, const float (&v)[32]) {
+  const float s = colsum32(v, e.lane);
+  atomicAdd(&e.gacc[slot * HID + e.g * 64 + half * 32 + e.lane], s);
+}
+
+// forward epilogue of one 64-column slab: h = relu(acc + bias).
+//   out_region != 0 : store packed bf16 to that TMEM region (next op's A operand / stash)
+//   save != nullptr : store to the global octet array
+//   mask != nullptr : record h > 0 (64 bits)
+//   NO > 0          : accumulate the head dot products hpart[o] += h . hw[o][cols]
+//   wait_all        : wait for every MMA of the op before touching out_region (it is one of the op's own A regions)
+template <int NO>
+__device__ __forceinline__ void epi_forward(Epi& e, int bias_off, uint32_t out_region, __nv_bfloat16* save, uint64_t* mask,
+                                            int hw_off, float (&hpart)[MAXO], bool wait_all) {
+  epi_wait_acc(e);
+  uint64_t m = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t raw[32];
+    tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
+    tmem_ld_wait();
+    if (half == 1) epi_free_acc(e);
+    const float4* b4 = reinterpret_cast<const float4*>(e.ctab + bias_off + e.g * 64 + half * 32);
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = b4[j];
+      h[4 * j] = fmaxf(__uint_as_float(raw[4 * j]) + b.x, 0.f);
+      h[4 * j + 1] = fmaxf(__uint_as_float(raw[4 * j + 1]) + b.y, 0.f);
+      h[4 * j + 2] = fmaxf(__uint_as_float(raw[4 * j + 2]) + b.z, 0.f);
+      h[4 * j + 3] = fmaxf(__uint_as_float(raw[4 * j + 3]) + b.w, 0.f);
+    }
+    if (NO > 0) {
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
+        float acc = hpart[o];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = w4[j];
+          acc = fmaf(h[4 * j], w.x, acc); acc = fmaf(h[4 * j + 1], w.y, acc);
+          acc = fmaf(h[4 * j + 2], w.z, acc); acc = fmaf(h[4 * j + 3], w.w, acc);
+        }
+        hpart[o] = acc;
+      }
+    }
+    if (mask) {
+      uint32_t mm = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mm |= (h[j] > 0.f ? 1u : 0u) << j;
+      m |= (uint64_t)mm << (32 * half);
+    }
+    if (out_region || save) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(h[2 * j], h[2 * j + 1]);
+      if (save) save_octets(e, save, half, pk);
+      if (out_region) {
+        if (wait_all && half == 0) epi_wait_all_mma(e);
+        tmem_st16(e.tm + out_region + e.g * 32 + half * 16, pk);
+      }
+    }
+  }
+  if (mask) *mask = m;
+  ++e.it;
+}
+
+// backward epilogue: dh = mask ? acc : 0; column sums -> bias gradient; save; optional TMEM store for the next backward op
+__device__ __forceinline__ void epi_backward(Epi& e, uint64_t mask, int bias_slot, __nv_bfloat16* save, uint32_t out_region,
+                                             bool wait_all) {
+  epi_wait_acc(e);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t raw[32];
+    tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
+    tmem_ld_wait();
+    if (half == 1) epi_free_acc(e);
+    const uint32_t mm = (uint32_t)(mask >> (32 * half));
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((mm >> j) & 1u) ? __uint_as_float(raw[j]) : 0.f;
+    add_colsum(e, bias_slot, half, v);
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    save_octets(e, save, half, pk);
+    if (out_region) {
+      if (wait_all && half == 0) epi_wait_all_mma(e);
+      tmem_st16(e.tm + out_region + e.g * 32 + half * 16, pk);
+    }
+  }
+  ++e.it;
+}
+
+// After the row's output gradients d[o] are known: read the stashed activation h (packed bf16 in `region`), accumulate the
+// head-weight gradient column sums d[o]*h, form dh = (h > 0) * sum_o d[o]*hw[o][col], its column sums (bias gradient of the
+// layer that produced h), store dh over h and save it.
+template <int NO>
+__device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const float (&d)[MAXO], int hw_off, int w_slot0, int bias_slot,
+                                                  __nv_bfloat16* save) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t hp16[16];
+    tmem_ld16(e.tm + region + e.g * 32 + half * 16, hp16);
+    tmem_ld_wait();
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { h[2 * j] = bf_lo(hp16[j]); h[2 * j + 1] = bf_hi(hp16[j]); }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = d[o] * h[j];
+      add_colsum(e, w_slot0 + o, half, t);
+    }
+    float dh[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dh[j] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w = w4[j];
+        dh[4 * j] = fmaf(d[o], w.x, dh[4 * j]); dh[4 * j + 1] = fmaf(d[o], w.y, dh[4 * j + 1]);
+        dh[4 * j + 2] = fmaf(d[o], w.z, dh[4 * j + 2]); dh[4 * j + 3] = fmaf(d[o], w.w, dh[4 * j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dh[j] = h[j] > 0.f ? dh[j] : 0.f;
+    add_colsum(e, bias_slot, half, dh);
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(dh[2 * j], dh[2 * j + 1]);
+    save_octets(e, save, half, pk);
+    tmem_st16(e.tm + region + e.g * 32 + half * 16, pk);
+  }
+}
+
+// head outputs of the row: sum of the four groups' partials + bias
+template <int NO>
+__device__ __forceinline__ void head_combine(Epi& e, const float (&hpart)[MAXO], int hb_off, float (&out)[MAXO]) {
+  float4 mine = make_float4(hpart[0], NO > 1 ? hpart[1] : 0.f, NO > 2 ? hpart[2] : 0.f, NO > 3 ? hpart[3] : 0.f);
+  e.hp[e.g * TILE + e.row] = mine;
+  named_bar_sync(1, EPI_THREADS);
+  float4 s = e.hp[e.row];
+#pragma unroll
+  for (int gg = 1; gg < NGROUPS; ++gg) {
+    const float4 p = e.hp[gg * TILE + e.row];
+    s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+  }
+  out[0] = s.x + e.ctab[hb_off];
+  if (NO > 1) out[1] = s.y + e.ctab[hb_off + 1];
+  if (NO > 2) out[2] = s.z + e.ctab[hb_off + 2];
+  if (NO > 3) out[3] = s.w + e.ctab[hb_off + 3];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the fused forward / loss / dX kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int A, int C>
+__global__ void __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int stages = p.stages;
+  uint8_t* ring = smem;
+  uint8_t* xs0 = ring + (size_t)stages * CHUNK_BYTES;
+  uint8_t* xs1 = xs0 + TILE * p.Kx * 2;
+  float* ctab = reinterpret_cast<float*>(xs1 + TILE * p.Kx * 2);
+  float* gacc = ctab + ((p.ctab_floats + 3) & ~3);
+  float4* hp = reinterpret_cast<float4*>(gacc + p.nv * HID);
+  FusedSmem* sm = reinterpret_cast<FusedSmem*>(hp + NGROUPS * TILE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PRODUCER = EPI_THREADS / 32, ISSUER = PRODUCER + 1;
+  int* err = p.err_flag;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+    for (int g = 0; g < NGROUPS; ++g) { mbar_init(&sm->acc_full[g], 1); mbar_init(&sm->acc_free[g], 128); }
+    mbar_init(&sm->act_ready, EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == ISSUER) tmem_alloc(&sm->tmem_base, 512);
+  for (int i = threadIdx.x; i < p.ctab_floats; i += F_THREADS) ctab[i] = p.ctab[i];
+  for (int i = threadIdx.x; i < p.nv * HID; i += F_THREADS) gacc[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == PRODUCER) {
+    // ---- TMA producer: (tile, op, chunk, part) weight blocks through the ring ---------------------------------------------
+    if (elect_one()) {
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t)
+        for (int o = 0; o < p.n_ops; ++o) {
+          const FOp op = p.op[o];
+          const uint32_t bytes = 64u * op.kp * 2u;
+          for (int c = 0; c < NGROUPS; ++c)
+            for (int part = 0; part < op.parts; ++part, ++n) {
+              const uint32_t s = n % stages, ph = (n / stages) & 1;
+              mbar_wait(&sm->empty[s], ph ^ 1, err, 1);
+              mbar_expect_tx(&sm->full[s], bytes);
+              bulk_g2s(ring + (size_t)s * CHUNK_BYTES, p.wimg + op.w_off[part] + (size_t)c * bytes, bytes, &sm->full[s]);
+            }
+        }
+    }
+  } else if (warp == ISSUER) {
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------------
+    uint32_t n = 0, it = 0;
+    const uint32_t ring_addr = smem_u32(ring), xs_addr[2] = {smem_u32(xs0), smem_u32(xs1)};
+    for (int t = 0; t < my_tiles; ++t)
+      for (int o = 0; o < p.n_ops; ++o, ++it) {
+        const FOp op = p.op[o];
+        const int nk = op.kp >> 4;
+        const uint32_t idesc = make_idesc(64);
+        mbar_wait(&sm->act_ready, it & 1, err, 2);
+        tc_fence_after();
+        for (int c = 0; c < NGROUPS; ++c) {
+          mbar_wait(&sm->acc_free[c], (it & 1) ^ 1, err, 3);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + TM_ACC + c * 64;
+          for (int part = 0; part < op.parts; ++part, ++n) {
+            const uint32_t s = n % stages, ph = (n / stages) & 1;
+            mbar_wait(&sm->full[s], ph, err, 4);
+            tc_fence_after();
+            // B: chunk image [64 cols][kp] K-major: LBO = 128 B (next K octet), SBO = kp*16 B (next 8 columns)
+            const uint64_t bd = make_desc(ring_addr + s * CHUNK_BYTES, 128, (uint32_t)op.kp * 16);
+            const uint32_t b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
+            const int src = op.a_src[part];
+            if (elect_one()) {
+              if (src <= A_XS1) {
+                // A: [128 rows][Kx] K-major in shared memory: LBO = 2048 B (next K octet), SBO = 128 B (next 8 rows)
+                const uint64_t ad = make_desc(xs_addr[src], 2048, 128);
+                const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < nk) mma_ss_p(d_tmem, a_lo + k * 256, a_hi, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
+              } else {
+                const uint32_t a_tmem = tmem + (src == A_R0 ? TM_R0 : TM_R1);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) mma_ts_p(d_tmem, a_tmem + k * 8, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
+              }
+              tc_commit(&sm->empty[s]);
+              if (part == op.parts - 1) tc_commit(&sm->acc_full[c]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+  } else {
+    // ---- epilogue groups ----------------------------------------------------------------------------------------------------
+    Epi e;
+    e.sm = sm; e.ctab = ctab; e.gacc = gacc; e.hp = hp; e.g = warp >> 2; e.lane = lane; e.row = (warp & 3) * 32 + lane;
+    e.tm = tmem + ((uint32_t)((warp & 3) * 32) << 16); e.it = 0; e.err = err; e.Bpad = p.Bpad;
+    const int S = p.S, D = p.D;
+    const float alpha = expf(*p.log_alpha);
+    double loss_q = 0.0, loss_c = 0.0;
+    float sc_q[2] = {0.f, 0.f}, sc_m[C], sc_l[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { sc_m[c] = 0.f; sc_l[c] = 0.f; }
+
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      e.grow = (int64_t)tile * TILE + e.row;
+      e.valid = e.grow < p.B;
+      const int64_t gr = e.valid ? e.grow : 0;
+      // ---- stage the tile's inputs: xs0 = [next_obs, 0], xs1 = [obs, act] (bf16, K-major), x_sa octets to global -------
+      for (int j = e.g; j < (p.Kx >> 3); j += NGROUPS) {
+        uint32_t w0[4], w1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a0[2], a1[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k = j * 8 + q * 2 + u;
+            a0[u] = (e.valid && k < S) ? p.next_obs[gr * S + k] : 0.f;
+            a1[u] = !e.valid ? 0.f : (k < S ? p.obs[gr * S + k] : (k < D ? p.act[gr * A + (k - S)] : 0.f));
+          }
+          w0[q] = pack_bf16(a0[0], a0[1]); w1[q] = pack_bf16(a1[0], a1[1]);
+        }
+        *reinterpret_cast<uint4*>(xs0 + j * 2048 + e.row * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        const uint4 v1 = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        *reinterpret_cast<uint4*>(xs1 + j * 2048 + e.row * 16) = v1;
+        *reinterpret_cast<uint4*>(p.x_sa + ((int64_t)j * p.Bpad + e.grow) * 8) = v1;
+      }
+      const float rew = e.valid ? p.rew[gr] : 0.f;
+      const float dn = (e.valid && p.done[gr]) ? 1.f : 0.f;
+      float cvr[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) cvr[c] = e.valid ? p.cv[gr * C + c] : 0.f;
+      fence_proxy_async();
+      epi_op_done(e);                                                     // op 0 may start
+
+      float none[MAXO] = {0.f, 0.f, 0.f, 0.f};
+      int o = 0;                                                          // op index within the tile (bias table)
+      // ---- actor / actor_safe on next_obs: sampled next actions (no grad)          src/ssac.py:286-288, 340-341 -------
+      float a1[A], a2[A], logp = 0.f, q_target = 0.f;
+      // order: actor, target Q1, target Q2, actor_safe, target Qc - the target Q's run between the two policies so that
+      // xs0's action columns hold a1 while they are read and a2 afterwards
+#pragma unroll 1
+      for (int pi = 0; pi < 2; ++pi) {
+        epi_forward<0>(e, p.bias_off[o], TM_R0, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
+        float hpart[MAXO] = {0.f, 0.f, 0.f, 0.f}, out[MAXO];
+        epi_forward<2 * A>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_actor[pi], hpart, false); ++o;
+        head_combine<2 * A>(e, hpart, p.hb_actor[pi], out);
+        float lp = 0.f, an[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+          const float mu = out[j], raw = out[A + j];
+          const float log_std = -6.f + 10.f * sigmoid_f(raw);
+          const float sd = expf(log_std);
+          const float eps = !e.valid ? 0.f : (pi == 0 ? p.n_actor.get(gr, j) : p.n_safe.get(gr, j));
+          const float x = fmaf(eps, sd, mu);
+          an[j] = tanhf(x);
+          const float ladj = 2.f * (0.69314718055994531f - x - softplus_f(-2.f * x));
+          const float dd = x - mu;
+          lp += (0.f - ladj) + (-(dd * dd) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467267f);
+        }
+        // patch the sampled action into xs0's action columns: the next ops read [next_obs, a]
+        if (e.g == 0) {
+#pragma unroll
+          for (int j = 0; j < A; ++j) {
+            const int k = S + j;
+            *reinterpret_cast<__nv_bfloat16*>(xs0 + (k >> 3) * 2048 + e.row * 16 + (k & 7) * 2) = __float2bfloat16_rn(e.valid ? an[j] : 0.f);
+          }
+          fence_proxy_async();
+        }
+        epi_op_done(e);
+        if (pi == 0) {
+          logp = lp;
+#pragma unroll
+          for (int j = 0; j < A; ++j) a1[j] = an[j];
+          float qt[2];
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            epi_forward<0>(e, p.bias_off[o], TM_R0, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
+            float hq[MAXO] = {0.f, 0.f, 0.f, 0.f}, oq[MAXO];
+            epi_forward<1>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_qt[i], hq, false); ++o;
+            head_combine<1>(e, hq, p.hb_qt[i], oq);
+            if (i == 0) qt[0] = oq[0]; else qt[1] = oq[0];
+            epi_op_done(e);
+          }
+          // compute_target                                                       src/ssac.py:284-294
+          q_target = rew + p.gamma * (1.f - dn) * (fminf(qt[0], qt[1]) - alpha * logp);
+          if (p.dbg && e.g == 0 && e.valid) { p.dbg[gr * 16 + 5] = qt[0]; p.dbg[gr * 16 + 6] = qt[1]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < A; ++j) a2[j] = an[j];
+        }
+      }
+      // ---- target Qc([next_obs, a2], sample=True)                                   src/ssac.py:342-344, 88-90 -------------
+      float nqc[C];
+      {
+        epi_forward<0>(e, p.bias_off[o], TM_R0, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
+        epi_forward<0>(e, p.bias_off[o], TM_R1, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
+        float hm[MAXO] = {0.f, 0.f, 0.f, 0.f}, hl[MAXO] = {0.f, 0.f, 0.f, 0.f}, om[MAXO], ol[MAXO];
+        epi_forward<C>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_ctm, hm, false); epi_op_done(e); ++o;
+        epi_forward<C>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_ctl, hl, false); ++o;
+        head_combine<C>(e, hm, p.hb_ctm, om);
+        named_bar_sync(1, EPI_THREADS);                                   // hp is reused by the second combine
+        head_combine<C>(e, hl, p.hb_ctl, ol);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float sd = expf(soft_clamp(ol[c], -4.f, 4.f));
+          const float ee = fminf(fmaxf(e.valid ? p.n_qc.get(gr, c) : 0.f, -2.f), 2.f);
+          nqc[c] = fmaf(ee, sd, om[c]);
+        }
+        epi_op_done(e);
+      }
+      if (p.dbg && e.g == 0 && e.valid) {
+        float* d = p.dbg + gr * 16;
+        d[0] = a1[0]; d[1] = A > 1 ? a1[A - 1] : 0.f; d[2] = logp; d[3] = a2[0]; d[4] = A > 1 ? a2[A - 1] : 0.f;
+        d[7] = nqc[0];
+      }
+      // ---- twin Q with gradient                                                      src/ssac.py:437-441 -------------------
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        uint64_t m1;
+        epi_forward<0>(e, p.bias_off[o], TM_R0, p.q_h1[i], &m1, 0, none, false); epi_op_done(e); ++o;
+        float hq[MAXO] = {0.f, 0.f, 0.f, 0.f}, oq[MAXO];
+        epi_forward<1>(e, p.bias_off[o], TM_R1, nullptr, nullptr, p.hw_q[i], hq, false); ++o;
+        tmem_st_wait();
+        head_combine<1>(e, hq, p.hb_q[i], oq);
+        const float err_q = oq[0] - q_target;
+        float dq[MAXO] = {e.valid ? err_q * p.inv_bg : 0.f, 0.f, 0.f, 0.f};
+        if (e.g == 0 && e.valid) { loss_q += 0.5 * (double)err_q * err_q; sc_q[i] += dq[0]; }
+        if (p.dbg && e.g == 0 && e.valid) { p.dbg[gr * 16 + 8 + i] = oq[0]; p.dbg[gr * 16 + 12 + i] = dq[0]; }
+        epi_head_backward<1>(e, TM_R1, dq, p.hw_q[i], slot_q_w2(i), slot_q_b1(i), p.q_dh2[i]);
+        epi_op_done(e);
+        epi_backward(e, m1, slot_q_b0(i), p.q_dh1[i], 0, false); epi_op_done(e); ++o;
+      }
+      // ---- distributional Qc with gradient                            src/ssac.py:345-354, 416-423 ---------------------------
+      {
+        uint64_t mt1, mt2;
+        epi_forward<0>(e, p.bias_off[o], TM_R0, p.c_t1, &mt1, 0, none, false); epi_op_done(e); ++o;
+        epi_forward<0>(e, p.bias_off[o], TM_R1, p.c_t2, &mt2, 0, none, false); epi_op_done(e); ++o;
+        float hm[MAXO] = {0.f, 0.f, 0.f, 0.f}, hl[MAXO] = {0.f, 0.f, 0.f, 0.f}, om[MAXO], ol[MAXO];
+        epi_forward<C>(e, p.bias_off[o], TM_R0, nullptr, nullptr, p.hw_cm, hm, false); epi_op_done(e); ++o;   // m1 stashed in R0
+        epi_forward<C>(e, p.bias_off[o], TM_R1, nullptr, nullptr, p.hw_cl, hl, true); ++o;                  // l1 stashed over t2
+        tmem_st_wait();
+        head_combine<C>(e, hm, p.hb_cm, om);
+        named_bar_sync(1, EPI_THREADS);
+        head_combine<C>(e, hl, p.hb_cl, ol);
+        float dmean[MAXO] = {0.f, 0.f, 0.f, 0.f}, dls[MAXO] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float h = cvr[c], mu = om[c];
+          const float nonterm = p.one_minus_gamma * h + p.gamma * fmaxf(h, nqc[c]);
+          const float tu = nonterm * (1.f - dn) + h * dn;
+          const float tb = fminf(fmaxf(tu - mu, -p.td_bound), p.td_bound) + mu;
+          const float x = ol[c];
+          const float y1 = 4.f - softplus_f(4.f - x);
+          const float ls = -4.f + softplus_f(y1 + 4.f);
+          const float sd = expf(ls), var = sd * sd;
+          const float du = mu - tu, db = mu - tb;
+          if (e.valid) {
+            dmean[c] = du / var * p.inv_bgc;
+            dls[c] = (1.f - db * db / var) * p.inv_bgc * dsoftplus(y1 + 4.f) * dsoftplus(4.f - x);
+            if (e.g == 0) {
+              loss_c += (double)(du * du / (2.f * var) + db * db / (2.f * var) + logf(sd));
+              sc_m[c] += dmean[c]; sc_l[c] += dls[c];
+            }
+          }
+        }
+        if (p.dbg && e.g == 0 && e.valid) {
+          float* d = p.dbg + gr * 16;
+          d[10] = om[0]; d[11] = ol[0]; d[14] = dmean[0]; d[15] = dls[0];
+        }
+        epi_head_backward<C>(e, TM_R0, dmean, p.hw_cm, slot_c_wm(0), SLOT_C_BM0, p.c_dm1);
+        epi_head_backward<C>(e, TM_R1, dls, p.hw_cl, slot_c_wl(0, C), SLOT_C_BL0, p.c_dl1);
+        epi_op_done(e);
+        epi_backward(e, mt2, SLOT_C_BT1, p.c_dt2, TM_R0, true); epi_op_done(e);      // dt2 = (dm1 W_m0 + dl1 W_l0) * (t2 > 0)
+        epi_backward(e, mt1, SLOT_C_BT0, p.c_dt1, 0, false);                           // dt1 = (dt2 W_t1) * (t1 > 0)
+        // the next arrival on act_ready follows the next tile's staging
+      }
+    }
+    // ---- per-CTA results ---------------------------------------------------------------------------------------------------
+    if (e.g == 0) {
+      float v;
+      v = warp_sum(sc_q[0]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 0], v);
+      v = warp_sum(sc_q[1]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 1], v);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        v = warp_sum(sc_m[c]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 2 + c], v);
+        v = warp_sum(sc_l[c]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 2 + C + c], v);
+      }
+      loss_q = warp_sum_d(loss_q); loss_c = warp_sum_d(loss_c);
+      double* lsm = reinterpret_cast<double*>(hp);                       // hp is idle now
+      if (lane == 0) { lsm[2 * (warp & 3)] = loss_q; lsm[2 * (warp & 3) + 1] = loss_c; }
+    }
+    named_bar_sync(1, EPI_THREADS);
+    if (threadIdx.x == 0) {
+      const double* lsm = reinterpret_cast<const double*>(hp);
+      p.loss_part[2 * blockIdx.x] = lsm[0] + lsm[2] + lsm[4] + lsm[6];
+      p.loss_part[2 * blockIdx.x + 1] = lsm[1] + lsm[3] + lsm[5] + lsm[7];
+    }
+    for (int i = threadIdx.x; i < p.nv * HID; i += EPI_THREADS) p.gacc_out[(int64_t)blockIdx.x * p.nv * HID + i] = gacc[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == ISSUER) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dW kernel
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DW_ROWS = 64;                                   // batch rows (K) per stage
+constexpr int DW_STAGES = 3;
+constexpr uint32_t DW_PANEL = DW_ROWS * 16;                   // one 8-feature panel of a stage: 1 KB
+constexpr uint32_t DW_STAGE_BYTES = 64 * DW_PANEL;            // 32 A panels + up to 32 B panels
+constexpr int DW_THREADS = 192;
+constexpr int MAX_DW_JOBS = 8;
+struct DwJob { const __nv_bfloat16* a; const __nv_bfloat16* b; int b_octets; int cta0, ksplit; float* partial; };
+struct DwParams { DwJob job[MAX_DW_JOBS]; int n_jobs; int64_t Bpad; int n_slabs; int* err_flag; uint32_t lbo, sbo; };
+struct DwSmem { uint64_t full[DW_STAGES], empty[DW_STAGES], done; uint32_t tmem_base, pad[3]; };
+
+__global__ void __launch_bounds__(DW_THREADS, 1) critic_dw_kernel(const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  DwSmem* sm = reinterpret_cast<DwSmem*>(smem + DW_STAGES * DW_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* err = p.err_flag;
+  int ji = 0;
+  while (ji + 1 < p.n_jobs && (int)blockIdx.x >= p.job[ji + 1].cta0) ++ji;
+  const DwJob job = p.job[ji];
+  const int split = (int)blockIdx.x - job.cta0;
+  const int slab0 = (int)((int64_t)p.n_slabs * split / job.ksplit), slab1 = (int)((int64_t)p.n_slabs * (split + 1) / job.ksplit);
+  const int N = job.b_octets * 8;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+    mbar_init(&sm->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 0) {
+    // producer: every lane copies its share of the 32 + b_octets panels of each stage (1 KB each)
+    const uint32_t bytes = (32 + job.b_octets) * DW_PANEL;
+    for (int sl = slab0, n = 0; sl < slab1; ++sl, ++n) {
+      const uint32_t s = n % DW_STAGES, ph = (n / DW_STAGES) & 1;
+      mbar_wait(&sm->empty[s], ph ^ 1, err, 21);
+      if (lane == 0) mbar_expect_tx(&sm->full[s], bytes);
+      __syncwarp();
+      uint8_t* dst = smem + s * DW_STAGE_BYTES;
+      const int64_t row0 = (int64_t)sl * DW_ROWS;
+      bulk_g2s(dst + lane * DW_PANEL, job.a + ((int64_t)lane * p.Bpad + row0) * 8, DW_PANEL, &sm->full[s]);
+      if (lane < job.b_octets) bulk_g2s(dst + (32 + lane) * DW_PANEL, job.b + ((int64_t)lane * p.Bpad + row0) * 8, DW_PANEL, &sm->full[s]);
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(N, 1, 1);
+    const uint32_t base = smem_u32(smem);
+    for (int sl = slab0, n = 0; sl < slab1; ++sl, ++n) {
+      const uint32_t s = n % DW_STAGES, ph = (n / DW_STAGES) & 1;
+      mbar_wait(&sm->full[s], ph, err, 22);
+      tc_fence_after();
+      // MN-major operands: LBO = 128 B (next 8 batch rows), SBO = 1 KB (next 8-feature panel); 16 rows per MMA = 256 B
+      const uint64_t ad = make_desc(base + s * DW_STAGE_BYTES, p.lbo, p.sbo);
+      const uint64_t bd = make_desc(base + s * DW_STAGE_BYTES + 32 * DW_PANEL, p.lbo, p.sbo);
+      const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32), b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DW_ROWS / 16; ++kk) {
+          const uint32_t accum = (n | kk) != 0;
+          mma_ss_p(tmem, a_lo + kk * 16, a_hi, b_lo + kk * 16, b_hi, idesc, accum);                                 // out features 0..127
+          mma_ss_p(tmem + 256, a_lo + (16 * DW_PANEL >> 4) + kk * 16, a_hi, b_lo + kk * 16, b_hi, idesc, accum);    // 128..255
+        }
+        tc_commit(&sm->empty[s]);
+        if (sl == slab1 - 1) tc_commit(&sm->done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lanes 32*(warp%4)..  = output feature within the half
+    mbar_wait(&sm->done, 0, err, 23);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* out = job.partial + (int64_t)split * HID * N;
+    for (int half = 0; half < 2; ++half) {
+      float* orow = out + (int64_t)(half * 128 + q * 32 + lane) * N;
+      for (int cb = 0; cb < N; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + half * 256 + cb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(orow + cb + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gradient assembly: grads[dst + r*cols + c] = sum_s src[s*stride + r*ld + c]
+// ---------------------------------------------------------------------------------------------------------------
+struct ReduceEntry { int64_t dst; const float* src; int n_src; int64_t stride; int rows, cols, ld; };
+struct ReduceTable { ReduceEntry e[40]; int n; };
+__global__ void __launch_bounds__(256) critic_grad_reduce_kernel(ReduceTable t, float* __restrict__ grads) {
+  const ReduceEntry e = t.e[blockIdx.y];
+  const int total = e.rows * e.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / e.cols, c = i - r * e.cols;
+    const float* s = e.src + (int64_t)r * e.ld + c;
+    float acc = 0.f;
+    for (int k = 0; k < e.n_src; ++k) acc += s[k * e.stride];
+    grads[e.dst + i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static float* g_dbg_rows = nullptr;
+
+struct Plan {
+  int64_t Bpad; int Kx, n_tiles, grid, nv;
+  int64_t img_bytes; int ctab_floats;
+  int dw_ctas; int64_t dw_partial_floats;
+};
+static Plan make_plan(int64_t B, int S, int A, int C) {
+  Plan pl;
+  pl.Bpad = (B + TILE - 1) / TILE * TILE;
+  pl.Kx = round_up(S + A, 16);
+  pl.n_tiles = (int)(pl.Bpad / TILE);
+  pl.grid = std::min(pl.n_tiles, 148);
+  pl.nv = n_slots(C);
+  // images: 8 first-layer (kp = Kx) + 17 hidden (kp = 256)
+  pl.img_bytes = (int64_t)8 * HID * pl.Kx * 2 + (int64_t)17 * HID * HID * 2;
+  pl.ctab_floats = 20 * HID + (4 * A + 4 + 4 * C) * HID + 64;
+  return pl;
+}
+// split-K factors of the dW jobs: big jobs (N = 256) and first-layer jobs (N = Kx) share 148 CTAs in proportion to their bytes
+static void dw_splits(const Plan& pl, int n_slabs, int& ks_big, int& ks_small) {
+  const double wb = 64.0, ws = 32.0 + pl.Kx / 8.0;
+  const double unit = 148.0 / (5 * wb + 3 * ws);
+  ks_big = std::max(1, std::min(n_slabs, (int)(unit * wb)));
+  ks_small = std::max(1, std::min(n_slabs, (int)((148 - 5 * ks_big) / 3)));
+}
+
+int64_t critic_ws_bytes(int64_t B, int S, int A, int C) {
+  Plan pl = make_plan(B, S, A, C);
+  int ksb, kss; dw_splits(pl, (int)(pl.Bpad / DW_ROWS), ksb, kss);
+  int64_t b = 0;
+  b += align_up(pl.img_bytes, 256) + align_up((int64_t)pl.ctab_floats * 4, 256);
+  b += 12 * align_up(pl.Bpad * HID * 2, 256) + align_up(pl.Bpad * pl.Kx * 2, 256);
+  b += align_up((int64_t)148 * pl.nv * HID * 4, 256) + align_up(148 * 2 * 8, 256);
+  b += align_up(((int64_t)5 * ksb * HID * HID + (int64_t)3 * kss * HID * pl.Kx) * 4, 256);
+  return b + 4096;
+}
+
+void critic_set_debug_rows(float* p) { g_dbg_rows = p; }
+
+template <int A, int C>
+static int launch_fused(const FusedParams& fp, int grid, size_t smem, cudaStream_t st) {
+  auto k = critic_fused_kernel<A, C>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DRPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    attr_done = true;
+  }
+  DRPO_LAUNCH(k, grid, F_THREADS, smem, st, fp);
+  return DRPO_OK;
+}
+
+// phase 1 of drpo_critic_step in DRPO_PREC_BF16: fills a.grads and a.losses[0..1]
+int critic_phase1(const drpo_critic_args& a, int* err_flag) {
+  const int64_t B = a.batch_size; const int S = a.state_dim, A = a.action_dim, C = a.con_dim, D = S + A;
+  cudaStream_t st = (cudaStream_t)a.stream;
+  DRPO_CHECK_ARG(a.q[0].l0.out_dim == HID && a.q[0].l1.out_dim == HID && a.actor->l0.out_dim == HID && a.actor->l1.out_dim == HID &&
+                     a.qc.trunk0.out_dim == HID, "drpo_critic_step(bf16): the fused kernel needs hidden width 256");
+  DRPO_CHECK_ARG(D <= 64, "drpo_critic_step(bf16): state_dim + action_dim must be <= 64 (got %d)", D);
+  DRPO_CHECK_ARG((A == 1 || A == 2) && (C == 1 || C == 2 || C == 4), "drpo_critic_step(bf16): fused kernel is built for action_dim 1-2, con_dim 1/2/4");
+  Plan pl = make_plan(B, S, A, C);
+  const int n_slabs = (int)(pl.Bpad / DW_ROWS);
+  int ksb, kss; dw_splits(pl, n_slabs, ksb, kss);
+  Arena ar(a.workspace, a.workspace_bytes);
+  uint8_t* img = ar.take<uint8_t>(pl.img_bytes);
+  float* ctab = ar.take<float>(pl.ctab_floats);
+  __nv_bfloat16* sv[12];
+  for (int i = 0; i < 12; ++i) sv[i] = ar.take<__nv_bfloat16>(pl.Bpad * HID);
+  __nv_bfloat16* x_sa = ar.take<__nv_bfloat16>(pl.Bpad * pl.Kx);
+  float* gacc_out = ar.take<float>((int64_t)148 * pl.nv * HID);
+  double* loss_part = ar.take<double>(148 * 2);
+  float* dw_part = ar.take<float>((int64_t)5 * ksb * HID * HID + (int64_t)3 * kss * HID * pl.Kx);
+  if (!ar.ok()) { set_error("drpo_critic_step(bf16): workspace too small (%lld needed, %lld given)", (long long)ar.off, (long long)a.workspace_bytes); return DRPO_ERR_WORKSPACE; }
+
+  // ---- plan: images, constant table, ops ---------------------------------------------------------------------------------
+  FusedParams fp; memset(&fp, 0, sizeof(fp));
+  PackTable pt; pt.n = 0; CopyTable ct; ct.n = 0;
+  int64_t img_off = 0; int ctab_off = 0; int n_ops = 0;
+  auto add_image = [&](const drpo_linear& l, bool transposed) -> uint32_t {
+    PackEntry& e = pt.e[pt.n++];
+    e.W = l.w; e.transposed = transposed ? 1 : 0;
+    if (!transposed) { e.n_real = l.out_dim; e.k_real = l.in_dim; e.kp = l.in_dim == HID ? HID : pl.Kx; }
+    else { e.n_real = l.in_dim; e.k_real = l.out_dim; e.kp = HID; }
+    e.dst = img_off / 2;
+    const uint32_t off = (uint32_t)img_off;
+    img_off += (int64_t)HID * e.kp * 2;
+    return off;
+  };
+  auto add_const = [&](const float* src, int n) -> int {
+    CopyEntry& e = ct.e[ct.n++]; e.src = src; e.n = n; e.dst = ctab_off;
+    const int off = ctab_off; ctab_off += (n + 3) & ~3; return off;
+  };
+  auto add_fwd = [&](const drpo_linear& l, int a_src) {
+    FOp& op = fp.op[n_ops];
+    op.w_off[0] = add_image(l, false); op.kp = (uint16_t)(l.in_dim == HID ? HID : pl.Kx); op.a_src[0] = (uint8_t)a_src; op.parts = 1;
+    fp.bias_off[n_ops] = add_const(l.b, HID);
+    ++n_ops;
+  };
+  auto add_bwd = [&](const drpo_linear& l, int a_src) {
+    FOp& op = fp.op[n_ops];
+    op.w_off[0] = add_image(l, true); op.kp = HID; op.a_src[0] = (uint8_t)a_src; op.parts = 1; fp.bias_off[n_ops] = 0;
+    ++n_ops;
+  };
+  // op order must match the epilogue program of critic_fused_kernel
+  add_fwd(a.actor->l0, A_XS0); add_fwd(a.actor->l1, A_R0);
+  fp.hw_actor[0] = add_const(a.actor->l2.w, 2 * A * HID); fp.hb_actor[0] = add_const(a.actor->l2.b, 2 * A);
+  for (int i = 0; i < 2; ++i) {
+    add_fwd(a.q_target[i].l0, A_XS0); add_fwd(a.q_target[i].l1, A_R0);
+    fp.hw_qt[i] = add_const(a.q_target[i].l2.w, HID); fp.hb_qt[i] = add_const(a.q_target[i].l2.b, 1);
+  }
+  add_fwd(a.actor_safe->l0, A_XS0); add_fwd(a.actor_safe->l1, A_R0);
+  fp.hw_actor[1] = add_const(a.actor_safe->l2.w, 2 * A * HID); fp.hb_actor[1] = add_const(a.actor_safe->l2.b, 2 * A);
+  add_fwd(a.qc_target.trunk0, A_XS0); add_fwd(a.qc_target.trunk1, A_R0); add_fwd(a.qc_target.mean0, A_R1); add_fwd(a.qc_target.lstd0, A_R1);
+  fp.hw_ctm = add_const(a.qc_target.mean1.w, C * HID); fp.hb_ctm = add_const(a.qc_target.mean1.b, C);
+  fp.hw_ctl = add_const(a.qc_target.lstd1.w, C * HID); fp.hb_ctl = add_const(a.qc_target.lstd1.b, C);
+  for (int i = 0; i < 2; ++i) {
+    add_fwd(a.q[i].l0, A_XS1); add_fwd(a.q[i].l1, A_R0); add_bwd(a.q[i].l1, A_R1);
+    fp.hw_q[i] = add_const(a.q[i].l2.w, HID); fp.hb_q[i] = add_const(a.q[i].l2.b, 1);
+  }
+  add_fwd(a.qc.trunk0, A_XS1); add_fwd(a.qc.trunk1, A_R0); add_fwd(a.qc.mean0, A_R1); add_fwd(a.qc.lstd0, A_R1);
+  fp.hw_cm = add_const(a.qc.mean1.w, C * HID); fp.hb_cm = add_const(a.qc.mean1.b, C);
+  fp.hw_cl = add_const(a.qc.lstd1.w, C * HID); fp.hb_cl = add_const(a.qc.lstd1.b, C);
+  {
+    FOp& op = fp.op[n_ops];                                       // dt2: two K parts into the same accumulators
+    op.w_off[0] = add_image(a.qc.mean0, true); op.w_off[1] = add_image(a.qc.lstd0, true);
+    op.kp = HID; op.a_src[0] = A_R0; op.a_src[1] = A_R1; op.parts = 2; fp.bias_off[n_ops] = 0; ++n_ops;
+  }
+  add_bwd(a.qc.trunk1, A_R0);
+  if (n_ops != MAX_OPS || img_off > pl.img_bytes || ctab_off > pl.ctab_floats) {
+    set_error("drpo_critic_step(bf16): internal plan mismatch (%d ops, %lld image bytes, %d consts)", n_ops, (long long)img_off, ctab_off);
+    return DRPO_ERR_ARG;
+  }
+  {
+    dim3 grid(16, pt.n);
+    DRPO_LAUNCH(pack_images_kernel, grid, 256, 0, st, pt, reinterpret_cast<__nv_bfloat16*>(img));
+    DRPO_LAUNCH(gather_ctab_kernel, ct.n, 256, 0, st, ct, ctab);
+  }
+  fp.n_ops = n_ops; fp.wimg = img; fp.ctab = ctab; fp.ctab_floats = ctab_off;
+  const drpo_batch& b = a.batch;
+  fp.obs = b.obs; fp.act = b.act; fp.next_obs = b.next_obs; fp.rew = b.rew; fp.cv = b.cv; fp.done = b.done;
+  fp.n_actor = make_noise(a.eps_actor, A, a.seed, TAG_CRITIC_ACTOR, a.noise_step, a.row_id_offset);
+  fp.n_safe = make_noise(a.eps_safe, A, a.seed, TAG_CRITIC_SAFE, a.noise_step, a.row_id_offset);
+  fp.n_qc = make_noise(a.eps_qc, C, a.seed, TAG_CRITIC_QC, a.noise_step, a.row_id_offset);
+  fp.log_alpha = a.log_alpha;
+  fp.gamma = (float)a.discount; fp.one_minus_gamma = (float)(1.0 - a.discount); fp.td_bound = (float)a.qc_td_bound;
+  fp.inv_bg = (float)(1.0 / (double)a.global_batch_size); fp.inv_bgc = (float)(1.0 / ((double)a.global_batch_size * C));
+  fp.B = B; fp.Bpad = pl.Bpad; fp.S = S; fp.A = A; fp.C = C; fp.D = D; fp.Kx = pl.Kx; fp.n_tiles = pl.n_tiles;
+  fp.x_sa = x_sa;
+  fp.q_h1[0] = sv[0]; fp.q_dh2[0] = sv[1]; fp.q_dh1[0] = sv[2]; fp.q_h1[1] = sv[3]; fp.q_dh2[1] = sv[4]; fp.q_dh1[1] = sv[5];
+  fp.c_t1 = sv[6]; fp.c_t2 = sv[7]; fp.c_dm1 = sv[8]; fp.c_dl1 = sv[9]; fp.c_dt2 = sv[10]; fp.c_dt1 = sv[11];
+  fp.gacc_out = gacc_out; fp.nv = pl.nv; fp.loss_part = loss_part; fp.err_flag = err_flag; fp.dbg = g_dbg_rows;
+  // shared memory: ring + 2 x-buffers + constants + column sums + head partials + barriers
+  const size_t fixed = (size_t)2 * TILE * pl.Kx * 2 + (size_t)((ctab_off + 3) & ~3) * 4 + (size_t)pl.nv * HID * 4 + NGROUPS * TILE * 16 + sizeof(FusedSmem);
+  int stages = (int)((232448 - 1024 - fixed) / CHUNK_BYTES);
+  if (stages > 6) stages = 6;
+  if (stages < 2) { set_error("drpo_critic_step(bf16): shared-memory budget exceeded"); return DRPO_ERR_ARG; }
+  fp.stages = stages;
+  const size_t smem = fixed + (size_t)stages * CHUNK_BYTES;
+  int rc;
+  if (A == 1 && C == 1) rc = launch_fused<1, 1>(fp, pl.grid, smem, st);
+  else if (A == 1 && C == 2) rc = launch_fused<1, 2>(fp, pl.grid, smem, st);
+  else if (A == 1 && C == 4) rc = launch_fused<1, 4>(fp, pl.grid, smem, st);
+  else if (A == 2 && C == 1) rc = launch_fused<2, 1>(fp, pl.grid, smem, st);
+  else if (A == 2 && C == 2) rc = launch_fused<2, 2>(fp, pl.grid, smem, st);
+  else rc = launch_fused<2, 4>(fp, pl.grid, smem, st);
+  if (rc) return rc;
+
+  // ---- dW ------------------------------------------------------------------------------------------------------------------
+  DwParams dp; memset(&dp, 0, sizeof(dp));
+  dp.Bpad = pl.Bpad; dp.n_slabs = n_slabs; dp.err_flag = err_flag; dp.lbo = 128; dp.sbo = DW_PANEL;
+  ReduceTable rt; rt.n = 0;
+  float* G = a.grads; const float* P = a.params;
+  auto goff = [&](const float* q) { return (int64_t)(q - P); };
+  int cta = 0; float* part = dw_part;
+  auto add_job = [&](const __nv_bfloat16* dH, const __nv_bfloat16* Hm, int in_dim, const drpo_linear& l) {
+    const bool big = in_dim == HID;
+    DwJob& j = dp.job[dp.n_jobs++];
+    j.a = dH; j.b = Hm; j.b_octets = big ? 32 : pl.Kx / 8; j.cta0 = cta; j.ksplit = big ? ksb : kss; j.partial = part;
+    const int N = j.b_octets * 8;
+    ReduceEntry& r = rt.e[rt.n++];
+    r.dst = goff(l.w); r.src = part; r.n_src = j.ksplit; r.stride = (int64_t)HID * N; r.rows = HID; r.cols = l.in_dim; r.ld = N;
+    cta += j.ksplit; part += (int64_t)j.ksplit * HID * N;
+  };
+  auto add_vec = [&](const float* dst_param, int slot, int off, int n) {
+    ReduceEntry& r = rt.e[rt.n++];
+    r.dst = goff(dst_param); r.src = gacc_out + slot * HID + off; r.n_src = pl.grid; r.stride = (int64_t)pl.nv * HID; r.rows = 1; r.cols = n; r.ld = n;
+  };
+  for (int i = 0; i < 2; ++i) {
+    add_job(fp.q_dh2[i], fp.q_h1[i], HID, a.q[i].l1);
+    add_job(fp.q_dh1[i], x_sa, D, a.q[i].l0);
+    add_vec(a.q[i].l2.w, slot_q_w2(i), 0, HID); add_vec(a.q[i].l2.b, SLOT_SCAL, i, 1);
+    add_vec(a.q[i].l1.b, slot_q_b1(i), 0, HID); add_vec(a.q[i].l0.b, slot_q_b0(i), 0, HID);
+  }
+  add_job(fp.c_dm1, fp.c_t2, HID, a.qc.mean0); add_job(fp.c_dl1, fp.c_t2, HID, a.qc.lstd0);
+  add_job(fp.c_dt2, fp.c_t1, HID, a.qc.trunk1); add_job(fp.c_dt1, x_sa, D, a.qc.trunk0);
+  for (int c = 0; c < C; ++c) {
+    add_vec(a.qc.mean1.w + c * HID, slot_c_wm(c), 0, HID); add_vec(a.qc.lstd1.w + c * HID, slot_c_wl(c, C), 0, HID);
+  }
+  add_vec(a.qc.mean1.b, SLOT_SCAL, 2, C); add_vec(a.qc.lstd1.b, SLOT_SCAL, 2 + C, C);
+  add_vec(a.qc.mean0.b, SLOT_C_BM0, 0, HID); add_vec(a.qc.lstd0.b, SLOT_C_BL0, 0, HID);
+  add_vec(a.qc.trunk1.b, SLOT_C_BT1, 0, HID); add_vec(a.qc.trunk0.b, SLOT_C_BT0, 0, HID);
+  {
+    static bool attr_done = false;
+    const size_t dsm = DW_STAGES * DW_STAGE_BYTES + sizeof(DwSmem);
+    if (!attr_done) { DRPO_CUDA_OK(cudaFuncSetAttribute(critic_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); attr_done = true; }
+    DRPO_LAUNCH(critic_dw_kernel, cta, DW_THREADS, dsm, st, dp);
+    dim3 grid(32, rt.n);
+    DRPO_LAUNCH(critic_grad_reduce_kernel, grid, 256, 0, st, rt, G);
+  }
+  Scale2 sc; sc.v[0] = 1.0 / (double)a.global_batch_size; sc.v[1] = 1.0 / ((double)a.global_batch_size * C);
+  DRPO_LAUNCH(loss_finalize2_kernel, 1, 32, 0, st, loss_part, pl.grid, sc, a.losses);
+  return DRPO_OK;
+}
+
+// test aid: dW of one (dH, H) pair given in the octet layout -> out[256, 8*b_octets]
+int critic_debug_dw(const void* a_oct, const void* b_oct, int b_octets, int64_t rows_padded, int ksplit, float* partial, float* out,
+                    int* err_flag, void* stream) {
+  DwParams dp; memset(&dp, 0, sizeof(dp));
+  dp.Bpad = rows_padded; dp.n_slabs = (int)(rows_padded / DW_ROWS); dp.err_flag = err_flag; dp.n_jobs = 1;
+  const bool swap = getenv("DRPO_DW_SWAP") != nullptr;          // experiment switch: LBO/SBO roles of the MN-major descriptor
+  dp.lbo = swap ? DW_PANEL : 128; dp.sbo = swap ? 128 : DW_PANEL;
+  dp.job[0].a = (const __nv_bfloat16*)a_oct; dp.job[0].b = (const __nv_bfloat16*)b_oct; dp.job[0].b_octets = b_octets;
+  dp.job[0].cta0 = 0; dp.job[0].ksplit = ksplit; dp.job[0].partial = partial;
+  const size_t dsm = DW_STAGES * DW_STAGE_BYTES + sizeof(DwSmem);
+  DRPO_CUDA_OK(cudaFuncSetAttribute(critic_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+  DRPO_LAUNCH(critic_dw_kernel, ksplit, DW_THREADS, dsm, (cudaStream_t)stream, dp);
+  ReduceTable rt; rt.n = 1;
+  const int N = b_octets * 8;
+  rt.e[0].dst = 0; rt.e[0].src = partial; rt.e[0].n_src = ksplit; rt.e[0].stride = (int64_t)HID * N; rt.e[0].rows = HID; rt.e[0].cols = N; rt.e[0].ld = N;
+  dim3 grid(32, 1);
+  DRPO_LAUNCH(critic_grad_reduce_kernel, grid, 256, 0, (cudaStream_t)stream, rt, out);
+  return DRPO_OK;
+}
+
+}  // namespace cu
+}  // namespace drpo

@@ -6,6 +6,7 @@
 #include "nets.cuh"
 #include "rollout.cuh"
 #include "umma_api.h"
+#include "critic_umma_api.h"
 
 namespace drpo {
 static thread_local char g_err[1024] = "";
@@ -275,7 +276,9 @@ int drpo_debug_rollout_layer(const drpo_rollout_args* a, int32_t layer, float* o
 }
 
 int64_t drpo_critic_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
-  return critic_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+  const int64_t a = critic_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+  const int64_t b = hidden == 256 && state_dim + action_dim <= 64 ? cu::critic_ws_bytes(batch, state_dim, action_dim, con_dim) + 4096 : 0;
+  return a > b ? a : b;
 }
 
 int drpo_critic_step(const drpo_critic_args* a) {
@@ -299,9 +302,26 @@ int drpo_critic_step(const drpo_critic_args* a) {
     const drpo_batch& b = a->batch;
     DRPO_CHECK_ARG(b.obs && b.act && b.next_obs && b.rew && b.done && b.cv, "drpo_critic_step: NULL batch tensor");
   }
-  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16, "drpo_critic_step: unknown precision %d", a->precision);
-  // DRPO_PREC_BF16 = tensor-core mode: the dense contractions run as TF32 tensor-op GEMMs, everything else is unchanged
-  g_gemm_mode = a->precision == DRPO_PREC_BF16 ? 1 : 0;
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
+                 "drpo_critic_step: unknown precision %d", a->precision);
+  if (a->precision == DRPO_PREC_BF16) {
+    // fused tcgen05 path: phase 1 = pack + fused forward/loss/dX kernel + dW kernel + gradient assembly; phase 2 is shared
+    drpo_critic_args b = *a;
+    if (a->phases & 1) {
+      int* words = umma_status_words();
+      DRPO_CHECK_ARG(words, "drpo_critic_step: cannot allocate the pinned status words");
+      DRPO_CHECK_ARG(a->workspace_bytes >= 4096, "drpo_critic_step: workspace too small");
+      int* err_flag = (int*)a->workspace;                       // first 4 KB of the workspace: in-kernel watchdog flag
+      b.workspace = (char*)a->workspace + 4096; b.workspace_bytes = a->workspace_bytes - 4096;
+      DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)a->stream));
+      if ((rc = cu::critic_phase1(b, err_flag))) return rc;
+      DRPO_CUDA_OK(cudaMemcpyAsync(words + 1, err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)a->stream));
+    }
+    if (a->phases & 2) { b = *a; b.phases = 2; return critic_step_fp32(b); }
+    return DRPO_OK;
+  }
+  // DRPO_PREC_TF32 = library tensor-core mode: the dense contractions run as TF32 tensor-op GEMMs (cuBLAS), rest unchanged
+  g_gemm_mode = a->precision == DRPO_PREC_TF32 ? 1 : 0;
   rc = critic_step_fp32(*a);
   g_gemm_mode = 0;
   return rc;
@@ -322,11 +342,28 @@ int drpo_multiplier_step(const drpo_multiplier_args* a) {
   DRPO_CHECK_ARG(a->lam.l0.in_dim == a->state_dim + 1 && a->lam.l2.out_dim == 1, "drpo_multiplier_step: multiplier dims disagree");
   DRPO_CHECK_ARG(a->params && a->grads && a->adam_m && a->adam_v && a->losses, "drpo_multiplier_step: NULL arena");
   DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_multiplier_step: bad phases");
-  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16, "drpo_multiplier_step: unknown precision %d", a->precision);
-  g_gemm_mode = a->precision == DRPO_PREC_BF16 ? 1 : 0;
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
+                 "drpo_multiplier_step: unknown precision %d", a->precision);
+  g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;          // both tensor modes: TF32 tensor-op GEMMs
   rc = multiplier_step_fp32(*a);
   g_gemm_mode = 0;
   return rc;
+}
+
+int drpo_debug_critic_rows(float* rows) { cu::critic_set_debug_rows(rows); return DRPO_OK; }
+
+int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets, int64_t rows_padded, int32_t ksplit, float* partial,
+                         float* out, void* stream) {
+  DRPO_CHECK_ARG(a_oct && b_oct && partial && out && b_octets >= 2 && b_octets <= 32 && (b_octets & 1) == 0 && rows_padded % 128 == 0 &&
+                     ksplit >= 1 && ksplit <= rows_padded / 64, "drpo_debug_critic_dw: bad arguments");
+  int* words = umma_status_words();
+  DRPO_CHECK_ARG(words, "drpo_debug_critic_dw: cannot allocate the pinned status words");
+  int* err_flag = (int*)partial;                                // first 16 bytes of the partial scratch
+  DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));
+  int rc = cu::critic_debug_dw(a_oct, b_oct, b_octets, rows_padded, ksplit, partial + 4, out, err_flag, stream);
+  if (rc) return rc;
+  DRPO_CUDA_OK(cudaMemcpyAsync(words + 1, err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return DRPO_OK;
 }
 
 }  // extern "C"

@@ -409,9 +409,10 @@ class SSAC(Configurable, BasePolicy, nn.Module):
             return dist
         return None
 
-    def update_critic(self, obs, action, next_obs, reward, done, violation, constraint_value, noise=None):
+    def update_critic(self, obs, action, next_obs, reward, done, violation, constraint_value, noise=None, phases=None):
         """SSAC.update_critic (src/ssac.py:437-456).  ``noise`` = (eps_actor [B,A], eps_safe [B,A], eps_qc [B(,C)])
-        injects the three Gaussian draws (parity); otherwise the in-kernel Philox stream is used."""
+        injects the three Gaussian draws (parity); otherwise the in-kernel Philox stream is used.  ``phases`` (tests) runs only
+        the given phases of drpo_critic_step (1 = forward/backward into the gradient arena, 2 = clip/Adam/EMA)."""
         lib = _lib.load()
         st = self._ensure_arenas()
         dist = self._dist()
@@ -427,7 +428,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         a = _lib.CriticArgs()
         a.batch = _lib.Batch(_lib.ptr(obs), _lib.ptr(action), _lib.ptr(next_obs), _lib.ptr(reward), _lib.ptr(done),
                              _lib.ptr(violation), _lib.ptr(cv))
-        a.batch_size, a.global_batch_size = B, B * world
+        a.batch_size, a.global_batch_size = B, getattr(self, "_global_batch_override", None) or B * world
         a.state_dim, a.action_dim, a.con_dim = self.state_dim, self.action_dim, self.con_dim
         a.actor, a.actor_safe = C_pointer(st["actor"]), C_pointer(st["actor_safe"])
         a.q[0], a.q[1], a.q_target[0], a.q_target[1] = st["q"][0], st["q"][1], st["qt"][0], st["qt"][1]
@@ -445,6 +446,10 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         a.losses, a.precision = _lib.ptr(self._losses), self.precision
         ws = self._ws.get(lib.drpo_critic_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim), obs.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        if phases is not None:
+            a.phases = phases
+            _lib.check(lib.drpo_critic_step(a), "drpo_critic_step")
+            return self._losses[0].clone(), self._losses[1].clone()
         if dist is None:
             a.phases = 3
             _lib.check(lib.drpo_critic_step(a), "drpo_critic_step")

@@ -35,8 +35,11 @@ enum { DRPO_OK = 0, DRPO_ERR_ARG = -1, DRPO_ERR_CUDA = -2, DRPO_ERR_WORKSPACE = 
 
 /* arithmetic mode of the dense layers */
 enum { DRPO_PREC_FP32 = 0,   /* fp32 FMA path, parity <= 1e-5 relative vs the reference */
-       DRPO_PREC_BF16 = 1 }; /* tensor-core path, fp32 accumulate, parity <= 2e-2: drpo_rollout = fused bf16 tcgen05/TMEM
-                                kernel; drpo_critic_step / drpo_multiplier_step = TF32 tensor-op GEMMs (cuBLAS), fp32 elsewhere */
+       DRPO_PREC_BF16 = 1,   /* hand-written tcgen05/TMEM path (bf16 operands, fp32 accumulate), parity <= 2e-2:
+                                drpo_rollout = fused rollout-step kernel; drpo_critic_step = fused forward/loss/dX kernel + dW
+                                kernel; drpo_multiplier_step = as DRPO_PREC_TF32 */
+       DRPO_PREC_TF32 = 2 }; /* library tensor-core mode of drpo_critic_step / drpo_multiplier_step: fp32 path with the dense
+                                contractions as TF32 tensor-op GEMMs (cuBLAS / cuBLASLt) */
 
 /* ------------------------------------------------------------------------------------------------------------
  * Env hooks: check_done / check_violation / get_constraint_values
@@ -262,6 +265,13 @@ typedef struct drpo_critic_args {
 int64_t drpo_critic_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim,
                                     int32_t hidden);
 int drpo_critic_step(const drpo_critic_args* args);
+/* Debug aids of the DRPO_PREC_BF16 critic step (tests): `rows` != NULL makes the next phase-1 calls write per-row
+ * intermediates [batch,16] = a1[2], log-prob, a2[2], Q1', Q2', Qc' sample, Q1, Q2, Qc mean, Qc raw log-std, dL/dQ1, dL/dQ2,
+ * dL/dmean, dL/dlogstd (first constraint).  drpo_debug_critic_dw runs the split-K weight-gradient kernel on one operand
+ * pair given in the octet layout ([features/8][rows_padded][8] bf16): out[256, 8*b_octets] = dH^T H. */
+int drpo_debug_critic_rows(float* rows);
+int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets, int64_t rows_padded, int32_t ksplit,
+                         float* partial, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * SSAC.update_multiplier (src/ssac.py:529-578) in DRPO mode (mlp_multiplier): actor rsample, two Qc passes with

@@ -351,12 +351,12 @@ def test_buffer_gather_matches_reference_assembly():
 
 @pytest.mark.parametrize("S,A,C,B", [(51, 2, 1, 4096), (12, 2, 2, 1000)])
 def test_critic_and_multiplier_tensor_mode_vs_oracle(S, A, C, B):
-    """Tensor-core mode of the SSAC steps (PREC_BF16: TF32 tensor-op GEMMs, fp32 everywhere else) against the fp32 oracle
+    """Library tensor-core mode of the SSAC steps (PREC_TF32: TF32 tensor-op GEMMs, fp32 everywhere else) against the fp32 oracle
     within the 2e-2 the north star allows for the reduced-precision GEMM path; losses much tighter."""
     import drpo_b200
     w = O.make_ssac_weights(61, S, A, C)
     solver = make_ssac(w, S, A, C, B)
-    solver.precision = drpo_b200.PREC_BF16
+    solver.precision = drpo_b200.PREC_TF32
     wo = {k: v.clone() for k, v in w.items()}
     g = torch.Generator().manual_seed(62)
     obs = torch.randn(B, S, generator=g); act = torch.rand(B, A, generator=g) * 2 - 1
