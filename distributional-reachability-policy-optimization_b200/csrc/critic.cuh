@@ -72,11 +72,13 @@ static __global__ void loss_finalize_kernel(const double* partials, int nblocks,
   }
 }
 struct Scale2 { double v[2]; };
-static __global__ void loss_finalize2_kernel(const double* partials, int nblocks, Scale2 sc, float* out) {
-  if (threadIdx.x < 2) {
+static __global__ void loss_finalize2_kernel(const double* partials, int nblocks, Scale2 sc, float* out) {   // one warp
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
     double s = 0;
-    for (int b = 0; b < nblocks; ++b) s += partials[2 * b + threadIdx.x];
-    out[threadIdx.x] = (float)(s * sc.v[threadIdx.x]);
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partials[2 * b + k];
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) out[k] = (float)(s * sc.v[k]);
   }
 }
 
@@ -101,13 +103,17 @@ static __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restri
   }
 }
 // norms[k] = sqrt(sum), coef[k] = min(1, max_norm/(norm+1e-6))        torch.nn.utils.clip_grad_norm_
-static __global__ void clip_coef_kernel(const double* partials, int nblocks, float max_norm, float* norms_out, float* coef) {
-  if (threadIdx.x < 2) {
+static __global__ void clip_coef_kernel(const double* partials, int nblocks, float max_norm, float* norms_out, float* coef) {   // one warp
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
     double s = 0;
-    for (int b = 0; b < nblocks; ++b) s += partials[2 * b + threadIdx.x];
-    const float nrm = (float)sqrt(s);
-    if (norms_out) norms_out[threadIdx.x] = nrm;
-    coef[threadIdx.x] = fminf(max_norm / (nrm + 1e-6f), 1.f);
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partials[2 * b + k];
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) {
+      const float nrm = (float)sqrt(s);
+      if (norms_out) norms_out[k] = nrm;
+      coef[k] = fminf(max_norm / (nrm + 1e-6f), 1.f);
+    }
   }
 }
 

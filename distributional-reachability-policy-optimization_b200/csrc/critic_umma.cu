@@ -42,24 +42,33 @@ constexpr int EPI_THREADS = NGROUPS * 128;
 constexpr int F_THREADS = EPI_THREADS + 64;   // + warp 16 TMA producer, warp 17 MMA issuer (owns the TMEM allocation)
 constexpr int MAX_OPS = 24;
 constexpr int MAXO = 4;                    // widest CUDA-core head: 2*action_dim <= 4, con_dim <= 4
-constexpr uint32_t CHUNK_BYTES = 64 * HID * 2;   // one ring stage: 64 output columns x K=256 bf16
+constexpr int KBIAS = 16;                  // extra K block of every forward weight chunk: bias (hi, lo) against a constant-ones A tile
+constexpr uint32_t CHUNK_BYTES = 64 * (HID + KBIAS) * 2;   // one ring stage: 64 output columns x (K=256 + bias block) bf16
 constexpr uint32_t TM_ACC = 0, TM_R0 = 256, TM_R1 = 384;
 
 enum ASrc { A_XS0 = 0, A_XS1 = 1, A_R0 = 2, A_R1 = 3 };
 
-struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t pad; };
+struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t bias; };   // bias: the chunks carry a bias K block
+// epilogue side of an op
+enum Post { POST_NONE = 0, POST_POLICY0, POST_POLICY1, POST_QT0, POST_QT1, POST_KEEP, POST_QCT, POST_Q0, POST_Q1, POST_QC };
+struct EOp {
+  int hw_off, hb_off;                      // offsets into the constant table: head weights [no][256], head bias [no]
+  uint8_t backward;                        // 0 forward epilogue (bias + ReLU), 1 backward epilogue (mask + column sums)
+  uint8_t no;                              // head outputs evaluated on the CUDA cores from this layer's activation (0 = none)
+  uint8_t out_region;                      // 0 none, 1 R0, 2 R1: TMEM region the packed result is stored to
+  uint8_t wait_all;                        // out_region is one of the op's own A operands: wait for all of its MMAs first
+  uint8_t save, hsave;                     // saved-array ids (0 = none): result to save / forward activation giving the ReLU mask
+  uint8_t bias_slot;                       // backward: column-sum slot of the bias gradient
+  uint8_t post;                            // Post
+};
 
 struct FusedParams {
   FOp op[MAX_OPS];
+  EOp eop[MAX_OPS];
   int n_ops;
   const uint8_t* wimg;
   const float* ctab; int ctab_floats;
-  // offsets (floats) into ctab
-  int bias_off[MAX_OPS];                   // [256] bias of forward op i
-  int hw_actor[2], hb_actor[2];            // head weights [2A][256] / bias [2A]: actor, actor_safe
-  int hw_qt[2], hb_qt[2], hw_q[2], hb_q[2];
-  int hw_ctm, hb_ctm, hw_ctl, hb_ctl;      // target Qc mean / log-std heads [C][256]
-  int hw_cm, hb_cm, hw_cl, hb_cl;          // online Qc heads
+  int hw_q[2], hw_cm, hw_cl;               // head weights needed again by the backward steps (offsets into ctab)
   // batch
   const float *obs, *act, *next_obs, *rew, *cv; const uint8_t* done;
   NoiseView n_actor, n_safe, n_qc;
@@ -67,12 +76,17 @@ struct FusedParams {
   float gamma, one_minus_gamma, td_bound, inv_bg, inv_bgc;
   int64_t B, Bpad; int S, A, C, D, Kx, stages, n_tiles;
   // saved activations (octet layout, Bpad rows)
-  __nv_bfloat16 *x_sa, *q_h1[2], *q_dh2[2], *q_dh1[2], *c_t1, *c_t2, *c_dm1, *c_dl1, *c_dt2, *c_dt1;
+  __nv_bfloat16* x_sa;
+  __nv_bfloat16* sv[13];                   // [0] unused; ids below
+
   float* gacc_out; int nv;                 // [grid][nv*256] per-CTA column sums
   double* loss_part;                       // [grid][2]
   int* err_flag;
   float* dbg;                              // optional [B,16] per-row intermediates (tests)
+  long long* prof;                         // optional [MAX_OPS][4] clock stamps of block 0's second tile (tools/prof_critic_ops.py)
 };
+
+enum SaveId { SV_Q_H1 = 1, SV_Q_DH2 = 3, SV_Q_DH1 = 5, SV_C_T1 = 7, SV_C_T2, SV_C_DM1, SV_C_DL1, SV_C_DT2, SV_C_DT1 };   // Q ids: + net index
 
 // slots of the per-CTA column-sum accumulators (each 256 floats)
 __host__ __device__ inline int slot_q_w2(int i) { return 3 * i; }
@@ -84,6 +98,7 @@ __host__ __device__ inline int slot_c_wl(int c, int C) { return SLOT_C_WM + C + 
 __host__ __device__ inline int n_slots(int C) { return SLOT_C_WM + 2 * C; }
 // scalars inside SLOT_SCAL: [0,1] dL/d q_i bias, [2..2+C) mean-head bias, [2+C..2+2C) log-std-head bias
 
+constexpr int CLUSTER = 2;                 // CTA pair: every weight chunk is fetched from L2 once and multicast to both
 struct FusedSmem {
   uint64_t full[6], empty[6], acc_full[NGROUPS], acc_free[NGROUPS], act_ready;
   uint32_t tmem_base, pad[3];
@@ -93,17 +108,24 @@ struct FusedSmem {
 // weight images: 256 x kp bf16 per image, four 64-column chunks, each in the canonical K-major no-swizzle layout
 //   [n/8][k/8][8 rows][8 elems];  transposed images hold W^T (the backward op's B operand)
 // ---------------------------------------------------------------------------------------------------------------
-struct PackEntry { const float* W; int n_real, k_real, kp, transposed; int64_t dst; };
+struct PackEntry { const float* W; const float* bias; int n_real, k_real, kp, transposed; int64_t dst; };
 struct PackTable { PackEntry e[28]; int n; };
+// Forward images (bias != NULL) carry a 16-wide extra K block per chunk: k = kp holds bf16(b), k = kp+1 holds bf16(b - bf16(b));
+// the issuer multiplies it with a constant tile of ones, so the accumulator already contains the fp32-accurate bias.
 __global__ void pack_images_kernel(PackTable t, __nv_bfloat16* __restrict__ img) {
   const PackEntry e = t.e[blockIdx.y];
-  const int total = HID * e.kp;
+  const int kt = e.kp + (e.bias ? KBIAS : 0);
+  const int total = HID * kt;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int n = i / e.kp, k = i - n * e.kp;
+    const int n = i / kt, k = i - n * kt;
     float v = 0.f;
-    if (n < e.n_real && k < e.k_real) v = e.transposed ? e.W[(int64_t)k * e.n_real + n] : e.W[(int64_t)n * e.k_real + k];
+    if (n < e.n_real) {
+      if (k < e.k_real) v = e.transposed ? e.W[(int64_t)k * e.n_real + n] : e.W[(int64_t)n * e.k_real + k];
+      else if (k == e.kp) v = e.bias[n];
+      else if (k == e.kp + 1) { const float b = e.bias[n]; v = b - __bfloat162float(__float2bfloat16_rn(b)); }
+    }
     const int c = n >> 6, nin = n & 63;
-    const int64_t idx = (int64_t)c * 64 * e.kp + ((int64_t)(nin >> 3) * (e.kp >> 3) + (k >> 3)) * 64 + (nin & 7) * 8 + (k & 7);
+    const int64_t idx = (int64_t)c * 64 * kt + ((int64_t)(nin >> 3) * (kt >> 3) + (k >> 3)) * 64 + (nin & 7) * 8 + (k & 7);
     img[e.dst + idx] = __float2bfloat16_rn(v);
   }
 }
@@ -161,11 +183,13 @@ struct Epi {
   bool valid;
   uint32_t it;              // global index of the op whose epilogue runs next (parity of the per-op barriers)
   int* err;
+  long long* prof;          // non-null only in the one thread that records clock stamps
 };
 
 __device__ __forceinline__ void epi_wait_acc(Epi& e) {
   mbar_wait(&e.sm->acc_full[e.g], e.it & 1, e.err, 100 + e.g);
   tc_fence_after();
+  if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 16 + 4 * e.g] = clock64();
 }
 __device__ __forceinline__ void epi_free_acc(Epi& e) {
   tc_fence_before();
@@ -198,54 +222,42 @@ __device__ __forceinline__ void add_colsum(const Epi& e, int slot, int half, con
 // forward epilogue of one 64-column slab: h = relu(acc + bias).
 //   out_region != 0 : store packed bf16 to that TMEM region (next op's A operand / stash)
 //   save != nullptr : store to the global octet array
-//   mask != nullptr : record h > 0 (64 bits)
-//   NO > 0          : accumulate the head dot products hpart[o] += h . hw[o][cols]
+//   no > 0          : accumulate the head dot products hpart[o] += h . hw[o][cols]
 //   wait_all        : wait for every MMA of the op before touching out_region (it is one of the op's own A regions)
-template <int NO>
-__device__ __forceinline__ void epi_forward(Epi& e, int bias_off, uint32_t out_region, __nv_bfloat16* save, uint64_t* mask,
-                                            int hw_off, float (&hpart)[MAXO], bool wait_all) {
+// One copy of this code serves all 20 forward ops (the per-op parameters come from the EOp table): the first version inlined
+// one specialised copy per op, 240 KB of SASS, and paid an instruction-cache miss chain at every site of every tile.
+__device__ __forceinline__ void epi_forward(Epi& e, uint32_t out_region, __nv_bfloat16* save, int hw_off, int no,
+                                            float (&hpart)[MAXO], bool wait_all) {
   epi_wait_acc(e);
-  uint64_t m = 0;
+  uint32_t raw[2][32];
+  tmem_ld32(e.tm + TM_ACC + e.g * 64, raw[0]);
+  tmem_ld32(e.tm + TM_ACC + e.g * 64 + 32, raw[1]);
+  tmem_ld_wait();
+  epi_free_acc(e);
+  if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 17 + 4 * e.g] = clock64();
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    uint32_t raw[32];
-    tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
-    tmem_ld_wait();
-    if (half == 1) epi_free_acc(e);
-    const float4* b4 = reinterpret_cast<const float4*>(e.ctab + bias_off + e.g * 64 + half * 32);
-    float h[32];
+    // the accumulator already holds x W^T + b (bias block of the weight chunk): the epilogue is ReLU + pack
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = b4[j];
-      h[4 * j] = fmaxf(__uint_as_float(raw[4 * j]) + b.x, 0.f);
-      h[4 * j + 1] = fmaxf(__uint_as_float(raw[4 * j + 1]) + b.y, 0.f);
-      h[4 * j + 2] = fmaxf(__uint_as_float(raw[4 * j + 2]) + b.z, 0.f);
-      h[4 * j + 3] = fmaxf(__uint_as_float(raw[4 * j + 3]) + b.w, 0.f);
-    }
-    if (NO > 0) {
-#pragma unroll
-      for (int o = 0; o < NO; ++o) {
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < no) {
         const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
         float acc = hpart[o];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 w = w4[j];
-          acc = fmaf(h[4 * j], w.x, acc); acc = fmaf(h[4 * j + 1], w.y, acc);
-          acc = fmaf(h[4 * j + 2], w.z, acc); acc = fmaf(h[4 * j + 3], w.w, acc);
+          acc = fmaf(fmaxf(__uint_as_float(raw[half][4 * j]), 0.f), w.x, acc);
+          acc = fmaf(fmaxf(__uint_as_float(raw[half][4 * j + 1]), 0.f), w.y, acc);
+          acc = fmaf(fmaxf(__uint_as_float(raw[half][4 * j + 2]), 0.f), w.z, acc);
+          acc = fmaf(fmaxf(__uint_as_float(raw[half][4 * j + 3]), 0.f), w.w, acc);
         }
         hpart[o] = acc;
       }
     }
-    if (mask) {
-      uint32_t mm = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mm |= (h[j] > 0.f ? 1u : 0u) << j;
-      m |= (uint64_t)mm << (32 * half);
-    }
     if (out_region || save) {
       uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(h[2 * j], h[2 * j + 1]);
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16_relu(__uint_as_float(raw[half][2 * j]), __uint_as_float(raw[half][2 * j + 1]));
       if (save) save_octets(e, save, half, pk);
       if (out_region) {
         if (wait_all && half == 0) epi_wait_all_mma(e);
@@ -253,24 +265,35 @@ __device__ __forceinline__ void epi_forward(Epi& e, int bias_off, uint32_t out_r
       }
     }
   }
-  if (mask) *mask = m;
+  if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 18 + 4 * e.g] = clock64();
   ++e.it;
 }
 
-// backward epilogue: dh = mask ? acc : 0; column sums -> bias gradient; save; optional TMEM store for the next backward op
-__device__ __forceinline__ void epi_backward(Epi& e, uint64_t mask, int bias_slot, __nv_bfloat16* save, uint32_t out_region,
-                                             bool wait_all) {
+// backward epilogue: dh = (h > 0) ? acc : 0 with h re-read from the saved forward activation (bf16 octets, written by this
+// very thread a few ops earlier, L2-resident); column sums -> bias gradient; save; optional TMEM store for the next backward op
+__device__ __forceinline__ void epi_backward(Epi& e, const __nv_bfloat16* hsave, int bias_slot, __nv_bfloat16* save, uint32_t out_region,
+                                          bool wait_all) {
   epi_wait_acc(e);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
+    uint4 hv[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      hv[o] = *reinterpret_cast<const uint4*>(hsave + ((int64_t)(e.g * 8 + half * 4 + o) * e.Bpad + e.grow) * 8);
     uint32_t raw[32];
     tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
     tmem_ld_wait();
     if (half == 1) epi_free_acc(e);
-    const uint32_t mm = (uint32_t)(mask >> (32 * half));
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ((mm >> j) & 1u) ? __uint_as_float(raw[j]) : 0.f;
+    for (int o = 0; o < 4; ++o) {
+      const uint32_t w[4] = {hv[o].x, hv[o].y, hv[o].z, hv[o].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[8 * o + 2 * q] = (w[q] & 0xFFFFu) ? __uint_as_float(raw[8 * o + 2 * q]) : 0.f;
+        v[8 * o + 2 * q + 1] = (w[q] >> 16) ? __uint_as_float(raw[8 * o + 2 * q + 1]) : 0.f;
+      }
+    }
     add_colsum(e, bias_slot, half, v);
     uint32_t pk[16];
 #pragma unroll
@@ -281,15 +304,15 @@ __device__ __forceinline__ void epi_backward(Epi& e, uint64_t mask, int bias_slo
       tmem_st16(e.tm + out_region + e.g * 32 + half * 16, pk);
     }
   }
+  if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 18 + 4 * e.g] = clock64();
   ++e.it;
 }
 
 // After the row's output gradients d[o] are known: read the stashed activation h (packed bf16 in `region`), accumulate the
 // head-weight gradient column sums d[o]*h, form dh = (h > 0) * sum_o d[o]*hw[o][col], its column sums (bias gradient of the
 // layer that produced h), store dh over h and save it.
-template <int NO>
-__device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const float (&d)[MAXO], int hw_off, int w_slot0, int bias_slot,
-                                                  __nv_bfloat16* save) {
+__device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const float (&d)[MAXO], int no, int hw_off, int w_slot0,
+                                                  int bias_slot, __nv_bfloat16* save) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     uint32_t hp16[16];
@@ -298,24 +321,23 @@ __device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const
     float h[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { h[2 * j] = bf_lo(hp16[j]); h[2 * j + 1] = bf_hi(hp16[j]); }
-#pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      float t[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = d[o] * h[j];
-      add_colsum(e, w_slot0 + o, half, t);
-    }
     float dh[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) dh[j] = 0.f;
 #pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < no) {
+        float t[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 w = w4[j];
-        dh[4 * j] = fmaf(d[o], w.x, dh[4 * j]); dh[4 * j + 1] = fmaf(d[o], w.y, dh[4 * j + 1]);
-        dh[4 * j + 2] = fmaf(d[o], w.z, dh[4 * j + 2]); dh[4 * j + 3] = fmaf(d[o], w.w, dh[4 * j + 3]);
+        for (int j = 0; j < 32; ++j) t[j] = d[o] * h[j];
+        add_colsum(e, w_slot0 + o, half, t);
+        const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = w4[j];
+          dh[4 * j] = fmaf(d[o], w.x, dh[4 * j]); dh[4 * j + 1] = fmaf(d[o], w.y, dh[4 * j + 1]);
+          dh[4 * j + 2] = fmaf(d[o], w.z, dh[4 * j + 2]); dh[4 * j + 3] = fmaf(d[o], w.w, dh[4 * j + 3]);
+        }
       }
     }
 #pragma unroll
@@ -329,11 +351,9 @@ __device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const
   }
 }
 
-// head outputs of the row: sum of the four groups' partials + bias
-template <int NO>
+// head outputs of the row: sum of the four groups' partials + bias (all MAXO lanes; unused ones carry zeros + padding)
 __device__ __forceinline__ void head_combine(Epi& e, const float (&hpart)[MAXO], int hb_off, float (&out)[MAXO]) {
-  float4 mine = make_float4(hpart[0], NO > 1 ? hpart[1] : 0.f, NO > 2 ? hpart[2] : 0.f, NO > 3 ? hpart[3] : 0.f);
-  e.hp[e.g * TILE + e.row] = mine;
+  e.hp[e.g * TILE + e.row] = make_float4(hpart[0], hpart[1], hpart[2], hpart[3]);
   named_bar_sync(1, EPI_THREADS);
   float4 s = e.hp[e.row];
 #pragma unroll
@@ -341,23 +361,22 @@ __device__ __forceinline__ void head_combine(Epi& e, const float (&hpart)[MAXO],
     const float4 p = e.hp[gg * TILE + e.row];
     s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
   }
-  out[0] = s.x + e.ctab[hb_off];
-  if (NO > 1) out[1] = s.y + e.ctab[hb_off + 1];
-  if (NO > 2) out[2] = s.z + e.ctab[hb_off + 2];
-  if (NO > 3) out[3] = s.w + e.ctab[hb_off + 3];
+  const float4 b = *reinterpret_cast<const float4*>(e.ctab + hb_off);
+  out[0] = s.x + b.x; out[1] = s.y + b.y; out[2] = s.z + b.z; out[3] = s.w + b.w;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the fused forward / loss / dX kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <int A, int C>
-__global__ void __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int stages = p.stages;
   uint8_t* ring = smem;
   uint8_t* xs0 = ring + (size_t)stages * CHUNK_BYTES;
   uint8_t* xs1 = xs0 + TILE * p.Kx * 2;
-  float* ctab = reinterpret_cast<float*>(xs1 + TILE * p.Kx * 2);
+  uint8_t* ones = xs1 + TILE * p.Kx * 2;                    // [128 rows][16 k] K-major, columns 0 and 1 are 1.0: A operand of the bias MMA
+  float* ctab = reinterpret_cast<float*>(ones + TILE * KBIAS * 2);
   float* gacc = ctab + ((p.ctab_floats + 3) & ~3);
   float4* hp = reinterpret_cast<float4*>(gacc + p.nv * HID);
   FusedSmem* sm = reinterpret_cast<FusedSmem*>(hp + NGROUPS * TILE);
@@ -366,7 +385,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid
   int* err = p.err_flag;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], CLUSTER); }
     for (int g = 0; g < NGROUPS; ++g) { mbar_init(&sm->acc_full[g], 1); mbar_init(&sm->acc_free[g], 128); }
     mbar_init(&sm->act_ready, EPI_THREADS);
     fence_barrier_init();
@@ -374,86 +393,124 @@ __global__ void __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid
   if (warp == ISSUER) tmem_alloc(&sm->tmem_base, 512);
   for (int i = threadIdx.x; i < p.ctab_floats; i += F_THREADS) ctab[i] = p.ctab[i];
   for (int i = threadIdx.x; i < p.nv * HID; i += F_THREADS) gacc[i] = 0.f;
+  for (int i = threadIdx.x; i < TILE * KBIAS; i += F_THREADS) {          // element (row, k) at (k/8)*2048 + row*16 + (k%8)*2
+    const int k = (i >> 10) * 8 + (i & 7);
+    reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(k < 2 ? 1.f : 0.f);
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                      // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
-  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // the two CTAs of a cluster walk through the same number of tiles (tile pairs are dealt to clusters round-robin) in
+  // lock step, coupled by the weight ring: each CTA fetches half of every chunk and multicasts it to both
+  const uint32_t crank = cluster_ctarank();
+  const int n_clusters = (int)gridDim.x / CLUSTER, cid = (int)blockIdx.x / CLUSTER;
+  const int my_tiles = (p.n_tiles / CLUSTER - cid + n_clusters - 1) / n_clusters;
 
   if (warp == PRODUCER) {
     // ---- TMA producer: (tile, op, chunk, part) weight blocks through the ring ---------------------------------------------
     if (elect_one()) {
-      uint32_t n = 0;
+      uint32_t s = 0, ph = 0;
       for (int t = 0; t < my_tiles; ++t)
         for (int o = 0; o < p.n_ops; ++o) {
           const FOp op = p.op[o];
-          const uint32_t bytes = 64u * op.kp * 2u;
+          const uint32_t bytes = 64u * (op.kp + (op.bias ? KBIAS : 0)) * 2u;
           for (int c = 0; c < NGROUPS; ++c)
-            for (int part = 0; part < op.parts; ++part, ++n) {
-              const uint32_t s = n % stages, ph = (n / stages) & 1;
-              mbar_wait(&sm->empty[s], ph ^ 1, err, 1);
+            for (int part = 0; part < op.parts; ++part) {
+              mbar_wait(&sm->empty[s], ph ^ 1, err, 1);   // both CTAs' MMAs on the stage's previous contents are done (multicast commits)
               mbar_expect_tx(&sm->full[s], bytes);
-              bulk_g2s(ring + (size_t)s * CHUNK_BYTES, p.wimg + op.w_off[part] + (size_t)c * bytes, bytes, &sm->full[s]);
+              const uint32_t half = bytes >> 1;
+              bulk_g2s_multicast(ring + (size_t)s * CHUNK_BYTES + crank * half,
+                                 p.wimg + op.w_off[part] + (size_t)c * bytes + crank * half, half, &sm->full[s], (uint16_t)3);
+              if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
             }
         }
     }
   } else if (warp == ISSUER) {
     // ---- MMA issuer ---------------------------------------------------------------------------------------------------------
-    uint32_t n = 0, it = 0;
+    // The tensor pipe accepts only ~4 MMAs ahead of execution, so every barrier wait between two chunks is a bubble in the
+    // pipe: the op's accumulators and up to `round` ring stages are awaited first, then that many chunks are issued back to back.
+    uint32_t it = 0, stage = 0, phase = 0;
     const uint32_t ring_addr = smem_u32(ring), xs_addr[2] = {smem_u32(xs0), smem_u32(xs1)};
+    const uint64_t ones_d = make_desc(smem_u32(ones), 2048, 128);
+    const uint32_t ones_lo = (uint32_t)ones_d, ones_hi = (uint32_t)(ones_d >> 32);
+    const int round = stages >= 4 ? 4 : 2;
+    const uint32_t idesc = make_idesc(64);
     for (int t = 0; t < my_tiles; ++t)
       for (int o = 0; o < p.n_ops; ++o, ++it) {
         const FOp op = p.op[o];
         const int nk = op.kp >> 4;
-        const uint32_t idesc = make_idesc(64);
-        mbar_wait(&sm->act_ready, it & 1, err, 2);
-        tc_fence_after();
-        for (int c = 0; c < NGROUPS; ++c) {
-          mbar_wait(&sm->acc_free[c], (it & 1) ^ 1, err, 3);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem + TM_ACC + c * 64;
-          for (int part = 0; part < op.parts; ++part, ++n) {
-            const uint32_t s = n % stages, ph = (n / stages) & 1;
-            mbar_wait(&sm->full[s], ph, err, 4);
-            tc_fence_after();
-            // B: chunk image [64 cols][kp] K-major: LBO = 128 B (next K octet), SBO = kp*16 B (next 8 columns)
-            const uint64_t bd = make_desc(ring_addr + s * CHUNK_BYTES, 128, (uint32_t)op.kp * 16);
-            const uint32_t b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
-            const int src = op.a_src[part];
-            if (elect_one()) {
-              if (src <= A_XS1) {
-                // A: [128 rows][Kx] K-major in shared memory: LBO = 2048 B (next K octet), SBO = 128 B (next 8 rows)
-                const uint64_t ad = make_desc(xs_addr[src], 2048, 128);
-                const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k < nk) mma_ss_p(d_tmem, a_lo + k * 256, a_hi, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
-              } else {
-                const uint32_t a_tmem = tmem + (src == A_R0 ? TM_R0 : TM_R1);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) mma_ts_p(d_tmem, a_tmem + k * 8, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
-              }
-              tc_commit(&sm->empty[s]);
-              if (part == op.parts - 1) tc_commit(&sm->acc_full[c]);
-            }
-            __syncwarp();
+        const int pshift = op.parts - 1;                              // parts is 1 or 2
+        const bool stamp = p.prof && blockIdx.x == 0 && lane == 0 && t == 1;
+        const uint32_t sbo = (uint32_t)(op.kp + (op.bias ? KBIAS : 0)) * 16;
+        for (int i0 = 0; i0 < (NGROUPS << pshift); i0 += round) {
+          // (the first round's weights and the accumulators become available while the previous op is still in its epilogue:
+          // these waits are off the critical path; the last one - the previous op's activations - is the real dependency)
+          uint32_t sw = stage, pw = phase;
+          for (int r = 0; r < round; ++r) {
+            mbar_wait(&sm->full[sw], pw, err, 4);
+            if (++sw == (uint32_t)stages) { sw = 0; pw ^= 1; }
           }
+          if (i0 == 0) {
+            if (stamp) p.prof[o * 32 + 8] = clock64();
+            for (int c = 0; c < NGROUPS; ++c) mbar_wait(&sm->acc_free[c], (it & 1) ^ 1, err, 3);
+            if (stamp) p.prof[o * 32 + 9] = clock64();
+            mbar_wait(&sm->act_ready, it & 1, err, 2);
+            if (stamp) p.prof[o * 32] = clock64();
+          }
+          tc_fence_after();
+          if (stamp) p.prof[o * 32 + 4 + (i0 >> pshift)] = clock64();
+          if (elect_one()) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (r < round) {
+                const int i = i0 + r, c = i >> pshift, part = i & pshift;
+                uint32_t s = stage + r; if (s >= (uint32_t)stages) s -= stages;
+                // B: chunk image [64 cols][kp] K-major: LBO = 128 B (next K octet), SBO = kp*16 B (next 8 columns)
+                const uint64_t bd = make_desc(ring_addr + s * CHUNK_BYTES, 128, sbo);
+                const uint32_t b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
+                const uint32_t d_tmem = tmem + TM_ACC + c * 64;
+                const int src = op.a_src[part];
+                if (src <= A_XS1) {
+                  // A: [128 rows][Kx] K-major in shared memory: LBO = 2048 B (next K octet), SBO = 128 B (next 8 rows)
+                  const uint64_t ad = make_desc(xs_addr[src], 2048, 128);
+                  const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (k < nk) mma_ss_p(d_tmem, a_lo + k * 256, a_hi, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
+                } else {
+                  const uint32_t a_tmem = tmem + (src == A_R0 ? TM_R0 : TM_R1);
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) mma_ts_p(d_tmem, a_tmem + k * 8, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
+                }
+                if (op.bias) mma_ss_p(d_tmem, ones_lo, ones_hi, b_lo + nk * 16, b_hi, idesc, 1u);      // + bias (ones x bias block)
+                tc_commit_multicast(&sm->empty[s], (uint16_t)3);      // frees the stage in both CTAs of the pair
+                if (part == pshift) tc_commit(&sm->acc_full[c]);
+              }
+            }
+          }
+          __syncwarp();
+          stage = sw; phase = pw;
         }
+        if (stamp) p.prof[o * 32 + 1] = clock64();
       }
   } else {
     // ---- epilogue groups ----------------------------------------------------------------------------------------------------
     Epi e;
     e.sm = sm; e.ctab = ctab; e.gacc = gacc; e.hp = hp; e.g = warp >> 2; e.lane = lane; e.row = (warp & 3) * 32 + lane;
     e.tm = tmem + ((uint32_t)((warp & 3) * 32) << 16); e.it = 0; e.err = err; e.Bpad = p.Bpad;
+    e.prof = (blockIdx.x == 0 && (threadIdx.x & 127) == 0) ? p.prof : nullptr;          // first thread of every group
     const int S = p.S, D = p.D;
     const float alpha = expf(*p.log_alpha);
     double loss_q = 0.0, loss_c = 0.0;
-    float sc_q[2] = {0.f, 0.f}, sc_m[C], sc_l[C];
+    float sc_q0 = 0.f, sc_q1 = 0.f, sc_m[C], sc_l[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { sc_m[c] = 0.f; sc_l[c] = 0.f; }
 
     for (int t = 0; t < my_tiles; ++t) {
-      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int tile = CLUSTER * (cid + t * n_clusters) + (int)crank;
       e.grow = (int64_t)tile * TILE + e.row;
       e.valid = e.grow < p.B;
       const int64_t gr = e.valid ? e.grow : 0;
@@ -484,154 +541,158 @@ __global__ void __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid
       fence_proxy_async();
       epi_op_done(e);                                                     // op 0 may start
 
-      float none[MAXO] = {0.f, 0.f, 0.f, 0.f};
-      int o = 0;                                                          // op index within the tile (bias table)
-      // ---- actor / actor_safe on next_obs: sampled next actions (no grad)          src/ssac.py:286-288, 340-341 -------
-      float a1[A], a2[A], logp = 0.f, q_target = 0.f;
-      // order: actor, target Q1, target Q2, actor_safe, target Qc - the target Q's run between the two policies so that
-      // xs0's action columns hold a1 while they are read and a2 afterwards
-#pragma unroll 1
-      for (int pi = 0; pi < 2; ++pi) {
-        epi_forward<0>(e, p.bias_off[o], TM_R0, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
-        float hpart[MAXO] = {0.f, 0.f, 0.f, 0.f}, out[MAXO];
-        epi_forward<2 * A>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_actor[pi], hpart, false); ++o;
-        head_combine<2 * A>(e, hpart, p.hb_actor[pi], out);
-        float lp = 0.f, an[A];
+      // ---- the tile's 24 ops: one generic forward / backward epilogue, then the op's post step -----------------------------
+      float hpart[MAXO] = {0.f, 0.f, 0.f, 0.f}, hkeep[MAXO] = {0.f, 0.f, 0.f, 0.f};
+      int hb_keep = 0;
+      float a1[A], a2[A], logp = 0.f, qt0 = 0.f, q_target = 0.f, nqc[C];
 #pragma unroll
-        for (int j = 0; j < A; ++j) {
-          const float mu = out[j], raw = out[A + j];
-          const float log_std = -6.f + 10.f * sigmoid_f(raw);
-          const float sd = expf(log_std);
-          const float eps = !e.valid ? 0.f : (pi == 0 ? p.n_actor.get(gr, j) : p.n_safe.get(gr, j));
-          const float x = fmaf(eps, sd, mu);
-          an[j] = tanhf(x);
-          const float ladj = 2.f * (0.69314718055994531f - x - softplus_f(-2.f * x));
-          const float dd = x - mu;
-          lp += (0.f - ladj) + (-(dd * dd) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467267f);
-        }
-        // patch the sampled action into xs0's action columns: the next ops read [next_obs, a]
-        if (e.g == 0) {
+      for (int j = 0; j < A; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+#pragma unroll
+      for (int c = 0; c < C; ++c) nqc[c] = 0.f;
+#pragma unroll 1
+      for (int o = 0; o < MAX_OPS; ++o) {
+        const EOp d = p.eop[o];
+        const uint32_t region = d.out_region == 0 ? 0u : (d.out_region == 1 ? TM_R0 : TM_R1);
+        if (!d.backward) epi_forward(e, region, p.sv[d.save], d.hw_off, d.no, hpart, d.wait_all != 0);
+        else epi_backward(e, p.sv[d.hsave], d.bias_slot, p.sv[d.save], region, d.wait_all != 0);
+        if (d.post == POST_POLICY0 || d.post == POST_POLICY1) {
+          // squashed-Gaussian sample of the next action (+ log-prob)                       src/ssac.py:286-288, 340-341
+          const bool first = d.post == POST_POLICY0;
+          float out[MAXO];
+          head_combine(e, hpart, d.hb_off, out);
+          float lp = 0.f, an[A];
 #pragma unroll
           for (int j = 0; j < A; ++j) {
-            const int k = S + j;
-            *reinterpret_cast<__nv_bfloat16*>(xs0 + (k >> 3) * 2048 + e.row * 16 + (k & 7) * 2) = __float2bfloat16_rn(e.valid ? an[j] : 0.f);
+            const float mu = out[j], raw = out[A + j];
+            const float log_std = -6.f + 10.f * sigmoid_f(raw);
+            const float sd = expf(log_std);
+            const float eps = !e.valid ? 0.f : (first ? p.n_actor.get(gr, j) : p.n_safe.get(gr, j));
+            const float x = fmaf(eps, sd, mu);
+            an[j] = tanhf(x);
+            const float ladj = 2.f * (0.69314718055994531f - x - softplus_f(-2.f * x));
+            const float dd = x - mu;
+            lp += (0.f - ladj) + (-(dd * dd) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467267f);
           }
-          fence_proxy_async();
-        }
-        epi_op_done(e);
-        if (pi == 0) {
-          logp = lp;
+          // patch the sampled action into xs0's action columns: the next ops read [next_obs, a].  Order of the ops: actor,
+          // target Q1, target Q2, actor_safe, target Qc - so the columns hold a1 while the Q's read them and a2 afterwards
+          if (e.g == 0) {
 #pragma unroll
-          for (int j = 0; j < A; ++j) a1[j] = an[j];
-          float qt[2];
-#pragma unroll 1
-          for (int i = 0; i < 2; ++i) {
-            epi_forward<0>(e, p.bias_off[o], TM_R0, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
-            float hq[MAXO] = {0.f, 0.f, 0.f, 0.f}, oq[MAXO];
-            epi_forward<1>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_qt[i], hq, false); ++o;
-            head_combine<1>(e, hq, p.hb_qt[i], oq);
-            if (i == 0) qt[0] = oq[0]; else qt[1] = oq[0];
-            epi_op_done(e);
+            for (int j = 0; j < A; ++j) {
+              const int k = S + j;
+              *reinterpret_cast<__nv_bfloat16*>(xs0 + (k >> 3) * 2048 + e.row * 16 + (k & 7) * 2) = __float2bfloat16_rn(e.valid ? an[j] : 0.f);
+            }
+            fence_proxy_async();
           }
-          // compute_target                                                       src/ssac.py:284-294
-          q_target = rew + p.gamma * (1.f - dn) * (fminf(qt[0], qt[1]) - alpha * logp);
-          if (p.dbg && e.g == 0 && e.valid) { p.dbg[gr * 16 + 5] = qt[0]; p.dbg[gr * 16 + 6] = qt[1]; }
-        } else {
+          if (first) {
+            logp = lp;
 #pragma unroll
-          for (int j = 0; j < A; ++j) a2[j] = an[j];
-        }
-      }
-      // ---- target Qc([next_obs, a2], sample=True)                                   src/ssac.py:342-344, 88-90 -------------
-      float nqc[C];
-      {
-        epi_forward<0>(e, p.bias_off[o], TM_R0, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
-        epi_forward<0>(e, p.bias_off[o], TM_R1, nullptr, nullptr, 0, none, false); epi_op_done(e); ++o;
-        float hm[MAXO] = {0.f, 0.f, 0.f, 0.f}, hl[MAXO] = {0.f, 0.f, 0.f, 0.f}, om[MAXO], ol[MAXO];
-        epi_forward<C>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_ctm, hm, false); epi_op_done(e); ++o;
-        epi_forward<C>(e, p.bias_off[o], 0, nullptr, nullptr, p.hw_ctl, hl, false); ++o;
-        head_combine<C>(e, hm, p.hb_ctm, om);
-        named_bar_sync(1, EPI_THREADS);                                   // hp is reused by the second combine
-        head_combine<C>(e, hl, p.hb_ctl, ol);
+            for (int j = 0; j < A; ++j) a1[j] = an[j];
+          } else {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float sd = expf(soft_clamp(ol[c], -4.f, 4.f));
-          const float ee = fminf(fmaxf(e.valid ? p.n_qc.get(gr, c) : 0.f, -2.f), 2.f);
-          nqc[c] = fmaf(ee, sd, om[c]);
-        }
-        epi_op_done(e);
-      }
-      if (p.dbg && e.g == 0 && e.valid) {
-        float* d = p.dbg + gr * 16;
-        d[0] = a1[0]; d[1] = A > 1 ? a1[A - 1] : 0.f; d[2] = logp; d[3] = a2[0]; d[4] = A > 1 ? a2[A - 1] : 0.f;
-        d[7] = nqc[0];
-      }
-      // ---- twin Q with gradient                                                      src/ssac.py:437-441 -------------------
-#pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        uint64_t m1;
-        epi_forward<0>(e, p.bias_off[o], TM_R0, p.q_h1[i], &m1, 0, none, false); epi_op_done(e); ++o;
-        float hq[MAXO] = {0.f, 0.f, 0.f, 0.f}, oq[MAXO];
-        epi_forward<1>(e, p.bias_off[o], TM_R1, nullptr, nullptr, p.hw_q[i], hq, false); ++o;
-        tmem_st_wait();
-        head_combine<1>(e, hq, p.hb_q[i], oq);
-        const float err_q = oq[0] - q_target;
-        float dq[MAXO] = {e.valid ? err_q * p.inv_bg : 0.f, 0.f, 0.f, 0.f};
-        if (e.g == 0 && e.valid) { loss_q += 0.5 * (double)err_q * err_q; sc_q[i] += dq[0]; }
-        if (p.dbg && e.g == 0 && e.valid) { p.dbg[gr * 16 + 8 + i] = oq[0]; p.dbg[gr * 16 + 12 + i] = dq[0]; }
-        epi_head_backward<1>(e, TM_R1, dq, p.hw_q[i], slot_q_w2(i), slot_q_b1(i), p.q_dh2[i]);
-        epi_op_done(e);
-        epi_backward(e, m1, slot_q_b0(i), p.q_dh1[i], 0, false); epi_op_done(e); ++o;
-      }
-      // ---- distributional Qc with gradient                            src/ssac.py:345-354, 416-423 ---------------------------
-      {
-        uint64_t mt1, mt2;
-        epi_forward<0>(e, p.bias_off[o], TM_R0, p.c_t1, &mt1, 0, none, false); epi_op_done(e); ++o;
-        epi_forward<0>(e, p.bias_off[o], TM_R1, p.c_t2, &mt2, 0, none, false); epi_op_done(e); ++o;
-        float hm[MAXO] = {0.f, 0.f, 0.f, 0.f}, hl[MAXO] = {0.f, 0.f, 0.f, 0.f}, om[MAXO], ol[MAXO];
-        epi_forward<C>(e, p.bias_off[o], TM_R0, nullptr, nullptr, p.hw_cm, hm, false); epi_op_done(e); ++o;   // m1 stashed in R0
-        epi_forward<C>(e, p.bias_off[o], TM_R1, nullptr, nullptr, p.hw_cl, hl, true); ++o;                  // l1 stashed over t2
-        tmem_st_wait();
-        head_combine<C>(e, hm, p.hb_cm, om);
-        named_bar_sync(1, EPI_THREADS);
-        head_combine<C>(e, hl, p.hb_cl, ol);
-        float dmean[MAXO] = {0.f, 0.f, 0.f, 0.f}, dls[MAXO] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < A; ++j) a2[j] = an[j];
+          }
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float h = cvr[c], mu = om[c];
-          const float nonterm = p.one_minus_gamma * h + p.gamma * fmaxf(h, nqc[c]);
-          const float tu = nonterm * (1.f - dn) + h * dn;
-          const float tb = fminf(fmaxf(tu - mu, -p.td_bound), p.td_bound) + mu;
-          const float x = ol[c];
-          const float y1 = 4.f - softplus_f(4.f - x);
-          const float ls = -4.f + softplus_f(y1 + 4.f);
-          const float sd = expf(ls), var = sd * sd;
-          const float du = mu - tu, db = mu - tb;
-          if (e.valid) {
-            dmean[c] = du / var * p.inv_bgc;
-            dls[c] = (1.f - db * db / var) * p.inv_bgc * dsoftplus(y1 + 4.f) * dsoftplus(4.f - x);
-            if (e.g == 0) {
-              loss_c += (double)(du * du / (2.f * var) + db * db / (2.f * var) + logf(sd));
-              sc_m[c] += dmean[c]; sc_l[c] += dls[c];
+          for (int j = 0; j < MAXO; ++j) hpart[j] = 0.f;
+        } else if (d.post == POST_QT0 || d.post == POST_QT1) {
+          float out[MAXO];
+          head_combine(e, hpart, d.hb_off, out);
+          if (d.post == POST_QT0) qt0 = out[0];
+          else {
+            // compute_target                                                              src/ssac.py:284-294
+            q_target = rew + p.gamma * (1.f - dn) * (fminf(qt0, out[0]) - alpha * logp);
+            if (p.dbg && e.g == 0 && e.valid) { p.dbg[gr * 16 + 5] = qt0; p.dbg[gr * 16 + 6] = out[0]; }
+          }
+          hpart[0] = 0.f;
+        } else if (d.post == POST_KEEP) {
+          // mean head of a constraint critic: its partial waits for the log-std head
+#pragma unroll
+          for (int j = 0; j < MAXO; ++j) { hkeep[j] = hpart[j]; hpart[j] = 0.f; }
+          hb_keep = d.hb_off;
+        } else if (d.post == POST_QCT) {
+          // constraint_critic_target(next_obs, a2, sample=True)                             src/ssac.py:342-344, 88-90
+          float om[MAXO], ol[MAXO];
+          head_combine(e, hkeep, hb_keep, om);
+          named_bar_sync(1, EPI_THREADS);                                 // hp is reused by the second combine
+          head_combine(e, hpart, d.hb_off, ol);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float sd = expf(soft_clamp(ol[c], -4.f, 4.f));
+            const float ee = fminf(fmaxf(e.valid ? p.n_qc.get(gr, c) : 0.f, -2.f), 2.f);
+            nqc[c] = fmaf(ee, sd, om[c]);
+          }
+          if (p.dbg && e.g == 0 && e.valid) {
+            float* dd = p.dbg + gr * 16;
+            dd[0] = a1[0]; dd[1] = a1[A - 1]; dd[2] = logp; dd[3] = a2[0]; dd[4] = a2[A - 1]; dd[7] = nqc[0];
+          }
+#pragma unroll
+          for (int j = 0; j < MAXO; ++j) hpart[j] = 0.f;
+        } else if (d.post == POST_Q0 || d.post == POST_Q1) {
+          // Q_i loss and its backward through the head                                      src/ssac.py:296-298, 437-441
+          const int i = d.post == POST_Q0 ? 0 : 1;
+          tmem_st_wait();
+          float oq[MAXO];
+          head_combine(e, hpart, d.hb_off, oq);
+          const float err_q = oq[0] - q_target;
+          float dq[MAXO] = {e.valid ? err_q * p.inv_bg : 0.f, 0.f, 0.f, 0.f};
+          if (e.g == 0 && e.valid) {
+            loss_q += 0.5 * (double)err_q * err_q;
+            if (i == 0) sc_q0 += dq[0]; else sc_q1 += dq[0];
+            if (p.dbg) { p.dbg[gr * 16 + 8 + i] = oq[0]; p.dbg[gr * 16 + 12 + i] = dq[0]; }
+          }
+          epi_head_backward(e, TM_R1, dq, 1, p.hw_q[i], slot_q_w2(i), slot_q_b1(i), p.sv[SV_Q_DH2 + i]);
+          hpart[0] = 0.f;
+        } else if (d.post == POST_QC) {
+          // distributional Qc loss (reachability targets with the TD bound) and its backward through both heads
+          //                                                                                src/ssac.py:345-354, 416-423
+          tmem_st_wait();
+          float om[MAXO], ol[MAXO];
+          head_combine(e, hkeep, hb_keep, om);
+          named_bar_sync(1, EPI_THREADS);
+          head_combine(e, hpart, d.hb_off, ol);
+          float dmean[MAXO] = {0.f, 0.f, 0.f, 0.f}, dls[MAXO] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float h = cvr[c], mu = om[c];
+            const float nonterm = p.one_minus_gamma * h + p.gamma * fmaxf(h, nqc[c]);
+            const float tu = nonterm * (1.f - dn) + h * dn;
+            const float tb = fminf(fmaxf(tu - mu, -p.td_bound), p.td_bound) + mu;
+            const float x = ol[c];
+            const float y1 = 4.f - softplus_f(4.f - x);
+            const float ls = -4.f + softplus_f(y1 + 4.f);
+            const float sd = expf(ls), var = sd * sd;
+            const float du = mu - tu, db = mu - tb;
+            if (e.valid) {
+              dmean[c] = du / var * p.inv_bgc;
+              dls[c] = (1.f - db * db / var) * p.inv_bgc * dsoftplus(y1 + 4.f) * dsoftplus(4.f - x);
+              if (e.g == 0) {
+                loss_c += (double)(du * du / (2.f * var) + db * db / (2.f * var) + logf(sd));
+                sc_m[c] += dmean[c]; sc_l[c] += dls[c];
+              }
             }
           }
+          if (p.dbg && e.g == 0 && e.valid) {
+            float* dd = p.dbg + gr * 16;
+            dd[10] = om[0]; dd[11] = ol[0]; dd[14] = dmean[0]; dd[15] = dls[0];
+          }
+#pragma unroll 1
+          for (int hd = 0; hd < 2; ++hd) {                                 // mean head (m1 stashed in R0), log-std head (l1 in R1)
+            float dsel[MAXO];
+#pragma unroll
+            for (int j = 0; j < MAXO; ++j) dsel[j] = hd == 0 ? dmean[j] : dls[j];
+            epi_head_backward(e, hd == 0 ? TM_R0 : TM_R1, dsel, C, hd == 0 ? p.hw_cm : p.hw_cl, hd == 0 ? slot_c_wm(0) : slot_c_wl(0, C),
+                              hd == 0 ? SLOT_C_BM0 : SLOT_C_BL0, p.sv[hd == 0 ? SV_C_DM1 : SV_C_DL1]);
+          }
+#pragma unroll
+          for (int j = 0; j < MAXO; ++j) hpart[j] = 0.f;
         }
-        if (p.dbg && e.g == 0 && e.valid) {
-          float* d = p.dbg + gr * 16;
-          d[10] = om[0]; d[11] = ol[0]; d[14] = dmean[0]; d[15] = dls[0];
-        }
-        epi_head_backward<C>(e, TM_R0, dmean, p.hw_cm, slot_c_wm(0), SLOT_C_BM0, p.c_dm1);
-        epi_head_backward<C>(e, TM_R1, dls, p.hw_cl, slot_c_wl(0, C), SLOT_C_BL0, p.c_dl1);
-        epi_op_done(e);
-        epi_backward(e, mt2, SLOT_C_BT1, p.c_dt2, TM_R0, true); epi_op_done(e);      // dt2 = (dm1 W_m0 + dl1 W_l0) * (t2 > 0)
-        epi_backward(e, mt1, SLOT_C_BT0, p.c_dt1, 0, false);                           // dt1 = (dt2 W_t1) * (t1 > 0)
-        // the next arrival on act_ready follows the next tile's staging
+        if (o != MAX_OPS - 1) epi_op_done(e);          // the arrival for the next tile's first op follows its staging
       }
     }
     // ---- per-CTA results ---------------------------------------------------------------------------------------------------
     if (e.g == 0) {
       float v;
-      v = warp_sum(sc_q[0]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 0], v);
-      v = warp_sum(sc_q[1]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 1], v);
+      v = warp_sum(sc_q0); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 0], v);
+      v = warp_sum(sc_q1); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 1], v);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         v = warp_sum(sc_m[c]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 2 + c], v);
@@ -651,6 +712,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) critic_fused_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                      // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == ISSUER) tmem_dealloc(tmem, 512);
 }
 
@@ -772,6 +834,7 @@ __global__ void __launch_bounds__(256) critic_grad_reduce_kernel(ReduceTable t, 
 // ---------------------------------------------------------------------------------------------------------------
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static float* g_dbg_rows = nullptr;
+static long long* g_prof = nullptr;
 
 struct Plan {
   int64_t Bpad; int Kx, n_tiles, grid, nv;
@@ -780,14 +843,14 @@ struct Plan {
 };
 static Plan make_plan(int64_t B, int S, int A, int C) {
   Plan pl;
-  pl.Bpad = (B + TILE - 1) / TILE * TILE;
+  pl.Bpad = (B + CLUSTER * TILE - 1) / (CLUSTER * TILE) * (CLUSTER * TILE);        // whole tile pairs (one per CTA pair)
   pl.Kx = round_up(S + A, 16);
   pl.n_tiles = (int)(pl.Bpad / TILE);
-  pl.grid = std::min(pl.n_tiles, 148);
+  pl.grid = std::min(pl.n_tiles, 148) / CLUSTER * CLUSTER;
   pl.nv = n_slots(C);
   // images: 8 first-layer (kp = Kx) + 17 hidden (kp = 256)
-  pl.img_bytes = (int64_t)8 * HID * pl.Kx * 2 + (int64_t)17 * HID * HID * 2;
-  pl.ctab_floats = 20 * HID + (4 * A + 4 + 4 * C) * HID + 64;
+  pl.img_bytes = (int64_t)8 * HID * (pl.Kx + KBIAS) * 2 + (int64_t)12 * HID * (HID + KBIAS) * 2 + (int64_t)5 * HID * HID * 2;
+  pl.ctab_floats = (4 * A + 4 + 4 * C) * HID + 64;
   return pl;
 }
 // split-K factors of the dW jobs: big jobs (N = 256) and first-layer jobs (N = Kx) share 148 CTAs in proportion to their bytes
@@ -810,15 +873,24 @@ int64_t critic_ws_bytes(int64_t B, int S, int A, int C) {
 }
 
 void critic_set_debug_rows(float* p) { g_dbg_rows = p; }
+void critic_set_prof(long long* p) { g_prof = p; }
 
 template <int A, int C>
-static int launch_fused(const FusedParams& fp, int grid, size_t smem, cudaStream_t st) {
+static int launch_fused(const FusedParams& fp, int& grid, size_t smem, cudaStream_t st) {
   auto k = critic_fused_kernel<A, C>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int max_clusters = 0;
+  if (!max_clusters) {
     DRPO_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    attr_done = true;
+    // CTA pairs must sit in one GPC: ask how many pairs of this footprint can be resident (74 on a full B200)
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = 232448 - 1024;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 148 / CLUSTER; }
+    max_clusters = n;
   }
+  grid = std::min(grid, max_clusters * CLUSTER);
   DRPO_LAUNCH(k, grid, F_THREADS, smem, st, fp);
   return DRPO_OK;
 }
@@ -851,60 +923,72 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
   int64_t img_off = 0; int ctab_off = 0; int n_ops = 0;
   auto add_image = [&](const drpo_linear& l, bool transposed) -> uint32_t {
     PackEntry& e = pt.e[pt.n++];
-    e.W = l.w; e.transposed = transposed ? 1 : 0;
+    e.W = l.w; e.transposed = transposed ? 1 : 0; e.bias = transposed ? nullptr : l.b;
     if (!transposed) { e.n_real = l.out_dim; e.k_real = l.in_dim; e.kp = l.in_dim == HID ? HID : pl.Kx; }
     else { e.n_real = l.in_dim; e.k_real = l.out_dim; e.kp = HID; }
     e.dst = img_off / 2;
     const uint32_t off = (uint32_t)img_off;
-    img_off += (int64_t)HID * e.kp * 2;
+    img_off += (int64_t)HID * (e.kp + (transposed ? 0 : KBIAS)) * 2;
     return off;
   };
   auto add_const = [&](const float* src, int n) -> int {
     CopyEntry& e = ct.e[ct.n++]; e.src = src; e.n = n; e.dst = ctab_off;
     const int off = ctab_off; ctab_off += (n + 3) & ~3; return off;
   };
-  auto add_fwd = [&](const drpo_linear& l, int a_src) {
+  auto add_fwd = [&](const drpo_linear& l, int a_src, int out_region, int save, bool wait_all = false) {
     FOp& op = fp.op[n_ops];
     op.w_off[0] = add_image(l, false); op.kp = (uint16_t)(l.in_dim == HID ? HID : pl.Kx); op.a_src[0] = (uint8_t)a_src; op.parts = 1;
-    fp.bias_off[n_ops] = add_const(l.b, HID);
+    op.bias = 1;
+    EOp& e = fp.eop[n_ops];
+    e.out_region = (uint8_t)out_region; e.save = (uint8_t)save; e.wait_all = wait_all ? 1 : 0;
     ++n_ops;
   };
-  auto add_bwd = [&](const drpo_linear& l, int a_src) {
+  auto set_head = [&](const drpo_linear& head, int post) -> int {            // CUDA-core head on the op just added
+    EOp& e = fp.eop[n_ops - 1];
+    e.no = (uint8_t)head.out_dim; e.hw_off = add_const(head.w, head.out_dim * HID); e.hb_off = add_const(head.b, head.out_dim);
+    e.post = (uint8_t)post;
+    return e.hw_off;
+  };
+  auto add_bwd = [&](const drpo_linear& l, int a_src, int hsave, int bias_slot, int save, int out_region, bool wait_all) {
     FOp& op = fp.op[n_ops];
-    op.w_off[0] = add_image(l, true); op.kp = HID; op.a_src[0] = (uint8_t)a_src; op.parts = 1; fp.bias_off[n_ops] = 0;
+    op.w_off[0] = add_image(l, true); op.kp = HID; op.a_src[0] = (uint8_t)a_src; op.parts = 1;
+    EOp& e = fp.eop[n_ops];
+    e.backward = 1; e.hsave = (uint8_t)hsave; e.bias_slot = (uint8_t)bias_slot; e.save = (uint8_t)save; e.out_region = (uint8_t)out_region;
+    e.wait_all = wait_all ? 1 : 0;
     ++n_ops;
   };
-  // op order must match the epilogue program of critic_fused_kernel
-  add_fwd(a.actor->l0, A_XS0); add_fwd(a.actor->l1, A_R0);
-  fp.hw_actor[0] = add_const(a.actor->l2.w, 2 * A * HID); fp.hb_actor[0] = add_const(a.actor->l2.b, 2 * A);
+  // order: actor, target Q1, target Q2, actor_safe, target Qc (the sampled action in xs0 is a1, then a2), Q1, Q2, Qc
+  add_fwd(a.actor->l0, A_XS0, 1, 0); add_fwd(a.actor->l1, A_R0, 0, 0); set_head(a.actor->l2, POST_POLICY0);
   for (int i = 0; i < 2; ++i) {
-    add_fwd(a.q_target[i].l0, A_XS0); add_fwd(a.q_target[i].l1, A_R0);
-    fp.hw_qt[i] = add_const(a.q_target[i].l2.w, HID); fp.hb_qt[i] = add_const(a.q_target[i].l2.b, 1);
+    add_fwd(a.q_target[i].l0, A_XS0, 1, 0); add_fwd(a.q_target[i].l1, A_R0, 0, 0); set_head(a.q_target[i].l2, i == 0 ? POST_QT0 : POST_QT1);
   }
-  add_fwd(a.actor_safe->l0, A_XS0); add_fwd(a.actor_safe->l1, A_R0);
-  fp.hw_actor[1] = add_const(a.actor_safe->l2.w, 2 * A * HID); fp.hb_actor[1] = add_const(a.actor_safe->l2.b, 2 * A);
-  add_fwd(a.qc_target.trunk0, A_XS0); add_fwd(a.qc_target.trunk1, A_R0); add_fwd(a.qc_target.mean0, A_R1); add_fwd(a.qc_target.lstd0, A_R1);
-  fp.hw_ctm = add_const(a.qc_target.mean1.w, C * HID); fp.hb_ctm = add_const(a.qc_target.mean1.b, C);
-  fp.hw_ctl = add_const(a.qc_target.lstd1.w, C * HID); fp.hb_ctl = add_const(a.qc_target.lstd1.b, C);
+  add_fwd(a.actor_safe->l0, A_XS0, 1, 0); add_fwd(a.actor_safe->l1, A_R0, 0, 0); set_head(a.actor_safe->l2, POST_POLICY1);
+  add_fwd(a.qc_target.trunk0, A_XS0, 1, 0); add_fwd(a.qc_target.trunk1, A_R0, 2, 0);
+  add_fwd(a.qc_target.mean0, A_R1, 0, 0); set_head(a.qc_target.mean1, POST_KEEP);
+  add_fwd(a.qc_target.lstd0, A_R1, 0, 0); set_head(a.qc_target.lstd1, POST_QCT);
   for (int i = 0; i < 2; ++i) {
-    add_fwd(a.q[i].l0, A_XS1); add_fwd(a.q[i].l1, A_R0); add_bwd(a.q[i].l1, A_R1);
-    fp.hw_q[i] = add_const(a.q[i].l2.w, HID); fp.hb_q[i] = add_const(a.q[i].l2.b, 1);
+    add_fwd(a.q[i].l0, A_XS1, 1, SV_Q_H1 + i);
+    add_fwd(a.q[i].l1, A_R0, 2, 0); fp.hw_q[i] = set_head(a.q[i].l2, i == 0 ? POST_Q0 : POST_Q1);           // h2 stashed in R1
+    add_bwd(a.q[i].l1, A_R1, SV_Q_H1 + i, slot_q_b0(i), SV_Q_DH1 + i, 0, false);                              // dh1 = (dh2 W1) * (h1 > 0)
   }
-  add_fwd(a.qc.trunk0, A_XS1); add_fwd(a.qc.trunk1, A_R0); add_fwd(a.qc.mean0, A_R1); add_fwd(a.qc.lstd0, A_R1);
-  fp.hw_cm = add_const(a.qc.mean1.w, C * HID); fp.hb_cm = add_const(a.qc.mean1.b, C);
-  fp.hw_cl = add_const(a.qc.lstd1.w, C * HID); fp.hb_cl = add_const(a.qc.lstd1.b, C);
+  add_fwd(a.qc.trunk0, A_XS1, 1, SV_C_T1); add_fwd(a.qc.trunk1, A_R0, 2, SV_C_T2);
+  add_fwd(a.qc.mean0, A_R1, 1, 0); fp.hw_cm = set_head(a.qc.mean1, POST_KEEP);                              // m1 stashed in R0
+  add_fwd(a.qc.lstd0, A_R1, 2, 0, true); fp.hw_cl = set_head(a.qc.lstd1, POST_QC);                          // l1 stashed over t2
   {
-    FOp& op = fp.op[n_ops];                                       // dt2: two K parts into the same accumulators
+    FOp& op = fp.op[n_ops];                                       // dt2 = (dm1 W_m0 + dl1 W_l0) * (t2 > 0): two K parts
     op.w_off[0] = add_image(a.qc.mean0, true); op.w_off[1] = add_image(a.qc.lstd0, true);
-    op.kp = HID; op.a_src[0] = A_R0; op.a_src[1] = A_R1; op.parts = 2; fp.bias_off[n_ops] = 0; ++n_ops;
+    op.kp = HID; op.a_src[0] = A_R0; op.a_src[1] = A_R1; op.parts = 2;
+    EOp& e = fp.eop[n_ops];
+    e.backward = 1; e.hsave = SV_C_T2; e.bias_slot = SLOT_C_BT1; e.save = SV_C_DT2; e.out_region = 1; e.wait_all = 1;
+    ++n_ops;
   }
-  add_bwd(a.qc.trunk1, A_R0);
+  add_bwd(a.qc.trunk1, A_R0, SV_C_T1, SLOT_C_BT0, SV_C_DT1, 0, false);                                        // dt1 = (dt2 W_t1) * (t1 > 0)
   if (n_ops != MAX_OPS || img_off > pl.img_bytes || ctab_off > pl.ctab_floats) {
     set_error("drpo_critic_step(bf16): internal plan mismatch (%d ops, %lld image bytes, %d consts)", n_ops, (long long)img_off, ctab_off);
     return DRPO_ERR_ARG;
   }
   {
-    dim3 grid(16, pt.n);
+    dim3 grid(64, pt.n);
     DRPO_LAUNCH(pack_images_kernel, grid, 256, 0, st, pt, reinterpret_cast<__nv_bfloat16*>(img));
     DRPO_LAUNCH(gather_ctab_kernel, ct.n, 256, 0, st, ct, ctab);
   }
@@ -919,17 +1003,18 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
   fp.inv_bg = (float)(1.0 / (double)a.global_batch_size); fp.inv_bgc = (float)(1.0 / ((double)a.global_batch_size * C));
   fp.B = B; fp.Bpad = pl.Bpad; fp.S = S; fp.A = A; fp.C = C; fp.D = D; fp.Kx = pl.Kx; fp.n_tiles = pl.n_tiles;
   fp.x_sa = x_sa;
-  fp.q_h1[0] = sv[0]; fp.q_dh2[0] = sv[1]; fp.q_dh1[0] = sv[2]; fp.q_h1[1] = sv[3]; fp.q_dh2[1] = sv[4]; fp.q_dh1[1] = sv[5];
-  fp.c_t1 = sv[6]; fp.c_t2 = sv[7]; fp.c_dm1 = sv[8]; fp.c_dl1 = sv[9]; fp.c_dt2 = sv[10]; fp.c_dt1 = sv[11];
-  fp.gacc_out = gacc_out; fp.nv = pl.nv; fp.loss_part = loss_part; fp.err_flag = err_flag; fp.dbg = g_dbg_rows;
+  fp.sv[0] = nullptr;
+  for (int i = 0; i < 12; ++i) fp.sv[1 + i] = sv[i];
+  fp.gacc_out = gacc_out; fp.nv = pl.nv; fp.loss_part = loss_part; fp.err_flag = err_flag; fp.dbg = g_dbg_rows; fp.prof = g_prof;
   // shared memory: ring + 2 x-buffers + constants + column sums + head partials + barriers
-  const size_t fixed = (size_t)2 * TILE * pl.Kx * 2 + (size_t)((ctab_off + 3) & ~3) * 4 + (size_t)pl.nv * HID * 4 + NGROUPS * TILE * 16 + sizeof(FusedSmem);
+  const size_t fixed = (size_t)2 * TILE * pl.Kx * 2 + TILE * KBIAS * 2 + (size_t)((ctab_off + 3) & ~3) * 4 + (size_t)pl.nv * HID * 4 + NGROUPS * TILE * 16 + sizeof(FusedSmem);
   int stages = (int)((232448 - 1024 - fixed) / CHUNK_BYTES);
   if (stages > 6) stages = 6;
   if (stages < 2) { set_error("drpo_critic_step(bf16): shared-memory budget exceeded"); return DRPO_ERR_ARG; }
   fp.stages = stages;
   const size_t smem = fixed + (size_t)stages * CHUNK_BYTES;
   int rc;
+  // (pl.grid may shrink to the number of co-resident CTA pairs; the reductions below read it afterwards)
   if (A == 1 && C == 1) rc = launch_fused<1, 1>(fp, pl.grid, smem, st);
   else if (A == 1 && C == 2) rc = launch_fused<1, 2>(fp, pl.grid, smem, st);
   else if (A == 1 && C == 4) rc = launch_fused<1, 4>(fp, pl.grid, smem, st);
@@ -959,13 +1044,13 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
     r.dst = goff(dst_param); r.src = gacc_out + slot * HID + off; r.n_src = pl.grid; r.stride = (int64_t)pl.nv * HID; r.rows = 1; r.cols = n; r.ld = n;
   };
   for (int i = 0; i < 2; ++i) {
-    add_job(fp.q_dh2[i], fp.q_h1[i], HID, a.q[i].l1);
-    add_job(fp.q_dh1[i], x_sa, D, a.q[i].l0);
+    add_job(fp.sv[SV_Q_DH2 + i], fp.sv[SV_Q_H1 + i], HID, a.q[i].l1);
+    add_job(fp.sv[SV_Q_DH1 + i], x_sa, D, a.q[i].l0);
     add_vec(a.q[i].l2.w, slot_q_w2(i), 0, HID); add_vec(a.q[i].l2.b, SLOT_SCAL, i, 1);
     add_vec(a.q[i].l1.b, slot_q_b1(i), 0, HID); add_vec(a.q[i].l0.b, slot_q_b0(i), 0, HID);
   }
-  add_job(fp.c_dm1, fp.c_t2, HID, a.qc.mean0); add_job(fp.c_dl1, fp.c_t2, HID, a.qc.lstd0);
-  add_job(fp.c_dt2, fp.c_t1, HID, a.qc.trunk1); add_job(fp.c_dt1, x_sa, D, a.qc.trunk0);
+  add_job(fp.sv[SV_C_DM1], fp.sv[SV_C_T2], HID, a.qc.mean0); add_job(fp.sv[SV_C_DL1], fp.sv[SV_C_T2], HID, a.qc.lstd0);
+  add_job(fp.sv[SV_C_DT2], fp.sv[SV_C_T1], HID, a.qc.trunk1); add_job(fp.sv[SV_C_DT1], x_sa, D, a.qc.trunk0);
   for (int c = 0; c < C; ++c) {
     add_vec(a.qc.mean1.w + c * HID, slot_c_wm(c), 0, HID); add_vec(a.qc.lstd1.w + c * HID, slot_c_wl(c, C), 0, HID);
   }
@@ -977,7 +1062,7 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
     const size_t dsm = DW_STAGES * DW_STAGE_BYTES + sizeof(DwSmem);
     if (!attr_done) { DRPO_CUDA_OK(cudaFuncSetAttribute(critic_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); attr_done = true; }
     DRPO_LAUNCH(critic_dw_kernel, cta, DW_THREADS, dsm, st, dp);
-    dim3 grid(32, rt.n);
+    dim3 grid(64, rt.n);
     DRPO_LAUNCH(critic_grad_reduce_kernel, grid, 256, 0, st, rt, G);
   }
   Scale2 sc; sc.v[0] = 1.0 / (double)a.global_batch_size; sc.v[1] = 1.0 / ((double)a.global_batch_size * C);

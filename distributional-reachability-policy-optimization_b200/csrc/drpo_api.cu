@@ -351,6 +351,7 @@ int drpo_multiplier_step(const drpo_multiplier_args* a) {
 }
 
 int drpo_debug_critic_rows(float* rows) { cu::critic_set_debug_rows(rows); return DRPO_OK; }
+int drpo_debug_critic_prof(int64_t* stamps) { cu::critic_set_prof((long long*)stamps); return DRPO_OK; }
 
 int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets, int64_t rows_padded, int32_t ksplit, float* partial,
                          float* out, void* stream) {

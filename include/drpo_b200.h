@@ -270,6 +270,9 @@ int drpo_critic_step(const drpo_critic_args* args);
  * dL/dmean, dL/dlogstd (first constraint).  drpo_debug_critic_dw runs the split-K weight-gradient kernel on one operand
  * pair given in the octet layout ([features/8][rows_padded][8] bf16): out[256, 8*b_octets] = dH^T H. */
 int drpo_debug_critic_rows(float* rows);
+/* profiling aid: device int64 [24][32] clock stamps per dense op (issuer: operands ready, MMAs issued, per-chunk waits; last epilogue group:
+ * accumulator full, epilogue done) of CTA 0's second tile */
+int drpo_debug_critic_prof(int64_t* stamps);
 int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets, int64_t rows_padded, int32_t ksplit,
                          float* partial, float* out, void* stream);
 
