@@ -253,7 +253,7 @@ def run_ours(args):
         sat_bytes_row = (4 * (2 * S + A + 1) + 4 * (2 * S + A + 1 + C) + 2 + 1) + (1 + 4 * S + 4 + 4 * S + 4)
         if ksat.value > 0:
             sat_gbs = sat_bytes_row * rows_launched / (ksat.value * 1e-3) / 1e9
-            roofline["elementwise"] = {"bound": "hbm", "kernels": "hooks_store_kernel + compact_count/scan/scatter", "achieved": round(sat_gbs, 1),
+            roofline["elementwise"] = {"bound": "hbm", "kernels": "hooks_store_kernel (env hooks + ring store + block survivor counts) + compact_scatter_scan_kernel", "achieved": round(sat_gbs, 1),
                                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(sat_gbs / pk["hbm"], 4),
                                        "avg_ms_per_step": round(ksat.value / kn.value, 4), "algorithmic_bytes_per_row": sat_bytes_row}
     else:

@@ -379,7 +379,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
   float* ctab = reinterpret_cast<float*>(ones + TILE * KBIAS * 2);
   float* gacc = ctab + ((p.ctab_floats + 3) & ~3);
   float4* hp = reinterpret_cast<float4*>(gacc + p.nv * HID);
-  FusedSmem* sm = reinterpret_cast<FusedSmem*>(hp + NGROUPS * TILE);
+  float4* polres = hp + NGROUPS * TILE;                     // [128 rows] sampled action + log-prob of the policy post step
+  FusedSmem* sm = reinterpret_cast<FusedSmem*>(polres + TILE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int PRODUCER = EPI_THREADS / 32, ISSUER = PRODUCER + 1;
   int* err = p.err_flag;
@@ -560,19 +561,29 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
           const bool first = d.post == POST_POLICY0;
           float out[MAXO];
           head_combine(e, hpart, d.hb_off, out);
-          float lp = 0.f, an[A];
+          // one warp per group does the transcendental work for 32 of the tile's rows (group g: rows 32g.., four warps on four
+          // different schedulers) and shares the result through shared memory; all 512 threads computing their own row
+          // redundantly cost ~4x the issue slots on the critical path
+          if ((warp & 3) == e.g) {
+            float lp = 0.f, an[A];
 #pragma unroll
-          for (int j = 0; j < A; ++j) {
-            const float mu = out[j], raw = out[A + j];
-            const float log_std = -6.f + 10.f * sigmoid_f(raw);
-            const float sd = expf(log_std);
-            const float eps = !e.valid ? 0.f : (first ? p.n_actor.get(gr, j) : p.n_safe.get(gr, j));
-            const float x = fmaf(eps, sd, mu);
-            an[j] = tanhf(x);
-            const float ladj = 2.f * (0.69314718055994531f - x - softplus_f(-2.f * x));
-            const float dd = x - mu;
-            lp += (0.f - ladj) + (-(dd * dd) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467267f);
+            for (int j = 0; j < A; ++j) {
+              const float mu = out[j], raw = out[A + j];
+              const float log_std = -6.f + 10.f * sigmoid_f(raw);
+              const float sd = expf(log_std);
+              const float eps = !e.valid ? 0.f : (first ? p.n_actor.get(gr, j) : p.n_safe.get(gr, j));
+              const float x = fmaf(eps, sd, mu);
+              an[j] = tanhf(x);
+              const float ladj = 2.f * (0.69314718055994531f - x - softplus_f(-2.f * x));
+              const float dd = x - mu;
+              lp += (0.f - ladj) + (-(dd * dd) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467267f);
+            }
+            polres[e.row] = make_float4(an[0], an[A - 1], lp, 0.f);
           }
+          named_bar_sync(1, EPI_THREADS);
+          const float4 pr = polres[e.row];
+          float lp = pr.z, an[A];
+          an[0] = pr.x; an[A - 1] = pr.y;
           // patch the sampled action into xs0's action columns: the next ops read [next_obs, a].  Order of the ops: actor,
           // target Q1, target Q2, actor_safe, target Qc - so the columns hold a1 while the Q's read them and a2 afterwards
           if (e.g == 0) {
@@ -1007,7 +1018,7 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
   for (int i = 0; i < 12; ++i) fp.sv[1 + i] = sv[i];
   fp.gacc_out = gacc_out; fp.nv = pl.nv; fp.loss_part = loss_part; fp.err_flag = err_flag; fp.dbg = g_dbg_rows; fp.prof = g_prof;
   // shared memory: ring + 2 x-buffers + constants + column sums + head partials + barriers
-  const size_t fixed = (size_t)2 * TILE * pl.Kx * 2 + TILE * KBIAS * 2 + (size_t)((ctab_off + 3) & ~3) * 4 + (size_t)pl.nv * HID * 4 + NGROUPS * TILE * 16 + sizeof(FusedSmem);
+  const size_t fixed = (size_t)2 * TILE * pl.Kx * 2 + TILE * KBIAS * 2 + (size_t)((ctab_off + 3) & ~3) * 4 + (size_t)pl.nv * HID * 4 + (NGROUPS + 1) * TILE * 16 + sizeof(FusedSmem);
   int stages = (int)((232448 - 1024 - fixed) / CHUNK_BYTES);
   if (stages > 6) stages = 6;
   if (stages < 2) { set_error("drpo_critic_step(bf16): shared-memory budget exceeded"); return DRPO_ERR_ARG; }
