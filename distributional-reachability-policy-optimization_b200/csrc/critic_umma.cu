@@ -48,7 +48,9 @@ constexpr uint32_t TM_ACC = 0, TM_R0 = 256, TM_R1 = 384;
 
 enum ASrc { A_XS0 = 0, A_XS1 = 1, A_R0 = 2, A_R1 = 3 };
 
-struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t bias; };   // bias: the chunks carry a bias K block
+// bias: the chunks carry a bias K block.  early: the op reads only shared-memory inputs that were complete before the previous op
+// (its A operand is [s,a] staged at the tile start), so its MMAs need not wait for the previous op's epilogues and post step
+struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t bias; uint8_t early; uint8_t pad[3]; };
 // epilogue side of an op
 enum Post { POST_NONE = 0, POST_POLICY0, POST_POLICY1, POST_QT0, POST_QT1, POST_KEEP, POST_QCT, POST_Q0, POST_Q1, POST_QC };
 struct EOp {
@@ -100,7 +102,7 @@ __host__ __device__ inline int n_slots(int C) { return SLOT_C_WM + 2 * C; }
 
 constexpr int CLUSTER = 2;                 // CTA pair: every weight chunk is fetched from L2 once and multicast to both
 struct FusedSmem {
-  uint64_t full[6], empty[6], acc_full[NGROUPS], acc_free[NGROUPS], act_ready;
+  uint64_t full[6], empty[6], acc_full[NGROUPS], acc_free[NGROUPS], act_ready[2];
   uint32_t tmem_base, pad[3];
 };
 
@@ -182,6 +184,7 @@ struct Epi {
   int64_t grow, Bpad;       // global row, padded row count
   bool valid;
   uint32_t it;              // global index of the op whose epilogue runs next (parity of the per-op barriers)
+  uint32_t arr;             // act_ready arrivals made so far
   int* err;
   long long* prof;          // non-null only in the one thread that records clock stamps
 };
@@ -203,7 +206,8 @@ __device__ __forceinline__ void epi_wait_all_mma(Epi& e) {
 __device__ __forceinline__ void epi_op_done(Epi& e) {      // this thread's TMEM / shared writes for the next op are complete
   tmem_st_wait();
   tc_fence_before();
-  mbar_arrive(&e.sm->act_ready);
+  mbar_arrive(&e.sm->act_ready[e.arr & 1]);      // arrival number k enables op k; even / odd ops use separate barriers so that an
+  ++e.arr;                                       // issuer that observes op k's phase late can never be two phases behind
 }
 // 16-byte panels of 32 packed columns -> global octet layout
 __device__ __forceinline__ void save_octets(const Epi& e, __nv_bfloat16* base, int half, const uint32_t (&pk)[16]) {
@@ -388,7 +392,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], CLUSTER); }
     for (int g = 0; g < NGROUPS; ++g) { mbar_init(&sm->acc_full[g], 1); mbar_init(&sm->acc_free[g], 128); }
-    mbar_init(&sm->act_ready, EPI_THREADS);
+    mbar_init(&sm->act_ready[0], EPI_THREADS); mbar_init(&sm->act_ready[1], EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == ISSUER) tmem_alloc(&sm->tmem_base, 512);
@@ -458,7 +462,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
             if (stamp) p.prof[o * 32 + 8] = clock64();
             for (int c = 0; c < NGROUPS; ++c) mbar_wait(&sm->acc_free[c], (it & 1) ^ 1, err, 3);
             if (stamp) p.prof[o * 32 + 9] = clock64();
-            mbar_wait(&sm->act_ready, it & 1, err, 2);
+            // the previous op's activations / post step; an `early` op does not read them: its MMAs go first and the phase is
+            // observed right after (every phase is observed, in order, before the next one of the same barrier can complete)
+            if (!op.early) mbar_wait(&sm->act_ready[it & 1], (it >> 1) & 1, err, 2);
             if (stamp) p.prof[o * 32] = clock64();
           }
           tc_fence_after();
@@ -495,13 +501,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
           __syncwarp();
           stage = sw; phase = pw;
         }
+        if (op.early) mbar_wait(&sm->act_ready[it & 1], (it >> 1) & 1, err, 6);
         if (stamp) p.prof[o * 32 + 1] = clock64();
       }
   } else {
     // ---- epilogue groups ----------------------------------------------------------------------------------------------------
     Epi e;
     e.sm = sm; e.ctab = ctab; e.gacc = gacc; e.hp = hp; e.g = warp >> 2; e.lane = lane; e.row = (warp & 3) * 32 + lane;
-    e.tm = tmem + ((uint32_t)((warp & 3) * 32) << 16); e.it = 0; e.err = err; e.Bpad = p.Bpad;
+    e.tm = tmem + ((uint32_t)((warp & 3) * 32) << 16); e.it = 0; e.arr = 0; e.err = err; e.Bpad = p.Bpad;
     e.prof = (blockIdx.x == 0 && (threadIdx.x & 127) == 0) ? p.prof : nullptr;          // first thread of every group
     const int S = p.S, D = p.D;
     const float alpha = expf(*p.log_alpha);
@@ -946,10 +953,10 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
     CopyEntry& e = ct.e[ct.n++]; e.src = src; e.n = n; e.dst = ctab_off;
     const int off = ctab_off; ctab_off += (n + 3) & ~3; return off;
   };
-  auto add_fwd = [&](const drpo_linear& l, int a_src, int out_region, int save, bool wait_all = false) {
+  auto add_fwd = [&](const drpo_linear& l, int a_src, int out_region, int save, bool wait_all = false, bool early = false) {
     FOp& op = fp.op[n_ops];
     op.w_off[0] = add_image(l, false); op.kp = (uint16_t)(l.in_dim == HID ? HID : pl.Kx); op.a_src[0] = (uint8_t)a_src; op.parts = 1;
-    op.bias = 1;
+    op.bias = 1; op.early = early ? 1 : 0;
     EOp& e = fp.eop[n_ops];
     e.out_region = (uint8_t)out_region; e.save = (uint8_t)save; e.wait_all = wait_all ? 1 : 0;
     ++n_ops;
@@ -971,18 +978,19 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
   // order: actor, target Q1, target Q2, actor_safe, target Qc (the sampled action in xs0 is a1, then a2), Q1, Q2, Qc
   add_fwd(a.actor->l0, A_XS0, 1, 0); add_fwd(a.actor->l1, A_R0, 0, 0); set_head(a.actor->l2, POST_POLICY0);
   for (int i = 0; i < 2; ++i) {
-    add_fwd(a.q_target[i].l0, A_XS0, 1, 0); add_fwd(a.q_target[i].l1, A_R0, 0, 0); set_head(a.q_target[i].l2, i == 0 ? POST_QT0 : POST_QT1);
+    add_fwd(a.q_target[i].l0, A_XS0, 1, 0, false, i == 1);      // (target Q1 waits for a1 to be patched into xs0; target Q2 need not)
+    add_fwd(a.q_target[i].l1, A_R0, 0, 0); set_head(a.q_target[i].l2, i == 0 ? POST_QT0 : POST_QT1);
   }
-  add_fwd(a.actor_safe->l0, A_XS0, 1, 0); add_fwd(a.actor_safe->l1, A_R0, 0, 0); set_head(a.actor_safe->l2, POST_POLICY1);
+  add_fwd(a.actor_safe->l0, A_XS0, 1, 0, false, true); add_fwd(a.actor_safe->l1, A_R0, 0, 0); set_head(a.actor_safe->l2, POST_POLICY1);
   add_fwd(a.qc_target.trunk0, A_XS0, 1, 0); add_fwd(a.qc_target.trunk1, A_R0, 2, 0);
   add_fwd(a.qc_target.mean0, A_R1, 0, 0); set_head(a.qc_target.mean1, POST_KEEP);
   add_fwd(a.qc_target.lstd0, A_R1, 0, 0); set_head(a.qc_target.lstd1, POST_QCT);
   for (int i = 0; i < 2; ++i) {
-    add_fwd(a.q[i].l0, A_XS1, 1, SV_Q_H1 + i);
+    add_fwd(a.q[i].l0, A_XS1, 1, SV_Q_H1 + i, false, true);
     add_fwd(a.q[i].l1, A_R0, 2, 0); fp.hw_q[i] = set_head(a.q[i].l2, i == 0 ? POST_Q0 : POST_Q1);           // h2 stashed in R1
     add_bwd(a.q[i].l1, A_R1, SV_Q_H1 + i, slot_q_b0(i), SV_Q_DH1 + i, 0, false);                              // dh1 = (dh2 W1) * (h1 > 0)
   }
-  add_fwd(a.qc.trunk0, A_XS1, 1, SV_C_T1); add_fwd(a.qc.trunk1, A_R0, 2, SV_C_T2);
+  add_fwd(a.qc.trunk0, A_XS1, 1, SV_C_T1, false, true); add_fwd(a.qc.trunk1, A_R0, 2, SV_C_T2);
   add_fwd(a.qc.mean0, A_R1, 1, 0); fp.hw_cm = set_head(a.qc.mean1, POST_KEEP);                              // m1 stashed in R0
   add_fwd(a.qc.lstd0, A_R1, 2, 0, true); fp.hw_cl = set_head(a.qc.lstd1, POST_QC);                          // l1 stashed over t2
   {
