@@ -121,3 +121,62 @@ def test_critic_bf16_row_sharding_matches_full_batch():
         part.update_critic(*[to_dev(b[lo:hi]) for b in batch], noise=tuple(to_dev(n[lo:hi]) for n in noise), phases=1)
         total += part.critic_optimizer.grad
     assert_close(total, g_full, 1e-4, "sum of shard gradients")
+
+
+@pytest.mark.parametrize("B", [1, 129])
+def test_critic_bf16_ragged_tiny_batches(B):
+    """Batches far below one tile pair (256 rows): padded rows must contribute nothing to losses or gradients."""
+    import drpo_b200
+    S, A, C = 11, 2, 1
+    w = O.make_ssac_weights(3, S, A, C)
+    batch, noise = _inputs(S, A, C, B, seed=17)
+    wo = {k: v.clone() for k, v in w.items()}
+    lq, lc, aux = O.critic_update(wo, batch, noise, O.SSACHyper(), 0.0, O.AdamState(), 3e-4)
+    solver = make_ssac(w, S, A, C, B); solver.precision = drpo_b200.PREC_BF16
+    glq, glc = solver.update_critic(*[to_dev(b) for b in batch], noise=tuple(to_dev(n) for n in noise), phases=1)
+    from drpo_b200 import _lib
+    _lib.check_kernel_status("critic bf16 step")
+    # a single row has no averaging at all: 5e-2 on the losses, gradients 1e-1 of scale
+    assert_close(glq, lq, 5e-2, "loss_q"); assert_close(glc, lc, 5e-2, "loss_c")
+    gviews = solver.critic_arena_views(solver.critic_optimizer.grad)
+    for k in [k for k in w if k.startswith(("critic.", "constraint_critic."))]:
+        assert_close(gviews[k], aux["grads_raw"][k], 1e-1, f"grad {k}", max_outlier_frac=5e-2)
+
+
+def test_critic_bf16_full_size_matches_fp32_path():
+    """BASELINE size (tracking dims, B = 65 536, in-kernel Philox noise): the fused bf16 step against the fp32 CUDA path (itself
+    pinned to the oracle at smaller sizes) on identical inputs and noise streams: losses, grad norms, gradients."""
+    import drpo_b200
+    from drpo_b200 import synthetic
+    _, S, A, C = synthetic.WORKLOADS["tracking"]
+    B = 65536
+    w = synthetic.make_ssac_weights(43567, S, A, C)
+    batch = [t.to(dev()) for t in synthetic.make_critic_batch("tracking", B, 49283)]
+    res = {}
+    for name, prec in (("fp32", drpo_b200.PREC_FP32), ("bf16", drpo_b200.PREC_BF16)):
+        cfg = drpo_b200.SSAC.Config(); cfg.batch_size = B; cfg.constraint_critic_cfg.std_ratio = 1.0
+        solver = drpo_b200.SSAC(cfg, S, A, C, 10, 100, 1000, 10, 5.0, device=dev())
+        solver.load_state_dict(w, strict=False)
+        solver.precision = prec
+        lq, lc = solver.update_critic(*batch)
+        res[name] = (float(lq), float(lc), solver._losses[2:4].clone().cpu(), solver.critic_optimizer.grad.clone().cpu())
+    from drpo_b200 import _lib
+    _lib.check_kernel_status("critic bf16 step")
+    f, b = res["fp32"], res["bf16"]
+    assert b[0] == pytest.approx(f[0], rel=2e-2) and b[1] == pytest.approx(f[1], rel=2e-2)
+    assert_close(b[2], f[2], 2e-2, "grad norms")
+    # at this batch size the per-row rounding errors average out: whole arena within 2e-2 of its scale, <= 0.5 % outliers
+    assert_close(b[3], f[3], 2e-2, "gradient arena", max_outlier_frac=5e-3)
+
+
+def test_multiplier_step_under_bf16_precision():
+    """drpo_multiplier_step accepts DRPO_PREC_BF16 (it runs its dense layers as TF32 tensor-op GEMMs)."""
+    import drpo_b200
+    S, A, C, B = 12, 2, 2, 1000
+    w = O.make_ssac_weights(61, S, A, C)
+    solver = make_ssac(w, S, A, C, B); solver.precision = drpo_b200.PREC_BF16
+    g = torch.Generator().manual_seed(4)
+    obs = torch.randn(B, S, generator=g); eps = torch.randn(B, A, generator=g)
+    lm, _ = O.multiplier_update({k: v.clone() for k, v in w.items()}, obs, eps, O.SSACHyper(), C, O.AdamState(), 3e-4)
+    glm = solver.update_multiplier(to_dev(obs), eps=to_dev(eps))
+    assert_close(glm, lm, 2e-2, "multiplier loss")
