@@ -98,7 +98,9 @@ class ClockSampler:
                         self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.25)        # NVML queries take driver locks that stall kernel launches for milliseconds: keep them sparse
+            # every NVML query perturbs the run it observes (driver locks; a sample landing inside a 0.25 s timed region was
+            # measured to cost ~1 ms per rollout step): one sample early in the region, then one per second
+            self._stop.wait(float(os.environ.get("DRPO_BENCH_CLOCK_INTERVAL", "1.0")))
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -182,13 +184,15 @@ def run_ours(args):
     t_pre = time.perf_counter()                       # untimed pre-warm: bring the SM clocks up before the W warm-up steps
     while time.perf_counter() - t_pre < 0.5:
         step_device(); torch.cuda.synchronize()
+    total = torch.zeros((), dtype=torch.int64, device=device)
     for _ in range(args.warmup):
         view = step_device()
+        total += view.step_counts[-1]                  # every torch op of the timed loop runs once here: on a fresh box the first
+    total.zero_()                                      # launch of a torch kernel pages its module in from disk (tens of ms)
     barrier()
     # ---- device-resident timing: K steps between two events ---------------------------------------------------
     launches0 = lib.drpo_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    total = torch.zeros((), dtype=torch.int64, device=device)
     with ClockSampler(local) as clocks:
         barrier()
         ev0.record()
