@@ -499,6 +499,68 @@ def multiplier_update(w: W, obs: Tensor, eps: Tensor, hp: SSACHyper, C: int, ada
     return loss.detach(), aux
 
 
+# ----------------------------------------------------------------------------------------------
+# SSAC actor / alpha / safe-actor step (src/ssac.py:458-527)  -- SURVEY.md §8(f) "next" row 1
+# ----------------------------------------------------------------------------------------------
+
+def actor_losses(w: W, obs: Tensor, noise, hp: SSACHyper, log_alpha: Tensor, q_index: int, C: int,
+                 target_entropy: float):
+    """SSAC.actor_loss (src/ssac.py:458-505), DRPO mode (reachability, distributional_qc, mlp_multiplier,
+    autotune_alpha, use_log_alpha_loss=False).  noise = (eps_actor [B,A], eps_safe [B,A]): the two rsample
+    draws; q_index = the critic random.choice picked (src/ssac.py:41-43).  Returns the three losses
+    [actor, alpha, actor_safe] as autograd scalars."""
+    eps_a, eps_s = noise
+    a, x, mu, std = policy_act(w, "actor.", obs, eps_a)                         # distr.rsample()
+    log_prob = squashed_log_prob(mu, std, x)
+    actor_q = q_forward(w, "critic.", obs, a)[q_index]                          # critic.random_choice
+    alpha = log_alpha.exp()
+    uncstr = torch.mean(alpha.detach() * log_prob - actor_q)
+    m_a, s_a = qc_forward(w, "constraint_critic.", obs, a)
+    actor_qc = get_qc(m_a + hp.std_ratio * s_a, C)                              # uncertainty=True, src/ssac.py:85
+    with torch.no_grad():
+        a_eval, _, _, _ = policy_act(w, "actor_safe.", obs, None)
+        m_s, s_s = qc_forward(w, "constraint_critic.", obs, a_eval)
+        safe_qc = get_qc(m_s + hp.std_ratio * s_s, C)
+        lams = multiplier_forward(w, obs, safe_qc, hp.multiplier_ub)
+    cstr = torch.mean(torch.mul(lams, actor_qc))
+    a2, _, _, _ = policy_act(w, "actor_safe.", obs, eps_s)                      # distr_safe.rsample()
+    m_2, s_2 = qc_forward(w, "constraint_critic.", obs, a2)
+    actor_safe_loss = torch.mean(get_qc(m_2 + hp.std_ratio * s_2, C))
+    alpha_loss = -alpha * torch.mean(log_prob.detach() + target_entropy)
+    return [uncstr + cstr, alpha_loss, actor_safe_loss], dict(log_prob=log_prob.detach(), lams=lams, actor_qc=actor_qc.detach())
+
+
+def actor_update(w: W, obs: Tensor, noise, hp: SSACHyper, log_alpha: Tensor, q_index: int, C: int, target_entropy: float,
+                 adams: Dict[str, AdamState], lrs: Dict[str, float]):
+    """SSAC.update_actor_and_alpha (src/ssac.py:507-527): three losses, three Adam optimisers (actor and
+    actor_safe with coupled L2 1e-4 and grad-norm clip 5, log_alpha without either); in place on ``w`` and
+    ``log_alpha`` (a 0-dim tensor).  The three backward passes of the reference touch disjoint parameter
+    sets (actor / log_alpha / actor_safe; alpha and lams are detached in the actor loss), so one backward of
+    their sum yields the same gradients."""
+    names_a = [k for k in w if k.startswith("actor.")]
+    names_s = [k for k in w if k.startswith("actor_safe.")]
+    for k in names_a + names_s:
+        w[k].requires_grad_(True)
+        w[k].grad = None
+    la = log_alpha.detach().clone().requires_grad_(True)
+    losses, aux = actor_losses(w, obs, noise, hp, la, q_index, C, target_entropy)
+    (losses[0] + losses[1] + losses[2]).backward()
+    grads = {k: w[k].grad.detach().clone() for k in names_a + names_s}
+    g_alpha = la.grad.detach().clone()
+    for k in list(w):
+        w[k].requires_grad_(False)
+        w[k].grad = None
+    aux["grads_raw"] = {k: g.clone() for k, g in grads.items()}
+    aux["grad_alpha"] = g_alpha.clone()
+    aux["grad_norm_actor"] = clip_grad_norm([grads[k] for k in names_a], hp.grad_norm)
+    aux["grad_norm_safe"] = clip_grad_norm([grads[k] for k in names_s], hp.grad_norm)
+    with torch.no_grad():
+        adam_step({k: w[k] for k in names_a}, grads, adams["actor"], lrs["actor"], hp.weight_decay)
+        adam_step({"log_alpha": log_alpha}, {"log_alpha": g_alpha}, adams["alpha"], lrs["alpha"], 0.0)
+        adam_step({k: w[k] for k in names_s}, grads, adams["safe"], lrs["safe"], hp.weight_decay)
+    return [l.detach() for l in losses], aux
+
+
 def preprocess_batch(batch, reward_scale: float, alive_bonus: float, constraint_scale: float,
                      constraint_offset: float):
     """src/smbpo.py:261-270."""

@@ -420,6 +420,57 @@ def gen_multiplier():
     np.savez_compressed(os.path.join(GOLD, "multiplier.npz"), **out)
 
 
+def gen_actor():
+    """SSAC.update_actor_and_alpha (src/ssac.py:507-527): three consecutive updates of the reference with injected rsample
+    draws and critic choices; the oracle restatement runs alongside and must land on the same parameters."""
+    out = {}
+    for tag, S, A, C, B, seed, spec in [("point_robot", 11, 2, 1, 64, 601, O.env_point_robot()),
+                                        ("cartpole", 4, 1, 4, 48, 602, O.env_cartpole())]:
+        w = O.make_ssac_weights(seed, S, A, C)
+        solver = build_reference_ssac(w, S, A, C, B, spec)
+        if not isinstance(solver.target_entropy, (int, float)):       # Config() built by hand leaves the Optional(float) marker: the
+            solver.target_entropy = -A                                # config loader resolves it to None -> -dim(A) (src/ssac.py:229-230)
+        wo = {k: v.clone() for k, v in w.items()}
+        la = torch.tensor(float(solver.log_alpha.detach()))
+        adams = {k: O.AdamState() for k in ("actor", "alpha", "safe")}
+        hp = O.SSACHyper()
+        g = torch.Generator().manual_seed(seed + 1)
+        lr_a = [solver.actor_optimizer.param_groups[0]["lr"]]
+        for it in range(3):
+            obs = torch.randn(B, S, generator=g)
+            eps_a, eps_s = torch.randn(B, A, generator=g), torch.randn(B, A, generator=g)
+            q_index = int(torch.randint(2, (1,), generator=g))
+
+            def tape_up(tape):
+                tape.std_normal += [eps_a, eps_s]
+                tape.choice.append(q_index)
+                tape.randn_like += [None, None, None]
+            with NoiseTape() as tape:
+                tape_up(tape)
+                ref_losses = [l.detach().clone() for l in solver.actor_loss(obs, include_alpha=True)]
+            with NoiseTape() as tape:
+                tape_up(tape)
+                solver.update_actor_and_alpha(obs)
+            lrs = dict(actor=lr_a[-1], alpha=solver.actor_lr, safe=lr_a[-1])
+            losses, aux = O.actor_update(wo, obs, (eps_a, eps_s), hp, la, q_index, C, float(solver.target_entropy), adams, lrs)
+            lr_a.append(O.cosine_lr(lr_a[-1], it + 1, solver.actor_updates_num, solver.actor_lr_end, solver.actor_lr))
+            assert abs(lr_a[-1] - solver.actor_optimizer.param_groups[0]["lr"]) < 1e-12
+            assert abs(lr_a[-1] - solver.actor_safe_optimizer.param_groups[0]["lr"]) < 1e-12
+            sd = solver.state_dict()
+            err = max(maxrel(wo[k], sd[k]) for k in wo if k.startswith(("actor.", "actor_safe.")))
+            print(f"actor[{tag}] it{it}: losses ref {[round(float(l), 6) for l in ref_losses]} oracle {[round(float(l), 6) for l in losses]}; "
+                  f"params maxrel {err:.2e}; log_alpha ref {float(solver.log_alpha):.8f} oracle {float(la):.8f}; "
+                  f"gnorm {aux['grad_norm_actor']:.3f}/{aux['grad_norm_safe']:.4f}")
+            out.update(t2n({f"{tag}.it{it}.obs": obs, f"{tag}.it{it}.eps_actor": eps_a, f"{tag}.it{it}.eps_safe": eps_s,
+                            f"{tag}.it{it}.q_index": q_index, f"{tag}.it{it}.losses": torch.stack(ref_losses),
+                            f"{tag}.it{it}.log_alpha_after": float(solver.log_alpha)}))
+            out.update({f"{tag}.it{it}.after.{k}": v for k, v in _summ(sd, ("actor.", "actor_safe.")).items()})
+        out.update(t2n({f"{tag}.seed": seed, f"{tag}.wsum": O.weights_checksum(w), f"{tag}.lrs": lr_a,
+                        f"{tag}.alpha_lr": solver.actor_lr, f"{tag}.target_entropy": float(solver.target_entropy),
+                        f"{tag}.T_max": solver.actor_updates_num}))
+    np.savez_compressed(os.path.join(GOLD, "actor.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.import_reference()
     torch.set_num_threads(4)
@@ -430,4 +481,5 @@ if __name__ == "__main__":
     gen_rollout()
     gen_critic()
     gen_multiplier()
+    gen_actor()
     print("golden vectors written to", GOLD)

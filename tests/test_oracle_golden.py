@@ -121,3 +121,21 @@ def test_multiplier_update(golden, tag, S, A, C):
                                       float(g[f"{tag}.lrs"][it]))
         close(loss, g[f"{tag}.it{it}.loss"], rtol=1e-6)
         _check_after(w, g, f"{tag}.it{it}", keys)
+
+
+@pytest.mark.parametrize("tag,S,A,C", [("point_robot", 11, 2, 1), ("cartpole", 4, 1, 4)])
+def test_actor_update(golden, tag, S, A, C):
+    """Oracle restatement of SSAC.update_actor_and_alpha (src/ssac.py:458-527) vs three consecutive updates of the reference:
+    the three losses, the actor / safe-actor parameters and log_alpha."""
+    g = golden("actor")
+    w = O.make_ssac_weights(int(g[f"{tag}.seed"]), S, A, C)
+    la = torch.tensor(0.0)
+    adams = {k: O.AdamState() for k in ("actor", "alpha", "safe")}
+    keys = [k for k in w if k.startswith(("actor.", "actor_safe."))]
+    for it in range(3):
+        lrs = dict(actor=float(g[f"{tag}.lrs"][it]), alpha=float(g[f"{tag}.alpha_lr"]), safe=float(g[f"{tag}.lrs"][it]))
+        losses, _ = O.actor_update(w, T(g[f"{tag}.it{it}.obs"]), (T(g[f"{tag}.it{it}.eps_actor"]), T(g[f"{tag}.it{it}.eps_safe"])),
+                                   O.SSACHyper(), la, int(g[f"{tag}.it{it}.q_index"]), C, float(g[f"{tag}.target_entropy"]), adams, lrs)
+        close(torch.stack(losses), g[f"{tag}.it{it}.losses"], rtol=1e-6)
+        assert float(la) == pytest.approx(float(g[f"{tag}.it{it}.log_alpha_after"]), rel=1e-6)
+        _check_after(w, g, f"{tag}.it{it}", keys)
