@@ -117,6 +117,22 @@ class MultiplierArgs(C.Structure):
     ]
 
 
+class ActorArgs(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p), ("batch_size", C.c_int64), ("global_batch_size", C.c_int64),
+        ("state_dim", C.c_int32), ("action_dim", C.c_int32), ("con_dim", C.c_int32),
+        ("actor", Mlp3), ("actor_safe", Mlp3), ("q", C.POINTER(Mlp3)), ("qc", C.POINTER(Qc)), ("lam", C.POINTER(Mlp3)),
+        ("params_actor", C.c_void_p), ("grads_actor", C.c_void_p), ("m_actor", C.c_void_p), ("v_actor", C.c_void_p), ("n_actor", C.c_int64),
+        ("params_safe", C.c_void_p), ("grads_safe", C.c_void_p), ("m_safe", C.c_void_p), ("v_safe", C.c_void_p), ("n_safe", C.c_int64),
+        ("log_alpha", C.c_void_p), ("alpha_m", C.c_void_p), ("alpha_v", C.c_void_p),
+        ("eps_actor", C.c_void_p), ("eps_safe", C.c_void_p), ("seed", C.c_uint64), ("noise_step", C.c_uint32), ("row_id_offset", C.c_int64),
+        ("std_ratio", C.c_double), ("multiplier_ub", C.c_double), ("grad_norm", C.c_double), ("target_entropy", C.c_double),
+        ("adam_actor", Adam), ("adam_alpha", Adam), ("adam_safe", Adam),
+        ("phases", C.c_int32), ("losses", C.c_void_p), ("precision", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/drpo_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("drpo_last_error", C.c_char_p, []),
@@ -147,6 +163,8 @@ SYMBOLS = [
     ("drpo_debug_critic_dw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drpo_multiplier_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_multiplier_step", C.c_int, [C.POINTER(MultiplierArgs)]),
+    ("drpo_actor_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("drpo_actor_step", C.c_int, [C.POINTER(ActorArgs)]),
     ("drpo_qc_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32]),
     ("drpo_qc_forward", C.c_int, [C.POINTER(Qc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_float, C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

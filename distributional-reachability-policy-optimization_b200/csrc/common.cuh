@@ -112,7 +112,7 @@ __device__ __forceinline__ float philox_normal1(uint64_t seed, uint32_t row, uin
 // stream tags (one per distinct draw of the hot path)
 enum NoiseTag : uint32_t {
   TAG_ROLLOUT_POLICY = 1, TAG_ROLLOUT_MODEL = 2, TAG_CRITIC_ACTOR = 3, TAG_CRITIC_SAFE = 4, TAG_CRITIC_QC = 5,
-  TAG_MULT_ACTOR = 6, TAG_USER = 16
+  TAG_MULT_ACTOR = 6, TAG_ACTOR_ACTOR = 7, TAG_ACTOR_SAFE = 8, TAG_USER = 16
 };
 
 // device view of drpo_noise

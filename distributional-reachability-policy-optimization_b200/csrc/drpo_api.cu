@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "critic.cuh"
+#include "actor.cuh"
 #include "nets.cuh"
 #include "rollout.cuh"
 #include "umma_api.h"
@@ -346,6 +347,37 @@ int drpo_multiplier_step(const drpo_multiplier_args* a) {
                  "drpo_multiplier_step: unknown precision %d", a->precision);
   g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;          // both tensor modes: TF32 tensor-op GEMMs
   rc = multiplier_step_fp32(*a);
+  g_gemm_mode = 0;
+  return rc;
+}
+
+int64_t drpo_actor_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
+  return actor_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+}
+
+int drpo_actor_step(const drpo_actor_args* a) {
+  DRPO_CHECK_ARG(a, "drpo_actor_step: NULL args");
+  int rc;
+  if ((rc = check_mlp3(&a->actor, "drpo_actor_step(actor)"))) return rc;
+  if ((rc = check_mlp3(&a->actor_safe, "drpo_actor_step(actor_safe)"))) return rc;
+  if ((rc = check_mlp3(a->q, "drpo_actor_step(q)"))) return rc;
+  if ((rc = check_mlp3(a->lam, "drpo_actor_step(lam)"))) return rc;
+  if ((rc = check_qc(a->qc, "drpo_actor_step(qc)"))) return rc;
+  DRPO_CHECK_ARG(a->batch_size >= 1 && a->global_batch_size >= a->batch_size && a->obs, "drpo_actor_step: bad batch");
+  DRPO_CHECK_ARG(a->con_dim >= 1 && a->con_dim <= DRPO_MAX_CON, "drpo_actor_step: bad con_dim");
+  DRPO_CHECK_ARG(a->actor.l0.in_dim == a->state_dim && a->actor.l2.out_dim == 2 * a->action_dim && a->actor_safe.l0.in_dim == a->state_dim &&
+                     a->actor_safe.l2.out_dim == 2 * a->action_dim && a->q->l0.in_dim == a->state_dim + a->action_dim && a->q->l2.out_dim == 1 &&
+                     a->qc->trunk0.in_dim == a->state_dim + a->action_dim && a->qc->mean1.out_dim == a->con_dim &&
+                     a->lam->l0.in_dim == a->state_dim + 1 && a->lam->l2.out_dim == 1, "drpo_actor_step: network dims disagree");
+  DRPO_CHECK_ARG(a->actor.l0.out_dim == a->q->l0.out_dim && a->actor.l0.out_dim == a->qc->trunk0.out_dim && a->actor.l0.out_dim == a->lam->l0.out_dim &&
+                     a->actor.l0.out_dim <= 256, "drpo_actor_step: the nets must share one hidden width <= 256");
+  DRPO_CHECK_ARG(a->params_actor && a->grads_actor && a->m_actor && a->v_actor && a->params_safe && a->grads_safe && a->m_safe && a->v_safe &&
+                     a->log_alpha && a->alpha_m && a->alpha_v && a->losses, "drpo_actor_step: NULL arena");
+  DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_actor_step: bad phases");
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
+                 "drpo_actor_step: unknown precision %d", a->precision);
+  g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;
+  rc = actor_step_fp32(*a);
   g_gemm_mode = 0;
   return rc;
 }

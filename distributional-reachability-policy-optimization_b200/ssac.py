@@ -316,19 +316,20 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self.multiplier_optimizer = FusedAdam(self._mult_arena, self.multiplier_lr, weight_decay=1e-4)
         self.multiplier_lr_scheduler = CosineLR(self.multiplier_optimizer, self.lam_updates_num, self.multiplier_lr_end)
 
-        # actors / alpha: SURVEY §8f "next" row 1 — torch optimisers for now
-        self.actor_optimizer = optimizer_factory(self.actor.parameters(), lr=self.actor_lr, weight_decay=1e-4)
-        self.actor_lr_scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.actor_optimizer, T_max=max(self.actor_updates_num, 1), eta_min=self.actor_lr_end)
-        self.actor_safe_optimizer = optimizer_factory(self.actor_safe.parameters(), lr=self.actor_lr, weight_decay=1e-4)
-        self.actor_safe_lr_scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.actor_safe_optimizer, T_max=max(self.actor_updates_num, 1), eta_min=self.actor_lr_end)
+        # actors / alpha (SURVEY §8f "next" row 1): in-kernel Adam over flat arenas as well (src/ssac.py:210-228)
+        self.actor_optimizer = FusedAdam(self._actor_arena, self.actor_lr, weight_decay=1e-4)
+        self.actor_lr_scheduler = CosineLR(self.actor_optimizer, max(self.actor_updates_num, 1), self.actor_lr_end)
+        self.actor_safe_optimizer = FusedAdam(self._safe_arena, self.actor_lr, weight_decay=1e-4)
+        self.actor_safe_lr_scheduler = CosineLR(self.actor_safe_optimizer, max(self.actor_updates_num, 1), self.actor_lr_end)
         self.log_alpha = torch.tensor(math.log(self.init_alpha), device=device, requires_grad=True)
         if self.autotune_alpha:
-            self.alpha_optimizer = optimizer_factory([self.log_alpha], lr=self.actor_lr)
+            self.alpha_optimizer = FusedAdam(torch.zeros(1, device=device), self.actor_lr, weight_decay=0.0)
         if self.target_entropy is None:
             self.target_entropy = -action_dim
 
         self.register_buffer('total_updates', torch.zeros([], device=device))
         self._losses = torch.zeros(8, device=device)
+        self._actor_losses = torch.zeros(8, device=device)
         self._ws = _lib.Workspace()
         self.noise_seed = 0xD2B0
         self.precision = _lib.PREC_FP32
@@ -346,6 +347,8 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self._critic_arena = _flatten_into_arena(self._critic_params())
         self._target_arena = _flatten_into_arena(self._target_params())
         self._mult_arena = _flatten_into_arena(list(self.multiplier.parameters()))
+        self._actor_arena = _flatten_into_arena(list(self.actor.parameters()))
+        self._safe_arena = _flatten_into_arena(list(self.actor_safe.parameters()))
         # the two clip groups are contiguous (padded) ranges of the critic arena: [Q1 | Q2] then [Qc]
         offs, total = _arena_offsets(self._critic_params())
         self._n_q = offs[len(list(self.critic.parameters()))]
@@ -354,10 +357,12 @@ class SSAC(Configurable, BasePolicy, nn.Module):
 
     def _ensure_arenas(self):
         if not (_arena_ok(self._critic_arena, self._critic_params()) and _arena_ok(self._target_arena, self._target_params())
-                and _arena_ok(self._mult_arena, list(self.multiplier.parameters()))):
-            old = (self.critic_optimizer, self.multiplier_optimizer)
+                and _arena_ok(self._mult_arena, list(self.multiplier.parameters()))
+                and _arena_ok(self._actor_arena, list(self.actor.parameters()))
+                and _arena_ok(self._safe_arena, list(self.actor_safe.parameters()))):
+            old = (self.critic_optimizer, self.multiplier_optimizer, self.actor_optimizer, self.actor_safe_optimizer)
             self._build_arenas()
-            for opt, arena in zip(old, (self._critic_arena, self._mult_arena)):
+            for opt, arena in zip(old, (self._critic_arena, self._mult_arena, self._actor_arena, self._safe_arena)):
                 if opt.m.device != arena.device:
                     opt.m, opt.v, opt.grad = opt.m.to(arena.device), opt.v.to(arena.device), opt.grad.to(arena.device)
         if self._structs is None:
@@ -533,25 +538,62 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         losses.append(actor_safe_loss)
         return losses
 
-    def update_actor_and_alpha(self, obs):
-        """src/ssac.py:507-527."""
-        losses = self.actor_loss(obs, include_alpha=self.autotune_alpha)
-        optimizers = [self.actor_optimizer] + ([self.alpha_optimizer] if self.autotune_alpha else []) + [self.actor_safe_optimizer]
-        last = len(optimizers) - 1
-        for i, (loss, optimizer) in enumerate(zip(losses, optimizers)):
-            optimizer.zero_grad()
-            loss.backward(retain_graph=True)
-            if i == 0:
-                torch.nn.utils.clip_grad_norm_(self.actor.parameters(), max_norm=self.grad_norm)
-            if i == last:
-                torch.nn.utils.clip_grad_norm_(self.actor_safe.parameters(), max_norm=self.grad_norm)
-            optimizer.step()
-            if i == 0:
-                self.actor_lr_scheduler.step()
-            if i == last:
-                self.actor_safe_lr_scheduler.step()
-        for p in [*self.critic.parameters(), *self.constraint_critic.parameters()]:
-            p.grad = None                     # the torch graph left grads on the (kernel-owned) critic parameters
+    def update_actor_and_alpha(self, obs, noise=None, q_index=None, phases=None):
+        """SSAC.update_actor_and_alpha (src/ssac.py:507-527) through drpo_actor_step: performance actor, temperature and safe
+        actor in one call.  ``noise`` = (eps_actor [B,A], eps_safe [B,A]) injects the two rsample draws (parity), otherwise the
+        in-kernel Philox stream is used; ``q_index`` is the critic `random.choice` picks (src/ssac.py:41-43)."""
+        assert self.autotune_alpha, "drpo_actor_step implements the autotune_alpha configuration of the reference"
+        lib = _lib.load()
+        st = self._ensure_arenas()
+        dist = self._dist()
+        world = dist.get_world_size() if dist else 1
+        rank = dist.get_rank() if dist else 0
+        obs = obs.contiguous().float()
+        B = obs.shape[0]
+        if q_index is None:
+            q_index = random.choice(range(len(self.critic.qs)))          # same draw from the host RNG as random.choice(self.qs)
+        oa, os_, oal = self.actor_optimizer, self.actor_safe_optimizer, self.alpha_optimizer
+        for o in (oa, os_, oal):
+            o.step_count += 1
+        a = _lib.ActorArgs()
+        a.obs, a.batch_size = _lib.ptr(obs), B
+        a.global_batch_size = getattr(self, "_global_batch_override", None) or B * world
+        a.state_dim, a.action_dim, a.con_dim = self.state_dim, self.action_dim, self.con_dim
+        a.actor, a.actor_safe = st["actor"], st["actor_safe"]
+        a.q, a.qc, a.lam = C_pointer(st["q"][q_index]), C_pointer(st["qc"]), C_pointer(st["lam"])
+        a.params_actor, a.grads_actor, a.m_actor, a.v_actor = _lib.ptr(self._actor_arena), _lib.ptr(oa.grad), _lib.ptr(oa.m), _lib.ptr(oa.v)
+        a.params_safe, a.grads_safe, a.m_safe, a.v_safe = _lib.ptr(self._safe_arena), _lib.ptr(os_.grad), _lib.ptr(os_.m), _lib.ptr(os_.v)
+        a.n_actor, a.n_safe = self._actor_arena.numel(), self._safe_arena.numel()
+        a.log_alpha, a.alpha_m, a.alpha_v = _lib.ptr(self.log_alpha.data), _lib.ptr(oal.m), _lib.ptr(oal.v)
+        if noise is not None:
+            n0, n1 = [x.contiguous().float() for x in noise]
+            a.eps_actor, a.eps_safe = _lib.ptr(n0), _lib.ptr(n1)
+        a.seed, a.noise_step, a.row_id_offset = self.noise_seed, oa.step_count, rank * B
+        a.std_ratio, a.multiplier_ub = float(self.constraint_critic.std_ratio), float(self.multiplier.upper_bound)
+        a.grad_norm, a.target_entropy = self.grad_norm, float(self.target_entropy)
+        a.adam_actor, a.adam_alpha, a.adam_safe = oa.as_struct(), oal.as_struct(), os_.as_struct()
+        a.losses, a.precision = _lib.ptr(self._actor_losses), self.precision
+        ws = self._ws.get(lib.drpo_actor_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim), obs.device)
+        a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        if phases is not None:
+            a.phases = phases
+            _lib.check(lib.drpo_actor_step(a), "drpo_actor_step")
+            return self._actor_losses[:3].clone()
+        if dist is None:
+            a.phases = 3
+            _lib.check(lib.drpo_actor_step(a), "drpo_actor_step")
+        else:
+            a.phases = 1
+            _lib.check(lib.drpo_actor_step(a), "drpo_actor_step(forward/backward)")
+            dist.all_reduce(oa.grad); dist.all_reduce(os_.grad)
+            red = torch.cat([self._actor_losses[:3], self._actor_losses[5:6]])
+            dist.all_reduce(red)
+            self._actor_losses[:3] = red[:3]; self._actor_losses[5] = red[3]
+            a.phases = 2
+            _lib.check(lib.drpo_actor_step(a), "drpo_actor_step(optimizer)")
+        self.actor_lr_scheduler.step()
+        self.actor_safe_lr_scheduler.step()
+        return self._actor_losses[:3].clone()
 
 
 def C_pointer(struct):

@@ -299,6 +299,37 @@ int64_t drpo_multiplier_workspace_bytes(int64_t batch, int32_t state_dim, int32_
                                         int32_t hidden);
 int drpo_multiplier_step(const drpo_multiplier_args* args);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * SSAC.update_actor_and_alpha (src/ssac.py:458-527) in DRPO mode ("next" row 1): performance actor
+ * loss mean(alpha*log_prob - Q_k + lambda*Qc_ub) with Q_k = critic.random_choice (:41-43, index chosen by the caller),
+ * Qc_ub = max_c(mean + std_ratio*std) (:85, :588-600), lambda = multiplier(obs, safe Qc_ub) (no gradient); temperature
+ * loss -alpha*mean(log_prob + target_entropy); safe-actor loss mean(Qc_ub(obs, a_safe')).  Backward through the frozen
+ * critics to the actions, the squashed-Gaussian rsample and both policy nets; grad-norm clips; three Adam steps.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_actor_args {
+  const float* obs; int64_t batch_size; int64_t global_batch_size;
+  int32_t state_dim, action_dim, con_dim;
+  drpo_mlp3 actor; drpo_mlp3 actor_safe;   /* trainable: pointers into params_actor / params_safe */
+  const drpo_mlp3* q;                      /* the critic random.choice picked */
+  const drpo_qc* qc; const drpo_mlp3* lam; /* frozen */
+  float* params_actor; float* grads_actor; float* m_actor; float* v_actor; int64_t n_actor;
+  float* params_safe; float* grads_safe; float* m_safe; float* v_safe; int64_t n_safe;
+  float* log_alpha; float* alpha_m; float* alpha_v;    /* device scalars */
+  /* noise: injected eps_actor [B,A], eps_safe [B,A] (the two rsample draws) or Philox(seed, step) */
+  const float* eps_actor; const float* eps_safe; uint64_t seed; uint32_t noise_step; int64_t row_id_offset;
+  double std_ratio, multiplier_ub, grad_norm, target_entropy;
+  drpo_adam adam_actor, adam_alpha, adam_safe;
+  /* phases: bit0 = forward+backward (fills grads_actor, grads_safe, losses[0..2] and losses[5]), bit1 = clips + Adam.
+   * Multi-GPU callers all-reduce the two gradient arenas and losses[0..2], losses[5] between the phases. */
+  int32_t phases;
+  float* losses;   /* device [8]: actor loss, alpha loss, safe-actor loss, actor grad norm, -, d alpha_loss/d log_alpha, safe grad norm, - */
+  int32_t precision;                       /* DRPO_PREC_FP32, or DRPO_PREC_TF32 / DRPO_PREC_BF16 = TF32 tensor-op GEMMs */
+  void* workspace; int64_t workspace_bytes; void* stream;
+} drpo_actor_args;
+
+int64_t drpo_actor_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden);
+int drpo_actor_step(const drpo_actor_args* args);
+
 /* ConstraintCritic.forward (src/ssac.py:64-92): mode 0 -> mean; 1 -> mean + std_ratio*std (uncertainty=True);
  * 2 -> (mean, std, mean + clamp(eps,-2,2)*std) (sample=True).  out_mean/out_std/out_sample are [B,C]. */
 int64_t drpo_qc_workspace_bytes(int64_t batch, int32_t hidden);
