@@ -347,6 +347,30 @@ def bench_critic(args, device, world, rank, pk):
                         "algorithmic_flops_per_sample": flops_per_critic_sample(S, A, C)}}
     if world == 1 and not args.skip_cpu:
         res["cpu_baseline"] = cpu_critic_baseline(args.cpu_critic_batch)
+    # ---- the other two SSAC steps of update_solver, reported separately: actor/alpha/safe-actor and multiplier -----
+    obs = batch[0]
+    for name, fn in (("actor", lambda: solver.update_actor_and_alpha(obs)), ("multiplier", lambda: solver.update_multiplier(obs))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = lib.drpo_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(max(n // 2, 1)):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        k = max(n // 2, 1)
+        res[name] = {"metric": f"ssac_{name}_updates_per_s", "value": k / (float(ms2) * 1e-3), "unit": "updates/s", "global_batch": Bg,
+                     "ms_per_update": float(ms2) / k, "gpu_launches": int(lib.drpo_launch_count() - l0),
+                     "dtype": "f32" if cprec == "fp32" else "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer"}
+    if world == 1 and not args.skip_cpu:
+        res["actor"]["cpu_baseline"] = cpu_actor_baseline(args.cpu_critic_batch)
     return res
 
 
@@ -394,6 +418,28 @@ def cpu_critic_baseline(B):
     dt = (time.perf_counter() - t0) / reps
     return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads,
             "kind": "port", "sample": f"{reps} x oracle critic_update at B={B} (tracking dims), torch CPU fp32 autograd, {threads} threads"}
+
+
+def cpu_actor_baseline(B):
+    from oracle import drpo_oracle as O
+    from drpo_b200 import synthetic
+    _, S, A, C = synthetic.WORKLOADS[CRITIC_WORKLOAD]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    w = synthetic.make_ssac_weights(43567, S, A, C)
+    obs = synthetic.make_critic_batch(CRITIC_WORKLOAD, B, 49283)[0]
+    g = torch.Generator().manual_seed(3)
+    noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g))
+    la, hp = torch.tensor(0.0), O.SSACHyper(std_ratio=1.0)
+    adams = {k: O.AdamState() for k in ("actor", "alpha", "safe")}
+    lrs = dict(actor=8e-5, alpha=8e-5, safe=8e-5)
+    O.actor_update(w, obs, noise, hp, la, 0, C, -float(A), adams, lrs)
+    t0, reps = time.perf_counter(), 3
+    for _ in range(reps):
+        O.actor_update(w, obs, noise, hp, la, 0, C, -float(A), adams, lrs)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads,
+            "kind": "port", "sample": f"{reps} x oracle actor_update at B={B} (tracking dims), torch CPU fp32 autograd, {threads} threads"}
 
 
 def run_reference(args):

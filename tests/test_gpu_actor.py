@@ -67,3 +67,62 @@ def test_actor_update_vs_oracle(S, A, C, B, prec, tol):
             if k.startswith(("actor.", "actor_safe.")):
                 assert_close(sd[k], wo[k], 2e-5, f"param {k}", max_outlier_frac=2e-3)
         assert float(solver.log_alpha) == pytest.approx(float(la), rel=1e-5)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_rollout_and_update_end_to_end(prec):
+    """SMBPO.rollout_and_update (src/smbpo.py:281-291): model rollout into the virtual ring, then critic / actor / multiplier
+    updates on minibatches gathered on the device - every step through the C ABI, nothing in eager torch."""
+    import drpo_b200
+    from drpo_b200 import _lib, synthetic
+    lib = _lib.load()
+    cfg = drpo_b200.SMBPO.Config()
+    cfg.buffer_max, cfg.horizon, cfg.rollout_batch_size, cfg.solver_updates_per_step = 1 << 16, 5, 2000, 10
+    cfg.sac_cfg.batch_size = 512
+    alg = drpo_b200.SMBPO(cfg, drpo_b200.device_env("quadrotor"), device=dev())
+    env_name, S, A, C = synthetic.WORKLOADS["quadrotor"]
+    alg.model_ensemble.load_state_dict(synthetic.make_ensemble_weights(64578, S, A), strict=True)
+    alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
+    alg.solver.load_state_dict(synthetic.make_ssac_weights(219803, S, A, C), strict=False)
+    p = {"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16}[prec]
+    alg.rollout_precision = p; alg.solver.precision = p
+    init = synthetic.make_start_states("quadrotor", 4000, 4354).to(dev())
+    g = torch.Generator().manual_seed(1)
+    n = init.shape[0]
+    alg.replay_buffer.extend(states=init, actions=to_dev(torch.rand(n, A, generator=g) * 2 - 1), next_states=init + 0.01,
+                             rewards=to_dev(torch.randn(n, generator=g)), dones=to_dev(torch.rand(n, generator=g) < 0.05),
+                             violations=to_dev(torch.rand(n, generator=g) < 0.05), constraint_values=to_dev(torch.randn(n, C, generator=g) - 0.5))
+    before = {k: v.clone() for k, v in alg.solver.state_dict().items()}
+    l0 = lib.drpo_launch_count()
+    alg.rollout_and_update()
+    torch.cuda.synchronize()
+    _lib.check_kernel_status("rollout_and_update")
+    assert lib.drpo_launch_count() - l0 > 100
+    assert len(alg.virt_buffer) > 2000                    # several rollout steps were stored
+    after = alg.solver.state_dict()
+    for prefix in ("critic.", "constraint_critic.", "actor.", "actor_safe.", "multiplier."):
+        moved = max(float((after[k] - before[k]).abs().max()) for k in after if k.startswith(prefix))
+        assert moved > 0, prefix
+    assert all(torch.isfinite(v).all() for v in after.values() if v.is_floating_point())
+    assert float(alg.solver.log_alpha) != 0.0
+
+
+def test_actor_row_sharding_matches_full_batch():
+    """Phase 1 on two row shards (global normaliser) sums to the full-batch gradients and losses: what the data-parallel
+    all-reduce between the two phases of drpo_actor_step relies on."""
+    S, A, C, B = 12, 2, 2, 1000
+    w = O.make_ssac_weights(5, S, A, C)
+    g = torch.Generator().manual_seed(9)
+    obs = torch.randn(B, S, generator=g)
+    noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g))
+    full = make_ssac(w, S, A, C, B)
+    lf = full.update_actor_and_alpha(to_dev(obs), noise=tuple(to_dev(n) for n in noise), q_index=0, phases=1)
+    ga, gs, galpha = full.actor_optimizer.grad.clone(), full.actor_safe_optimizer.grad.clone(), full._actor_losses[5].clone()
+    ta, ts, tl, tal = torch.zeros_like(ga), torch.zeros_like(gs), torch.zeros(3, device=dev()), torch.zeros((), device=dev())
+    for lo, hi in ((0, 300), (300, 1000)):
+        part = make_ssac(w, S, A, C, hi - lo)
+        part._global_batch_override = B
+        lp = part.update_actor_and_alpha(to_dev(obs[lo:hi]), noise=tuple(to_dev(n[lo:hi]) for n in noise), q_index=0, phases=1)
+        ta += part.actor_optimizer.grad; ts += part.actor_safe_optimizer.grad; tl += lp; tal += part._actor_losses[5]
+    assert_close(ta, ga, 5e-5, "actor gradient"); assert_close(ts, gs, 5e-5, "safe-actor gradient")
+    assert_close(tl, lf, 2e-5, "losses"); assert_close(tal, galpha, 2e-5, "alpha gradient")
