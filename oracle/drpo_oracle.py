@@ -225,6 +225,64 @@ def ensemble_elite_samples(w: W, states: Tensor, actions: Tensor, elites: List[i
     return samples[:, :, :-1], samples[:, :, -1]
 
 
+ENSEMBLE_TRAINABLE = ("trunk.", "diff_head.", "log_var_head.", "min_log_var", "max_log_var")
+
+
+def ensemble_mse_loss(w: W, states: Tensor, actions: Tensor, targets: Tensor) -> Tensor:
+    """BatchedGaussianEnsemble._mse_loss (src/dynamics.py:236-253): per-member Gaussian NLL [E]; inputs are [E,B,*]."""
+    means, log_vars = ensemble_forward_all(w, states, actions)
+    inv_vars = torch.exp(-log_vars)
+    squared_errors = torch.mean((targets - means) ** 2 * inv_vars, dim=(-2, -1))
+    log_dets = torch.mean(log_vars, dim=(-2, -1))
+    return squared_errors + log_dets
+
+
+def ensemble_compute_loss(w: W, states: Tensor, actions: Tensor, targets: Tensor, log_var_bound_weight: float = 0.01) -> Tensor:
+    """compute_loss (src/dynamics.py:143-153): rows are dealt to the members in contiguous blocks (_rebatch :136-141), a remainder
+    that does not divide by the ensemble size is dropped."""
+    E = w["trunk.0.weight"].shape[0]
+    n = targets.shape[0] - targets.shape[0] % E
+    rb = lambda x: x[:n].reshape(E, n // E, *x.shape[1:])
+    return torch.sum(ensemble_mse_loss(w, rb(states), rb(actions), rb(targets))) + \
+        log_var_bound_weight * (w["max_log_var"].sum() - w["min_log_var"].sum())
+
+
+def ensemble_train_step(w: W, states: Tensor, actions: Tensor, targets: Tensor, adam: AdamState, lr: float = 1e-3,
+                        weight_decay: float = 1e-4):
+    """One iteration of BatchedGaussianEnsemble.fit's loop (src/dynamics.py:164-170): compute_loss, backward, Adam (coupled L2
+    1e-4 on every trainable tensor incl. the log-var bounds, :93-101).  In place on ``w``."""
+    names = [k for k in w if k.startswith(ENSEMBLE_TRAINABLE)]
+    for k in names:
+        w[k].requires_grad_(True)
+        w[k].grad = None
+    loss = ensemble_compute_loss(w, states, actions, targets)
+    loss.backward()
+    grads = {k: w[k].grad.detach().clone() for k in names}
+    for k in names:
+        w[k].requires_grad_(False)
+        w[k].grad = None
+    with torch.no_grad():
+        adam_step({k: w[k] for k in names}, {k: g.clone() for k, g in grads.items()}, adam, lr, weight_decay)
+    return loss.detach(), dict(grads_raw=grads)
+
+
+def normalizer_fit(w: W, states: Tensor):
+    """Normalizer.fit (src/normalization.py:14-21): unbiased std, std < 1e-6 -> 1."""
+    w["state_normalizer.mean"] = states.mean(dim=0)
+    std = states.std(dim=0)
+    std[std < 1e-6] = 1.0
+    w["state_normalizer.std"] = std
+
+
+def ensemble_holdout_ranking(w: W, states: Tensor, actions: Tensor, targets: Tensor, num_elites: int = 5):
+    """End of fit (src/dynamics.py:172-186): every member scores the same holdout rows; the best ``num_elites`` become the elites."""
+    E = w["trunk.0.weight"].shape[0]
+    rep = lambda x: x.unsqueeze(0).repeat(E, *([1] * x.dim()))
+    with torch.no_grad():
+        losses = ensemble_mse_loss(w, rep(states), rep(actions), rep(targets))
+    return torch.argsort(losses)[:num_elites].tolist(), losses
+
+
 LOG_STD_BOUNDS = (-6.0, 4.0)          # src/policy.py:85
 
 

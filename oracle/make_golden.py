@@ -471,6 +471,49 @@ def gen_actor():
     np.savez_compressed(os.path.join(GOLD, "actor.npz"), **out)
 
 
+def gen_ensemble_fit():
+    """The training loop of BatchedGaussianEnsemble.fit (src/dynamics.py:155-189) with its three torch.randint draws replaced by
+    fixed index tensors: normaliser fit, three Adam steps on compute_loss, holdout ranking."""
+    out = {}
+    for tag, S, A, seed in [("point_robot", 11, 2, 701), ("quadrotor", 12, 2, 703)]:
+        w = O.make_ensemble_weights(seed, S, A)
+        ens = build_reference_ensemble(w, S, A)
+        E, Bm = ens.ensemble_size, 32
+        g = torch.Generator().manual_seed(seed + 1)
+        n = 600
+        states = torch.randn(n, S, generator=g) * 2 + 0.5
+        actions = torch.rand(n, A, generator=g) * 2 - 1
+        next_states = states + 0.05 * torch.randn(n, S, generator=g)
+        rewards = torch.randn(n, generator=g)
+        targets = torch.cat([next_states, rewards.unsqueeze(1)], dim=1)
+        ens.state_normalizer.fit(states)
+        wo = {k: v.clone() for k, v in w.items()}
+        O.normalizer_fit(wo, states)
+        adam = O.AdamState()
+        idxs = [torch.randint(n, [E * Bm + (3 if it == 1 else 0)], generator=g) for it in range(3)]     # one batch with a remainder
+        losses = []
+        for it, idx in enumerate(idxs):
+            loss = ens.compute_loss(states[idx], actions[idx], targets[idx])
+            ens.optimizer.zero_grad(); loss.backward(); ens.optimizer.step()
+            lo, _ = O.ensemble_train_step(wo, states[idx], actions[idx], targets[idx], adam)
+            sd = ens.state_dict()
+            err = max(maxrel(wo[k], sd[k]) for k in wo)
+            print(f"ensemble_fit[{tag}] it{it}: loss ref {float(loss):.6f} oracle {float(lo):.6f}; params maxrel {err:.2e}")
+            losses.append(float(loss))
+            out.update({f"{tag}.it{it}.after.{k}": v for k, v in _summ(sd, ("trunk.", "diff_head.", "log_var_head.", "min_log_var", "max_log_var")).items()})
+        hold = torch.randint(n, [ens.holdout_size], generator=g)
+        hi = hold.repeat(E, 1)
+        ref_h = ens._mse_loss(states[hi], actions[hi], targets[hi], enable_grad=False)
+        elites, oh = O.ensemble_holdout_ranking(wo, states[hold], actions[hold], targets[hold], ens.num_elites)
+        print(f"ensemble_fit[{tag}] holdout maxrel {maxrel(oh, ref_h):.2e} elites ref {torch.argsort(ref_h)[:ens.num_elites].tolist()} oracle {elites}")
+        out.update(t2n({f"{tag}.seed": seed, f"{tag}.states": states, f"{tag}.actions": actions, f"{tag}.targets": targets,
+                        f"{tag}.idx0": idxs[0], f"{tag}.idx1": idxs[1], f"{tag}.idx2": idxs[2], f"{tag}.losses": torch.tensor(losses),
+                        f"{tag}.norm_mean": ens.state_normalizer.mean, f"{tag}.norm_std": ens.state_normalizer.std,
+                        f"{tag}.holdout_idx": hold, f"{tag}.holdout_losses": ref_h,
+                        f"{tag}.elites": torch.tensor(torch.argsort(ref_h)[:ens.num_elites].tolist())}))
+    np.savez_compressed(os.path.join(GOLD, "ensemble_fit.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.import_reference()
     torch.set_num_threads(4)
@@ -482,4 +525,5 @@ if __name__ == "__main__":
     gen_critic()
     gen_multiplier()
     gen_actor()
+    gen_ensemble_fit()
     print("golden vectors written to", GOLD)

@@ -139,3 +139,25 @@ def test_actor_update(golden, tag, S, A, C):
         close(torch.stack(losses), g[f"{tag}.it{it}.losses"], rtol=1e-6)
         assert float(la) == pytest.approx(float(g[f"{tag}.it{it}.log_alpha_after"]), rel=1e-6)
         _check_after(w, g, f"{tag}.it{it}", keys)
+
+
+@pytest.mark.parametrize("tag,S,A", [("point_robot", 11, 2), ("quadrotor", 12, 2)])
+def test_ensemble_fit(golden, tag, S, A):
+    """Oracle restatement of BatchedGaussianEnsemble.fit's loop (src/dynamics.py:143-189, src/normalization.py:14-21): normaliser
+    fit, three Adam steps on compute_loss (one batch with a remainder), holdout losses and elite ranking vs the reference."""
+    g = golden("ensemble_fit")
+    w = O.make_ensemble_weights(int(g[f"{tag}.seed"]), S, A)
+    states, actions, targets = T(g[f"{tag}.states"]), T(g[f"{tag}.actions"]), T(g[f"{tag}.targets"])
+    O.normalizer_fit(w, states)
+    close(w["state_normalizer.mean"], g[f"{tag}.norm_mean"], rtol=1e-6); close(w["state_normalizer.std"], g[f"{tag}.norm_std"], rtol=1e-6)
+    adam = O.AdamState()
+    keys = [k for k in w if k.startswith(O.ENSEMBLE_TRAINABLE)]
+    for it in range(3):
+        idx = torch.as_tensor(g[f"{tag}.idx{it}"])
+        loss, _ = O.ensemble_train_step(w, states[idx], actions[idx], targets[idx], adam)
+        close(loss, g[f"{tag}.losses"][it], rtol=1e-6)
+        _check_after(w, g, f"{tag}.it{it}", keys)
+    hold = torch.as_tensor(g[f"{tag}.holdout_idx"])
+    elites, losses = O.ensemble_holdout_ranking(w, states[hold], actions[hold], targets[hold])
+    close(losses, g[f"{tag}.holdout_losses"], rtol=1e-5)
+    assert elites == [int(x) for x in g[f"{tag}.elites"]]
