@@ -133,6 +133,16 @@ class ActorArgs(C.Structure):
     ]
 
 
+class EnsembleTrainArgs(C.Structure):
+    _fields_ = [
+        ("ens", Ensemble),
+        ("params", C.c_void_p), ("grads", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("n_params", C.c_int64),
+        ("states", C.c_void_p), ("actions", C.c_void_p), ("targets", C.c_void_p), ("n_rows", C.c_int64), ("shared_rows", C.c_int32),
+        ("log_var_bound_weight", C.c_double), ("adam", Adam), ("phases", C.c_int32), ("losses", C.c_void_p), ("precision", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/drpo_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("drpo_last_error", C.c_char_p, []),
@@ -163,6 +173,8 @@ SYMBOLS = [
     ("drpo_debug_critic_dw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drpo_multiplier_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_multiplier_step", C.c_int, [C.POINTER(MultiplierArgs)]),
+    ("drpo_ensemble_train_workspace_bytes", C.c_int64, [C.POINTER(Ensemble), C.c_int64]),
+    ("drpo_ensemble_train_step", C.c_int, [C.POINTER(EnsembleTrainArgs)]),
     ("drpo_actor_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_actor_step", C.c_int, [C.POINTER(ActorArgs)]),
     ("drpo_qc_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32]),

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "critic.cuh"
 #include "actor.cuh"
+#include "ensemble_train.cuh"
 #include "nets.cuh"
 #include "rollout.cuh"
 #include "umma_api.h"
@@ -378,6 +379,33 @@ int drpo_actor_step(const drpo_actor_args* a) {
                  "drpo_actor_step: unknown precision %d", a->precision);
   g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;
   rc = actor_step_fp32(*a);
+  g_gemm_mode = 0;
+  return rc;
+}
+
+int64_t drpo_ensemble_train_workspace_bytes(const drpo_ensemble* ens, int64_t rows_per_member) {
+  if (!ens) return -1;
+  return ens_train_ws_bytes(rows_per_member, ens->state_dim, ens->action_dim, ens->hidden, ens->ensemble_size);
+}
+
+int drpo_ensemble_train_step(const drpo_ensemble_train_args* a) {
+  DRPO_CHECK_ARG(a, "drpo_ensemble_train_step: NULL args");
+  int rc;
+  if ((rc = check_ens(&a->ens))) return rc;
+  DRPO_CHECK_ARG(a->states && a->actions && a->targets && a->n_rows >= 1 && a->losses, "drpo_ensemble_train_step: bad batch");
+  DRPO_CHECK_ARG((a->phases & ~7) == 0 && a->phases != 0 && !((a->phases & 4) && (a->phases & 3)), "drpo_ensemble_train_step: bad phases");
+  DRPO_CHECK_ARG((a->phases & 4) || (a->params && a->grads && a->adam_m && a->adam_v && a->n_params > 0), "drpo_ensemble_train_step: NULL arena");
+  DRPO_CHECK_ARG(a->ens.hidden <= 256 && a->ens.state_dim + a->ens.action_dim + 1 <= 320, "drpo_ensemble_train_step: dims too large for the split-K scratch");
+  if (a->phases & 3) {
+    const float* lo = a->params; const float* hi = a->params + a->n_params;
+    const float* ptrs[] = {a->ens.trunk0_w, a->ens.trunk0_b, a->ens.trunk1_w, a->ens.trunk1_b, a->ens.diff0_w, a->ens.diff0_b, a->ens.diff1_w, a->ens.diff1_b,
+                           a->ens.lvar0_w, a->ens.lvar0_b, a->ens.lvar1_w, a->ens.lvar1_b, a->ens.min_log_var, a->ens.max_log_var};
+    for (const float* q : ptrs) DRPO_CHECK_ARG(q >= lo && q < hi, "drpo_ensemble_train_step: a trainable tensor lies outside the parameter arena");
+  }
+  DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
+                 "drpo_ensemble_train_step: unknown precision %d", a->precision);
+  g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;
+  rc = ensemble_train_step(*a);
   g_gemm_mode = 0;
   return rc;
 }

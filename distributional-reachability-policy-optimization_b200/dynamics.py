@@ -89,13 +89,39 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         self.trunk = _batched_mlp(E, [D, H, H], True, device)
         self.diff_head = _batched_mlp(E, [H, H, O], False, device)
         self.log_var_head = _batched_mlp(E, [H, H, O], False, device)
-        self.optimizer = optimizer_factory(
-            [*self.trunk.parameters(), *self.diff_head.parameters(), *self.log_var_head.parameters(),
-             self.min_log_var, self.max_log_var], lr=self.learning_rate, weight_decay=1e-4)
+        # trainable tensors in one flat arena (views keep the reference's state_dict names / shapes): the in-kernel Adam of
+        # drpo_ensemble_train_step streams over it (src/dynamics.py:93-101: lr 1e-3, coupled L2 1e-4 on every tensor)
+        from .ssac import FusedAdam, _flatten_into_arena
+        self._arena = _flatten_into_arena(self._trainable())
+        self.optimizer = FusedAdam(self._arena, self.learning_rate, weight_decay=1e-4)
+        self._fit_losses = torch.zeros(1 + E, device=device)
+        self.precision = _lib.PREC_FP32
         self.elite_inds = torch.randint(high=E, size=(self.num_elites,)).tolist()      # src/dynamics.py:105-106
         self._ws = _lib.Workspace()
         self.noise_seed = 0x5EEDD12A
         self._noise_step = 0
+
+    def _trainable(self):
+        return [*self.trunk.parameters(), *self.diff_head.parameters(), *self.log_var_head.parameters(), self.min_log_var, self.max_log_var]
+
+    def _ensure_arena(self):
+        from .ssac import _arena_ok, _flatten_into_arena
+        if not _arena_ok(self._arena, self._trainable()):
+            self._arena = _flatten_into_arena(self._trainable())
+            opt = self.optimizer
+            if opt.m.device != self._arena.device:
+                opt.m, opt.v, opt.grad = opt.m.to(self._arena.device), opt.v.to(self._arena.device), opt.grad.to(self._arena.device)
+            self._fit_losses = self._fit_losses.to(self._arena.device)
+
+    def arena_views(self, arena):
+        """name -> view of ``arena`` (parameter / gradient / Adam arena) in the order of ``_trainable``."""
+        from .ssac import _arena_offsets
+        named = [(f"trunk.{k}", p) for k, p in self.trunk.named_parameters()] + \
+                [(f"diff_head.{k}", p) for k, p in self.diff_head.named_parameters()] + \
+                [(f"log_var_head.{k}", p) for k, p in self.log_var_head.named_parameters()] + \
+                [("min_log_var", self.min_log_var), ("max_log_var", self.max_log_var)]
+        offs, _ = _arena_offsets([p for _, p in named])
+        return {k: arena[o:o + p.numel()].view(p.shape) for (k, p), o in zip(named, offs)}
 
     # ------------------------------------------------------------------------------------------------------
     @property
@@ -199,23 +225,58 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         s, a, t = [x[:n].reshape(E, n // E, *x.shape[1:]) for x in (states, actions, targets)]
         return torch.sum(self._mse_loss(s, a, t)) + self.log_var_bound_weight * (self.max_log_var.sum() - self.min_log_var.sum())
 
+    def train_step(self, states, actions, targets, phases=3):
+        """One iteration of fit's loop (src/dynamics.py:164-170) through drpo_ensemble_train_step: compute_loss on the batch
+        (members take contiguous blocks, a remainder is dropped), backward, Adam.  Returns compute_loss as a device scalar."""
+        lib = _lib.load()
+        self._ensure_arena()
+        f = lambda t: t.contiguous().float()
+        states, actions, targets = f(states), f(actions), f(targets)
+        n = targets.shape[0]
+        opt = self.optimizer
+        if phases & 2:
+            opt.step_count += 1
+        a = _lib.EnsembleTrainArgs()
+        a.ens = self.as_struct()
+        a.params, a.grads, a.adam_m, a.adam_v, a.n_params = _lib.ptr(self._arena), _lib.ptr(opt.grad), _lib.ptr(opt.m), _lib.ptr(opt.v), self._arena.numel()
+        a.states, a.actions, a.targets, a.n_rows, a.shared_rows = _lib.ptr(states), _lib.ptr(actions), _lib.ptr(targets), n, 0
+        a.log_var_bound_weight, a.adam, a.phases = float(self.log_var_bound_weight), opt.as_struct(), phases
+        a.losses, a.precision = _lib.ptr(self._fit_losses), self.precision
+        ws = self._ws.get(lib.drpo_ensemble_train_workspace_bytes(a.ens, max(n // self.ensemble_size, 1)), states.device)
+        a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        _lib.check(lib.drpo_ensemble_train_step(a), "drpo_ensemble_train_step")
+        return self._fit_losses[0]
+
+    def holdout_losses(self, states, actions, targets):
+        """Every member's NLL on the SAME rows (the holdout scoring at the end of fit, src/dynamics.py:172-181)."""
+        lib = _lib.load()
+        f = lambda t: t.contiguous().float()
+        states, actions, targets = f(states), f(actions), f(targets)
+        a = _lib.EnsembleTrainArgs()
+        a.ens = self.as_struct()
+        a.states, a.actions, a.targets, a.n_rows, a.shared_rows = _lib.ptr(states), _lib.ptr(actions), _lib.ptr(targets), targets.shape[0], 1
+        a.log_var_bound_weight, a.phases = float(self.log_var_bound_weight), 4
+        a.losses, a.precision = _lib.ptr(self._fit_losses), self.precision
+        ws = self._ws.get(lib.drpo_ensemble_train_workspace_bytes(a.ens, targets.shape[0]), states.device)
+        a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        _lib.check(lib.drpo_ensemble_train_step(a), "drpo_ensemble_train_step(holdout)")
+        return self._fit_losses[1:1 + self.ensemble_size].clone()
+
     def fit(self, buffer, steps=None, epochs=None, progress_bar=False, **kwargs):
-        """src/dynamics.py:155-196 (steps form).  Not on the CUDA hot path yet: eager torch."""
+        """src/dynamics.py:155-189 (steps form): normaliser fit, ``steps`` Adam iterations on random minibatches, holdout ranking
+        of the members -> ``_elite_inds``.  The index draws stay torch.randint on the device (as in the reference); every
+        iteration is one drpo_ensemble_train_step; the losses are read back once at the end."""
         if steps is None:
             raise NotImplementedError("only fit(steps=...) is provided")
         n = len(buffer)
         states, actions, next_states, rewards = buffer.get()[:4]
         self.state_normalizer.fit(states)
         targets = torch.cat([next_states, rewards.unsqueeze(1)], dim=1)
-        losses = []
-        for _ in range(steps):
+        losses = torch.empty(steps, device=states.device)
+        for i in range(steps):
             idx = torch.randint(n, [self.total_batch_size], device=states.device)
-            loss = self.compute_loss(states[idx], actions[idx], targets[idx])
-            losses.append(loss.item())
-            self.optimizer.zero_grad()
-            loss.backward()
-            self.optimizer.step()
-        hold = torch.randint(n, [self.holdout_size], device=states.device).repeat(self.ensemble_size, 1)
-        mse = self._mse_loss(states[hold], actions[hold], targets[hold], enable_grad=False)
+            losses[i] = self.train_step(states[idx], actions[idx], targets[idx])
+        hold = torch.randint(n, [self.holdout_size], device=states.device)
+        mse = self.holdout_losses(states[hold], actions[hold], targets[hold])
         self._elite_inds = torch.argsort(mse)[:self.num_elites].tolist()
-        return losses
+        return losses.tolist()

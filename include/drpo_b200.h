@@ -330,6 +330,30 @@ typedef struct drpo_actor_args {
 int64_t drpo_actor_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden);
 int drpo_actor_step(const drpo_actor_args* args);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * BatchedGaussianEnsemble.fit's training iteration (src/dynamics.py:143-170; SURVEY.md section 8f "next" row 2): compute_loss =
+ * sum over members of the Gaussian NLL on the member's contiguous block of the batch (_rebatch :136-141, a remainder is
+ * dropped) + log_var_bound_weight * (sum max_log_var - sum min_log_var); backward; Adam with coupled L2 on every trainable
+ * tensor.  Trainable parameters (trunk, both heads, the two log-var bounds) live in ONE flat fp32 arena `params`; `ens`
+ * points into it.  phases: bit0 = forward + backward (grads, losses), bit1 = Adam, bit2 = forward only (per-member NLL; with
+ * shared_rows != 0 every member scores the same n_rows rows: the holdout ranking at the end of fit, :172-186).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct drpo_ensemble_train_args {
+  drpo_ensemble ens;
+  float* params; float* grads; float* adam_m; float* adam_v; int64_t n_params;
+  const float* states; const float* actions; const float* targets;   /* [n_rows,S], [n_rows,A], [n_rows,S+1] = [next_state, reward] */
+  int64_t n_rows; int32_t shared_rows;
+  double log_var_bound_weight;
+  drpo_adam adam;
+  int32_t phases;
+  float* losses;               /* device [1 + ensemble_size]: compute_loss, then every member's NLL */
+  int32_t precision;           /* DRPO_PREC_FP32, or DRPO_PREC_TF32 / DRPO_PREC_BF16 = TF32 tensor-op GEMMs */
+  void* workspace; int64_t workspace_bytes; void* stream;
+} drpo_ensemble_train_args;
+
+int64_t drpo_ensemble_train_workspace_bytes(const drpo_ensemble* ens, int64_t rows_per_member);
+int drpo_ensemble_train_step(const drpo_ensemble_train_args* args);
+
 /* ConstraintCritic.forward (src/ssac.py:64-92): mode 0 -> mean; 1 -> mean + std_ratio*std (uncertainty=True);
  * 2 -> (mean, std, mean + clamp(eps,-2,2)*std) (sample=True).  out_mean/out_std/out_sample are [B,C]. */
 int64_t drpo_qc_workspace_bytes(int64_t batch, int32_t hidden);
