@@ -24,12 +24,18 @@ static __global__ void silu_bwd_kernel(float* __restrict__ dh, const float* __re
 struct EnsNllArgs {
   const float *dd, *lr, *s, *t, *min_lv, *max_lv;
   float *g_dd, *g_lr, *g_hi, *g_lo;         // [B,O] each (g_hi / g_lo: per-row contributions to d loss / d max_log_var, min_log_var)
-  double* partials;                          // [grid] loss partial sums
-  int64_t B; int S; float inv_n;             // inv_n = 1 / (B * (S+1))
+  double* partials;                          // [gridDim.y members][gridDim.x] loss partial sums
+  int64_t B; int S; float inv_n;             // rows per member; inv_n = 1 / (B * (S+1))
+  int64_t row_stride;                        // rows between consecutive members' blocks of s / t (0: all members score the same rows)
 };
 static __global__ void __launch_bounds__(256) ens_nll_kernel(EnsNllArgs a) {
   const int O = a.S + 1;
   double acc = 0.0;
+  // member blockIdx.y: its head outputs / gradients are the blockIdx.y-th [B,O] block, its rows start at blockIdx.y*row_stride
+  const int64_t mo = (int64_t)blockIdx.y * a.B * O;
+  a.dd += mo; a.lr += mo;
+  if (a.g_dd) { a.g_dd += mo; a.g_lr += mo; a.g_hi += mo; a.g_lo += mo; }
+  a.s += (int64_t)blockIdx.y * a.row_stride * a.S; a.t += (int64_t)blockIdx.y * a.row_stride * O;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.B * O; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / O; const int c = (int)(i - r * O);
     const float mean = __fadd_rn(a.dd[i], c < a.S ? a.s[r * a.S + c] : 0.f);
@@ -55,7 +61,7 @@ static __global__ void __launch_bounds__(256) ens_nll_kernel(EnsNllArgs a) {
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < 8; ++w) t += sh[w];
-    a.partials[blockIdx.x] = t;
+    a.partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
 }
 // column sums of g_hi / g_lo over the member's rows, accumulated into the bound gradients (one block per output column;
@@ -102,7 +108,7 @@ constexpr int ENS_LOSS_BLOCKS = 64;
 
 static inline int64_t ens_train_ws_bytes(int64_t rows_per_member, int S, int A, int H, int E) {
   const int64_t B = rows_per_member, D = S + A, O = S + 1;
-  int64_t f = B * D + 10 * B * H + 6 * B * O + 3 * B * H + PARTIAL_FLOATS + 64;
+  int64_t f = (int64_t)E * (B * D + 10 * B * H + 6 * B * O + 3 * B * H) + PARTIAL_FLOATS + 64;      // [E][B][*] scratch of the batched path
   return f * 4 + (int64_t)E * ENS_LOSS_BLOCKS * 8 + 64 * 256 + LT_WORKSPACE_BYTES;
 }
 
@@ -128,7 +134,71 @@ static inline int ensemble_train_step(const drpo_ensemble_train_args& a) {
   auto gp = [&](const float* p) { return a.grads + (p - a.params); };
   const unsigned gH = grid_for(Bm * H);
 
-  if (a.phases & 5) {
+  // ---- all members in one launch per layer (fp32 FFMA kernel, batched over blockIdx.z): the per-member loop below needs ~35
+  //      small launches per member and is launch-bound at the reference's 256 rows per member ------------------------------
+  // (used in the tensor mode as well: at <= 512 rows per member the layers are too small for the tensor-op GEMMs to pay)
+  if ((a.phases & 5) && Bm <= 512) {
+    const int saved_mode = g_gemm_mode;
+    g_gemm_mode = 0;
+    struct Restore { int v; ~Restore() { g_gemm_mode = v; } } restore{saved_mode};
+    Arena br(a.workspace, a.workspace_bytes);
+    const int64_t R = (int64_t)E * Bm;                                  // rows over all members
+    float* X0 = br.take<float>(R * D);
+    float *Z0 = br.take<float>(R * H), *H0 = br.take<float>(R * H), *Z1 = br.take<float>(R * H), *H1 = br.take<float>(R * H);
+    float *ZD = br.take<float>(R * H), *HD = br.take<float>(R * H), *ZL = br.take<float>(R * H), *HL = br.take<float>(R * H);
+    float *DD = br.take<float>(R * O), *LR = br.take<float>(R * O);
+    float *GDD = br.take<float>(R * O), *GLR = br.take<float>(R * O), *GHI = br.take<float>(R * O), *GLO = br.take<float>(R * O);
+    float *DA = br.take<float>(R * H), *DB = br.take<float>(R * H), *DH1 = br.take<float>(R * H);
+    float* bcoef = br.take<float>(4);
+    double* bloss = br.take<double>((int64_t)E * ENS_LOSS_BLOCKS);
+    if (!br.ok()) { set_error("drpo_ensemble_train_step: workspace too small (%lld needed, %lld given)", (long long)br.off, (long long)a.workspace_bytes); return DRPO_ERR_WORKSPACE; }
+    coef = bcoef;
+    const int64_t sH = Bm * H, sO = Bm * O;
+    const int64_t xrows = a.shared_rows ? Bm : R;                       // shared rows: one packed input block read by every member
+    const int64_t sX = a.shared_rows ? 0 : Bm * D;
+    MemberNet n = member_of(e, 0);
+    const unsigned gA = grid_for(R * H);
+    DRPO_LAUNCH(ens_pack_kernel, grid_for(xrows * D), 256, 0, stream, a.states, a.actions, e.norm_mean, e.norm_std, X0, xrows, S, A, (const int*)nullptr);
+    if ((rc = linear_fwd_batched(E, X0, D, sX, n.t0, Z0, H, sH, (int)Bm, ACT_NONE, stream))) return rc;
+    DRPO_LAUNCH(silu_fwd_kernel, gA, 256, 0, stream, Z0, H0, R * H);
+    if ((rc = linear_fwd_batched(E, H0, H, sH, n.t1, Z1, H, sH, (int)Bm, ACT_NONE, stream))) return rc;
+    DRPO_LAUNCH(silu_fwd_kernel, gA, 256, 0, stream, Z1, H1, R * H);
+    if ((rc = linear_fwd_batched(E, H1, H, sH, n.d0, ZD, H, sH, (int)Bm, ACT_NONE, stream))) return rc;
+    DRPO_LAUNCH(silu_fwd_kernel, gA, 256, 0, stream, ZD, HD, R * H);
+    if ((rc = linear_fwd_batched(E, HD, H, sH, n.d1, DD, O, sO, (int)Bm, ACT_NONE, stream))) return rc;
+    if ((rc = linear_fwd_batched(E, H1, H, sH, n.l0, ZL, H, sH, (int)Bm, ACT_NONE, stream))) return rc;
+    DRPO_LAUNCH(silu_fwd_kernel, gA, 256, 0, stream, ZL, HL, R * H);
+    if ((rc = linear_fwd_batched(E, HL, H, sH, n.l1, LR, O, sO, (int)Bm, ACT_NONE, stream))) return rc;
+    EnsNllArgs L;
+    L.dd = DD; L.lr = LR; L.s = a.states; L.t = a.targets; L.min_lv = e.min_log_var; L.max_lv = e.max_log_var;
+    L.g_dd = train ? GDD : nullptr; L.g_lr = GLR; L.g_hi = GHI; L.g_lo = GLO;
+    L.partials = bloss; L.B = Bm; L.S = S; L.inv_n = (float)(1.0 / ((double)Bm * O)); L.row_stride = a.shared_rows ? 0 : Bm;
+    DRPO_LAUNCH(ens_nll_kernel, dim3(ENS_LOSS_BLOCKS, E), 256, 0, stream, L);
+    if (train) {
+      DRPO_LAUNCH(ens_bounds_init_kernel, 1, 64, 0, stream, gp(e.max_log_var), gp(e.min_log_var), O, (float)a.log_var_bound_weight, coef);
+      DRPO_LAUNCH(ens_bounds_grad_kernel, O, 256, 0, stream, GHI, GLO, R, O, gp(e.max_log_var), gp(e.min_log_var));
+      // log-var head
+      if ((rc = linear_bwd_weight_batched(E, GLR, O, sO, HL, H, sH, (int)Bm, O, H, gp(n.l1.w), gp(n.l1.b), stream))) return rc;
+      if ((rc = linear_bwd_data_batched(E, GLR, O, sO, n.l1, DA, H, sH, (int)Bm, 0.f, stream))) return rc;
+      DRPO_LAUNCH(silu_bwd_kernel, gA, 256, 0, stream, DA, ZL, R * H);
+      if ((rc = linear_bwd_weight_batched(E, DA, H, sH, H1, H, sH, (int)Bm, H, H, gp(n.l0.w), gp(n.l0.b), stream))) return rc;
+      if ((rc = linear_bwd_data_batched(E, DA, H, sH, n.l0, DH1, H, sH, (int)Bm, 0.f, stream))) return rc;
+      // diff head
+      if ((rc = linear_bwd_weight_batched(E, GDD, O, sO, HD, H, sH, (int)Bm, O, H, gp(n.d1.w), gp(n.d1.b), stream))) return rc;
+      if ((rc = linear_bwd_data_batched(E, GDD, O, sO, n.d1, DB, H, sH, (int)Bm, 0.f, stream))) return rc;
+      DRPO_LAUNCH(silu_bwd_kernel, gA, 256, 0, stream, DB, ZD, R * H);
+      if ((rc = linear_bwd_weight_batched(E, DB, H, sH, H1, H, sH, (int)Bm, H, H, gp(n.d0.w), gp(n.d0.b), stream))) return rc;
+      if ((rc = linear_bwd_data_batched(E, DB, H, sH, n.d0, DH1, H, sH, (int)Bm, 1.f, stream))) return rc;
+      // trunk
+      DRPO_LAUNCH(silu_bwd_kernel, gA, 256, 0, stream, DH1, Z1, R * H);
+      if ((rc = linear_bwd_weight_batched(E, DH1, H, sH, H0, H, sH, (int)Bm, H, H, gp(n.t1.w), gp(n.t1.b), stream))) return rc;
+      if ((rc = linear_bwd_data_batched(E, DH1, H, sH, n.t1, DA, H, sH, (int)Bm, 0.f, stream))) return rc;
+      DRPO_LAUNCH(silu_bwd_kernel, gA, 256, 0, stream, DA, Z0, R * H);
+      if ((rc = linear_bwd_weight_batched(E, DA, H, sH, X0, D, sX, (int)Bm, H, D, gp(n.t0.w), gp(n.t0.b), stream))) return rc;
+    }
+    DRPO_LAUNCH(ens_loss_finalize_kernel, 1, 32, 0, stream, bloss, ENS_LOSS_BLOCKS, E, 1.0 / ((double)Bm * O), e.max_log_var, e.min_log_var, O,
+                (float)a.log_var_bound_weight, a.losses);
+  } else if (a.phases & 5) {
     if (train) DRPO_LAUNCH(ens_bounds_init_kernel, 1, 64, 0, stream, gp(e.max_log_var), gp(e.min_log_var), O, (float)a.log_var_bound_weight, coef);
     for (int m = 0; m < E; ++m) {
       const int64_t r0 = a.shared_rows ? 0 : (int64_t)m * Bm;
@@ -150,7 +220,7 @@ static inline int ensemble_train_step(const drpo_ensemble_train_args& a) {
       EnsNllArgs L;
       L.dd = dd; L.lr = lr; L.s = s; L.t = t; L.min_lv = e.min_log_var; L.max_lv = e.max_log_var;
       L.g_dd = train ? g_dd : nullptr; L.g_lr = g_lr; L.g_hi = g_hi; L.g_lo = g_lo;
-      L.partials = loss_part + (int64_t)m * ENS_LOSS_BLOCKS; L.B = Bm; L.S = S; L.inv_n = (float)(1.0 / ((double)Bm * O));
+      L.partials = loss_part + (int64_t)m * ENS_LOSS_BLOCKS; L.B = Bm; L.S = S; L.inv_n = (float)(1.0 / ((double)Bm * O)); L.row_stride = 0;
       DRPO_LAUNCH(ens_nll_kernel, ENS_LOSS_BLOCKS, 256, 0, stream, L);
       if (!train) continue;
       DRPO_LAUNCH(ens_bounds_grad_kernel, O, 256, 0, stream, g_hi, g_lo, Bm, O, gp(e.max_log_var), gp(e.min_log_var));

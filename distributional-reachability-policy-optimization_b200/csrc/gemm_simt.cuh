@@ -23,6 +23,8 @@ struct GemmArgs {
   float* bias_out;                       // backward-weight: B gets a virtual all-ones last column; that column of the
                                          // result (= column sums of dY = db) is routed to bias_out[m]
   int splitk; float* partial;            // split-K: raw partial sums [splitk, M, N], reduced by splitk_reduce_kernel
+  int batch;                             // > 1 (and splitk == 1): blockIdx.z walks independent problems (ensemble members) whose
+  int64_t a_sb, b_sb, c_sb, bias_sb, mask_sb, bo_sb;   // operands are `*_sb` elements apart (0 = shared by all)
 };
 
 constexpr int GM = 64, GN = 64, GK = 16, GPAD = 4;
@@ -32,6 +34,13 @@ static __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
   __shared__ __align__(16) float Bs[GK][GN + GPAD];
   int M = g.M;
   if (g.m_dev) M = min(M, *g.m_dev);
+  if (g.batch > 1) {                      // per-problem operand bases
+    const int64_t bz = blockIdx.z;
+    g.A += bz * g.a_sb; g.B += bz * g.b_sb; g.C += bz * g.c_sb;
+    if (g.bias) g.bias += bz * g.bias_sb;
+    if (g.mask) g.mask += bz * g.mask_sb;
+    if (g.bias_out) g.bias_out += bz * g.bo_sb;
+  }
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
   if (m0 >= M) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -121,7 +130,8 @@ static inline GemmArgs gemm_args() { GemmArgs g; memset(&g, 0, sizeof(g)); g.spl
 
 static inline int launch_gemm(const GemmArgs& g, void* stream) {
   if (g.M <= 0 || g.N <= 0) return DRPO_OK;
-  dim3 grid((g.N + GN - 1) / GN, (g.M + GM - 1) / GM, g.splitk > 1 ? g.splitk : 1);
+  if (g.batch > 1 && g.splitk > 1) { set_error("launch_gemm: split-K and batching are exclusive"); return DRPO_ERR_ARG; }
+  dim3 grid((g.N + GN - 1) / GN, (g.M + GM - 1) / GM, g.splitk > 1 ? g.splitk : (g.batch > 1 ? g.batch : 1));
   DRPO_LAUNCH(gemm_f32_kernel, grid, 256, 0, stream, g);
   if (g.splitk > 1) {
     int64_t total = (int64_t)g.M * g.N;
@@ -319,6 +329,34 @@ static inline int linear_fwd(const float* X, int64_t ldx, const drpo_linear& L, 
   g.A = X; g.a_sm = ldx; g.a_sk = 1;
   g.B = L.w; g.b_sk = 1; g.b_sn = L.in_dim;
   g.C = Y; g.ldc = ldy; g.bias = L.b; g.M = M; g.N = L.out_dim; g.K = L.in_dim; g.act = act; g.m_dev = m_dev;
+  return launch_gemm(g, stream);
+}
+// ---- the same three contractions for E independent layers in one launch (ensemble members; fp32 FFMA kernel only) --------
+// X[e] = X + e*x_sb (x_sb = 0: every member reads the same rows), W[e] = W + e*N*K, b[e] = b + e*N, Y[e] = Y + e*y_sb
+static inline int linear_fwd_batched(int E, const float* X, int64_t ldx, int64_t x_sb, const drpo_linear& L0, float* Y, int64_t ldy, int64_t y_sb,
+                                     int M, int act, void* stream) {
+  GemmArgs g = gemm_args();
+  g.A = X; g.a_sm = ldx; g.a_sk = 1; g.a_sb = x_sb;
+  g.B = L0.w; g.b_sk = 1; g.b_sn = L0.in_dim; g.b_sb = (int64_t)L0.out_dim * L0.in_dim;
+  g.C = Y; g.ldc = ldy; g.c_sb = y_sb; g.bias = L0.b; g.bias_sb = L0.out_dim;
+  g.M = M; g.N = L0.out_dim; g.K = L0.in_dim; g.act = act; g.batch = E;
+  return launch_gemm(g, stream);
+}
+static inline int linear_bwd_data_batched(int E, const float* dY, int64_t ldy, int64_t dy_sb, const drpo_linear& L0, float* dX, int64_t lddx,
+                                          int64_t dx_sb, int M, float beta, void* stream) {
+  GemmArgs g = gemm_args();
+  g.A = dY; g.a_sm = ldy; g.a_sk = 1; g.a_sb = dy_sb;
+  g.B = L0.w; g.b_sk = L0.in_dim; g.b_sn = 1; g.b_sb = (int64_t)L0.out_dim * L0.in_dim;
+  g.C = dX; g.ldc = lddx; g.c_sb = dx_sb; g.M = M; g.N = L0.in_dim; g.K = L0.out_dim; g.beta = beta; g.batch = E;
+  return launch_gemm(g, stream);
+}
+// dW[e] = dY[e]^T X[e], db[e] = column sums of dY[e]; no split-K: meant for a few hundred rows per member
+static inline int linear_bwd_weight_batched(int E, const float* dY, int64_t ldy, int64_t dy_sb, const float* X, int64_t ldx, int64_t x_sb, int M,
+                                            int n_out, int k_in, float* dW, float* db, void* stream) {
+  GemmArgs g = gemm_args();
+  g.A = dY; g.a_sm = 1; g.a_sk = ldy; g.a_sb = dy_sb;
+  g.B = X; g.b_sk = ldx; g.b_sn = 1; g.b_sb = x_sb;
+  g.C = dW; g.ldc = k_in; g.c_sb = (int64_t)n_out * k_in; g.M = n_out; g.N = k_in + 1; g.K = M; g.bias_out = db; g.bo_sb = n_out; g.batch = E;
   return launch_gemm(g, stream);
 }
 // dX[M,K] = (dY[M,N] W[N,K]) * act'(saved)   (+ beta*dX)
