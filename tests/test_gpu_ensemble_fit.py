@@ -32,7 +32,10 @@ def test_ensemble_fit_vs_golden(golden, tag, S, A):
     assert torch.argsort(hl)[:5].tolist() == [int(x) for x in g[f"{tag}.elites"]]
 
 
-@pytest.mark.parametrize("S,A,n,prec,tol", [(12, 2, 7 * 256 + 5, "fp32", 5e-5), (60, 2, 7 * 64, "fp32", 5e-5), (12, 2, 7 * 256, "tf32", 2e-2)])
+# up to 512 rows per member all members run in one launch per layer (batched FFMA GEMM); above, member by member with split-K
+# weight gradients and, in the tensor mode, TF32 tensor-op GEMMs: both paths, both precisions
+@pytest.mark.parametrize("S,A,n,prec,tol", [(12, 2, 7 * 256 + 5, "fp32", 5e-5), (60, 2, 7 * 64, "fp32", 5e-5), (12, 2, 7 * 256, "tf32", 2e-2),
+                                            (12, 2, 7 * 640, "fp32", 5e-5), (12, 2, 7 * 640, "tf32", 2e-2)])
 def test_ensemble_train_step_vs_oracle(S, A, n, prec, tol):
     import drpo_b200
     w = O.make_ensemble_weights(81, S, A)
