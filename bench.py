@@ -288,6 +288,9 @@ def run_ours(args):
     # ---- SSAC critic updates/s (second half of the metric) -------------------------------------------------------------
     if not args.skip_critic:
         out["critic"] = bench_critic(args, device, world, rank, pk)
+    # ---- ensemble training iterations/s (BatchedGaussianEnsemble.fit's loop body): replicas only ----------
+    if not args.skip_critic:
+        out["ensemble_fit"] = bench_ensemble_fit(args, alg, workload, device, world == 1 and not args.skip_cpu)
     # ---- CPU baseline (oracle port) on rank 0, N=1 only --------------------------------------------------------------
     if world == 1 and not args.skip_cpu:
         out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=5)
@@ -418,6 +421,46 @@ def cpu_critic_baseline(B):
     dt = (time.perf_counter() - t0) / reps
     return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads,
             "kind": "port", "sample": f"{reps} x oracle critic_update at B={B} (tracking dims), torch CPU fp32 autograd, {threads} threads"}
+
+
+def bench_ensemble_fit(args, alg, workload, device, with_cpu):
+    """One training iteration of the dynamics ensemble at the reference's batch (7 members x 256 rows, src/dynamics.py:66)."""
+    from drpo_b200 import _lib, synthetic
+    lib = _lib.load()
+    ens = alg.model_ensemble
+    _, S, A, C = synthetic.WORKLOADS[workload]
+    n = ens.ensemble_size * ens.batch_size
+    g = torch.Generator().manual_seed(11)
+    s = torch.randn(n, S, generator=g); a = torch.rand(n, A, generator=g) * 2 - 1
+    t = torch.cat([s + 0.05 * torch.randn(n, S, generator=g), torch.randn(n, 1, generator=g)], dim=1)
+    sd, ad, td = s.to(device), a.to(device), t.to(device)
+    for _ in range(5):
+        ens.train_step(sd, ad, td)
+    torch.cuda.synchronize()
+    k, l0 = 100, lib.drpo_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        ens.train_step(sd, ad, td)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    res = {"metric": "ensemble_train_iterations_per_s", "value": 1e3 / ms, "unit": "iterations/s", "ms_per_iteration": ms,
+           "rows": n, "gpu_launches": int(lib.drpo_launch_count() - l0), "dtype": "f32", "scaling": "replicas only"}
+    if with_cpu:
+        from oracle import drpo_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        w = synthetic.make_ensemble_weights(64578, S, A)
+        adam = O.AdamState()
+        O.ensemble_train_step(w, s, a, t, adam)
+        t0, reps = time.perf_counter(), 10
+        for _ in range(reps):
+            O.ensemble_train_step(w, s, a, t, adam)
+        dt = (time.perf_counter() - t0) / reps
+        res["cpu_baseline"] = {"value": 1.0 / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
+                               "sample": f"{reps} x oracle ensemble_train_step at {n} rows ({workload} dims), torch CPU fp32 autograd, {threads} threads"}
+    return res
 
 
 def cpu_actor_baseline(B):
