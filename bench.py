@@ -177,8 +177,9 @@ def run_ours(args):
 
     def step_e2e():
         alg.virt_buffer._pointer.zero_()
-        dev_init = init_host.to(device, non_blocking=True)                    # H2D of this step's inputs (pinned)
-        view = alg.rollout(alg.actor, initial_states=dev_init, member_idx=members)
+        # H2D of this step's inputs (pinned) happens inside the public call: SMBPO.rollout streams host start states in row blocks
+        # on a copy stream and the first step's kernel waits per block
+        view = alg.rollout(alg.actor, initial_states=init_host, member_idx=members)
         return view.step_counts.to("cpu", non_blocking=False)                  # D2H of the step's result
 
     t_pre = time.perf_counter()                       # untimed pre-warm: bring the SM clocks up before the W warm-up steps

@@ -78,6 +78,7 @@ class RolloutArgs(C.Structure):
         ("member_idx_host", C.POINTER(C.c_int32)), ("eps_policy", C.c_void_p), ("eps_model", C.c_void_p),
         ("eps_batch_stride", C.c_int64), ("seed", C.c_uint64), ("virt", Buffer), ("step_counts", C.c_void_p),
         ("precision", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
+        ("init_ready_flags", C.c_void_p), ("init_rows_per_flag_log2", C.c_int32),
     ]
 
 

@@ -265,6 +265,8 @@ int drpo_rollout(const drpo_rollout_args* a) {
     DRPO_CUDA_OK(cudaMemsetAsync(a->step_counts, 0, sizeof(int32_t) * (a->horizon + 1), (cudaStream_t)a->stream));
     return DRPO_OK;
   }
+  DRPO_CHECK_ARG(!a->init_ready_flags || (a->precision == DRPO_PREC_BF16 && a->init_rows_per_flag_log2 >= 7 && a->init_rows_per_flag_log2 <= 30),
+                 "drpo_rollout: streamed start states need DRPO_PREC_BF16 and row blocks of 2^7..2^30 rows");
   if (a->precision == DRPO_PREC_FP32) return rollout_fp32(*a);
   if (a->precision == DRPO_PREC_BF16) return umma_rollout(*a);
   set_error("drpo_rollout: unknown precision %d", a->precision);

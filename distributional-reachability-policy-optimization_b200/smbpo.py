@@ -104,6 +104,28 @@ class SMBPO(Configurable, nn.Module):
             initial_states = states.index_select(0, idx)
         initial_states = initial_states.contiguous().float()
         B, H = initial_states.shape[0], self.horizon
+        # Host start states (bf16 path): the host-to-device transfer runs in row blocks on a side stream, every block followed by a
+        # DMA write of its ready flag, and the first step's kernel waits per block - the copy overlaps that step
+        flags = copy_stream = None
+        if initial_states.device.type == "cpu" and self.virt_buffer.device.type == "cuda":
+            dev = self.virt_buffer.device
+            if self.rollout_precision == _lib.PREC_BF16 and initial_states.is_pinned() and B >= (1 << 16) and _debug_layer is None:
+                host, shift = initial_states, 17                                    # 131 072-row blocks: few host calls per transfer
+                nblk = (B + (1 << shift) - 1) >> shift
+                initial_states = torch.empty_like(host, device=dev)
+                flags = torch.zeros(nblk, dtype=torch.int32, device=dev)
+                if getattr(self, "_flag_ones", None) is None or self._flag_ones.numel() < nblk:
+                    self._flag_ones = torch.ones(max(nblk, 64), dtype=torch.int32).pin_memory()
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                copy_stream = self._copy_stream
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))             # the flags are zero before any copy starts
+                with torch.cuda.stream(copy_stream):
+                    for j in range(nblk):
+                        lo, hi = j << shift, min((j + 1) << shift, B)
+                        initial_states[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                        flags[j:j + 1].copy_(self._flag_ones[j:j + 1], non_blocking=True)     # copy engine, not a kernel
+            else:
+                initial_states = initial_states.to(dev, non_blocking=True)
         if member_idx is None:        # one host-side random.choice per step, as BatchedGaussianEnsemble.sample does (:199)
             member_idx = [random.choice(self.model_ensemble._elite_inds) for _ in range(H)]
         members = (ctypes.c_int32 * H)(*[int(m) for m in member_idx])
@@ -127,6 +149,8 @@ class SMBPO(Configurable, nn.Module):
         a.virt, a.step_counts, a.precision = ring.as_struct(), _lib.ptr(counts), self.rollout_precision
         ws = self._ws.get(lib.drpo_rollout_workspace_bytes(a), initial_states.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        if flags is not None:
+            a.init_ready_flags, a.init_rows_per_flag_log2 = _lib.ptr(flags), 17
         if _debug_layer is not None:
             n_out = 1024 if _debug_layer == 100 else [policy.net[0].weight.shape[0], policy.net[2].weight.shape[0], policy.net[4].weight.shape[0],
                      self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim,
@@ -135,6 +159,10 @@ class SMBPO(Configurable, nn.Module):
             _lib.check(lib.drpo_debug_rollout_layer(a, _debug_layer, _lib.ptr(out)), "drpo_debug_rollout_layer")
             return out
         _lib.check(lib.drpo_rollout(a), "drpo_rollout")
+        if copy_stream is not None:
+            cur = torch.cuda.current_stream(initial_states.device)
+            cur.wait_stream(copy_stream)                    # later work on this stream is ordered after the transfer as usual
+            initial_states.record_stream(copy_stream); flags.record_stream(copy_stream)
         return RolloutView(ring, start, counts)
 
     # ---- SMBPO.update_solver  (src/smbpo.py:251-279) ---------------------------------------------------------------

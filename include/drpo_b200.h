@@ -209,6 +209,13 @@ typedef struct drpo_rollout_args {
   void* workspace;
   int64_t workspace_bytes;
   void* stream;
+  /* Optional streaming of the start states (DRPO_PREC_BF16 only; NULL = off): `initial_states` may still be in flight from the
+   * host on ANOTHER stream, in row blocks of 2^init_rows_per_flag_log2 rows; the copy of block j is followed (same stream) by a
+   * DMA write of a non-zero int32 to init_ready_flags[j].  The first step's kernel polls the flag of a row block before it
+   * reads it, so the host-to-device transfer overlaps that step instead of preceding it.  The flags must be written by copy
+   * engines (cudaMemcpyAsync from pinned memory), never by a kernel: the rollout kernel occupies every SM while it waits. */
+  const int32_t* init_ready_flags;
+  int32_t init_rows_per_flag_log2;
 } drpo_rollout_args;
 
 int64_t drpo_rollout_workspace_bytes(const drpo_rollout_args* args);

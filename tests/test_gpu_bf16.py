@@ -227,3 +227,30 @@ def test_bf16_rollout_empty_and_all_done():
     assert view.counts() == [300] + [0] * (H - 1) and len(view) == 300
     out = view.get(as_dict=True)
     assert bool(out["dones"].all()) and bool(out["violations"].all())
+
+
+@pytest.mark.gpu
+def test_rollout_from_pinned_host_states_streams_and_matches():
+    """Host start states (pinned): SMBPO.rollout streams them in row blocks on a copy stream while the first step's kernel waits
+    per block (init_ready_flags of the C ABI).  Results are bit-identical to the device-resident call."""
+    import drpo_b200
+    from drpo_b200 import synthetic, _lib
+    B, H = 200_000, 4
+    cfg = drpo_b200.SMBPO.Config(); cfg.buffer_max, cfg.horizon = B * H, H
+    outs = []
+    init = synthetic.make_start_states("quadrotor", B, 11)
+    for mode in ("device", "host"):
+        alg = drpo_b200.SMBPO(cfg, drpo_b200.device_env("quadrotor"), device=dev())
+        env_name, S, A, C = synthetic.WORKLOADS["quadrotor"]
+        alg.model_ensemble.load_state_dict(synthetic.make_ensemble_weights(64578, S, A), strict=True)
+        alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
+        alg.solver.load_state_dict(synthetic.make_ssac_weights(219803, S, A, C), strict=False)
+        alg.rollout_precision = drpo_b200.PREC_BF16
+        x = init.to(dev()) if mode == "device" else init.pin_memory()
+        view = alg.rollout(alg.actor, initial_states=x, member_idx=[0, 1, 2, 3])
+        torch.cuda.synchronize()
+        _lib.check_kernel_status("streamed rollout")
+        outs.append((view.step_counts.cpu(), alg.virt_buffer._bufs["next_states"][:int(view.step_counts[-1])].cpu(),
+                     alg.virt_buffer._bufs["states"][:int(view.step_counts[-1])].cpu(), alg.virt_buffer._bufs["dones"][:int(view.step_counts[-1])].cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
