@@ -144,6 +144,20 @@ class EnsembleTrainArgs(C.Structure):
     ]
 
 
+SHIELD_NONE, SHIELD_SAFE, SHIELD_LINEAR = 0, 1, 2
+SHIELD_TYPES = {"none": SHIELD_NONE, "safe": SHIELD_SAFE, "linear": SHIELD_LINEAR}
+
+
+class ShieldArgs(C.Structure):
+    _fields_ = [
+        ("actor", C.POINTER(Mlp3)), ("actor_safe", C.POINTER(Mlp3)), ("qc", C.POINTER(Qc)), ("states", C.c_void_p), ("n", C.c_int64),
+        ("state_dim", C.c_int32), ("action_dim", C.c_int32), ("con_dim", C.c_int32), ("shield_type", C.c_int32),
+        ("eval_perf", C.c_int32), ("uncertainty", C.c_int32), ("std_ratio", C.c_float), ("threshold", C.c_float),
+        ("noise_perf", C.POINTER(Noise)), ("actions", C.c_void_p), ("qc_perf", C.c_void_p), ("choice", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/drpo_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("drpo_last_error", C.c_char_p, []),
@@ -178,6 +192,8 @@ SYMBOLS = [
     ("drpo_ensemble_train_step", C.c_int, [C.POINTER(EnsembleTrainArgs)]),
     ("drpo_actor_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_actor_step", C.c_int, [C.POINTER(ActorArgs)]),
+    ("drpo_shield_workspace_bytes", C.c_int64, [C.POINTER(Mlp3), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("drpo_shield_act", C.c_int, [C.POINTER(ShieldArgs)]),
     ("drpo_qc_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32]),
     ("drpo_qc_forward", C.c_int, [C.POINTER(Qc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_float, C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

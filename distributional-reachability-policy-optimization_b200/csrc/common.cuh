@@ -65,7 +65,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
-    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_RELU: return x < 0.f ? 0.f : x;              // NaN-propagating, like torch.relu (fmaxf would turn NaN into 0)
     case ACT_SILU: return silu_f(x);
     case ACT_TANH: return tanhf(x);
     default: return x;

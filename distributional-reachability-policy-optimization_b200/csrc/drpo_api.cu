@@ -6,6 +6,7 @@
 #include "actor.cuh"
 #include "ensemble_train.cuh"
 #include "nets.cuh"
+#include "shield.cuh"
 #include "rollout.cuh"
 #include "umma_api.h"
 #include "critic_umma_api.h"
@@ -206,6 +207,55 @@ int drpo_qc_forward(const drpo_qc* qc, const float* states, const float* actions
   NoiseView nv = noise ? make_noise(noise->eps, noise->row_stride, noise->seed, noise->stream_tag, noise->step) : make_noise(nullptr, 0, 0, 0, 0);
   DRPO_LAUNCH(qc_head_kernel, grid_for(batch * C), 256, 0, stream, a.mean_raw, a.ls_raw, mode, std_ratio, nv, (int64_t)0, out_mean, out_std,
               out_sample, batch, C);
+  return DRPO_OK;
+}
+
+int64_t drpo_shield_workspace_bytes(const drpo_mlp3* actor, int64_t n, int32_t state_dim, int32_t action_dim, int32_t con_dim,
+                                    int32_t hidden) {
+  if (!actor || n < 0) return -1;
+  const int64_t rows = (int64_t)SHIELD_MIX * n;
+  return drpo_policy_workspace_bytes(actor, n) + drpo_qc_workspace_bytes(rows, hidden) +
+         (2 * n * action_dim + rows * (state_dim + action_dim + con_dim)) * 4 + 8 * 256;
+}
+
+int drpo_shield_act(const drpo_shield_args* a) {
+  DRPO_CHECK_ARG(a, "drpo_shield_act: NULL args");
+  int rc;
+  if ((rc = check_mlp3(a->actor, "drpo_shield_act(actor)"))) return rc;
+  const int S = a->state_dim, A = a->action_dim, C = a->con_dim;
+  const int64_t n = a->n;
+  DRPO_CHECK_ARG(a->shield_type >= DRPO_SHIELD_NONE && a->shield_type <= DRPO_SHIELD_LINEAR, "drpo_shield_act: unknown shield type %d", a->shield_type);
+  DRPO_CHECK_ARG(n >= 0 && (n == 0 || (a->states && a->actions)) && (a->eval_perf || a->noise_perf), "drpo_shield_act: bad arguments");
+  DRPO_CHECK_ARG(a->actor->l0.in_dim == S && a->actor->l2.out_dim == 2 * A, "drpo_shield_act: actor dims do not match");
+  DRPO_CHECK_ARG(C >= 1 && C <= DRPO_MAX_CON, "drpo_shield_act: con_dim out of range");
+  if (n == 0) return DRPO_OK;
+  if (a->shield_type == DRPO_SHIELD_NONE) {
+    if ((rc = drpo_policy_act(a->actor, a->states, n, a->eval_perf, a->noise_perf, a->actions, nullptr, DRPO_PREC_FP32, a->workspace,
+                              a->workspace_bytes, a->stream))) return rc;
+    if (a->choice) DRPO_CUDA_OK(cudaMemsetAsync(a->choice, 0, n * sizeof(int32_t), (cudaStream_t)a->stream));
+    return DRPO_OK;
+  }
+  if ((rc = check_mlp3(a->actor_safe, "drpo_shield_act(actor_safe)"))) return rc;
+  if ((rc = check_qc(a->qc, "drpo_shield_act"))) return rc;
+  DRPO_CHECK_ARG(a->actor_safe->l0.in_dim == S && a->actor_safe->l2.out_dim == 2 * A, "drpo_shield_act: actor_safe dims do not match");
+  const int n_mix = a->shield_type == DRPO_SHIELD_LINEAR ? SHIELD_MIX : 1;
+  const int64_t rows = (int64_t)n_mix * n;
+  const int H = a->qc->trunk0.out_dim;
+  Arena ar(a->workspace, a->workspace_bytes);
+  float* a_perf = ar.take<float>(n * A); float* a_safe = ar.take<float>(n * A);
+  float* cand_s = ar.take<float>(rows * S); float* cand_a = ar.take<float>(rows * A); float* q = ar.take<float>(rows * C);
+  const int64_t pol_bytes = drpo_policy_workspace_bytes(a->actor, n), qc_bytes = drpo_qc_workspace_bytes(rows, H);
+  char* sub = ar.take<char>(std::max(pol_bytes, qc_bytes));
+  if (!ar.ok()) { set_error("drpo_shield_act: workspace too small"); return DRPO_ERR_WORKSPACE; }
+  cudaStream_t stream = (cudaStream_t)a->stream;
+  if ((rc = drpo_policy_act(a->actor, a->states, n, a->eval_perf, a->noise_perf, a_perf, nullptr, DRPO_PREC_FP32, sub, pol_bytes, stream))) return rc;
+  if ((rc = drpo_policy_act(a->actor_safe, a->states, n, 1, nullptr, a_safe, nullptr, DRPO_PREC_FP32, sub, pol_bytes, stream))) return rc;
+  DRPO_LAUNCH(shield_candidates_kernel, grid_for(rows * (S + A)), 256, 0, stream, a->states, a_perf, a_safe, shield_ratios(), n_mix, n, S, A,
+              cand_s, cand_a);
+  if ((rc = drpo_qc_forward(a->qc, cand_s, cand_a, rows, S, A, C, a->uncertainty ? 1 : 0, a->std_ratio, nullptr, a->uncertainty ? nullptr : q, nullptr, q, sub, qc_bytes,
+                            stream))) return rc;
+  DRPO_LAUNCH(shield_select_kernel, grid_for(n), 256, 0, stream, q, cand_a, a_safe, a->threshold, n_mix, n, A, C, a->actions, a->qc_perf,
+              a->choice);
   return DRPO_OK;
 }
 

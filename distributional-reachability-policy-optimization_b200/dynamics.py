@@ -262,21 +262,46 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         _lib.check(lib.drpo_ensemble_train_step(a), "drpo_ensemble_train_step(holdout)")
         return self._fit_losses[1:1 + self.ensemble_size].clone()
 
-    def fit(self, buffer, steps=None, epochs=None, progress_bar=False, **kwargs):
-        """src/dynamics.py:155-189 (steps form): normaliser fit, ``steps`` Adam iterations on random minibatches, holdout ranking
-        of the members -> ``_elite_inds``.  The index draws stay torch.randint on the device (as in the reference); every
-        iteration is one drpo_ensemble_train_step; the losses are read back once at the end."""
-        if steps is None:
-            raise NotImplementedError("only fit(steps=...) is provided")
+    def fit(self, buffer, steps=None, epochs=None, progress_bar=False, max_grad_norm=None, post_epoch_callback=None,
+            post_step_callback=None, verbose=False, **kwargs):
+        """src/dynamics.py:155-196: normaliser fit, then either ``steps`` Adam iterations on random minibatches followed by the
+        holdout ranking of the members -> ``_elite_inds`` (:161-185), or ``epochs`` x ensemble_size shuffled passes over the
+        buffer (:186-194 -> epochal_training, src/train.py:58-101; returns the per-epoch mean loss).  The index draws stay
+        torch.randint / torch.randperm (as in the reference); every iteration is one drpo_ensemble_train_step; the losses are
+        read back once per call (steps form) or once per epoch (epochs form)."""
         n = len(buffer)
         states, actions, next_states, rewards = buffer.get()[:4]
         self.state_normalizer.fit(states)
         targets = torch.cat([next_states, rewards.unsqueeze(1)], dim=1)
-        losses = torch.empty(steps, device=states.device)
-        for i in range(steps):
-            idx = torch.randint(n, [self.total_batch_size], device=states.device)
-            losses[i] = self.train_step(states[idx], actions[idx], targets[idx])
-        hold = torch.randint(n, [self.holdout_size], device=states.device)
-        mse = self.holdout_losses(states[hold], actions[hold], targets[hold])
-        self._elite_inds = torch.argsort(mse)[:self.num_elites].tolist()
-        return losses.tolist()
+        if steps is not None:
+            assert epochs is None, 'Cannot pass both steps and epochs'
+            losses = torch.empty(steps, device=states.device)
+            for i in range(steps):
+                idx = torch.randint(n, [self.total_batch_size], device=states.device)
+                losses[i] = self.train_step(states[idx], actions[idx], targets[idx])
+            hold = torch.randint(n, [self.holdout_size], device=states.device)
+            mse = self.holdout_losses(states[hold], actions[hold], targets[hold])
+            self._elite_inds = torch.argsort(mse)[:self.num_elites].tolist()
+            return losses.tolist()
+        if epochs is None:
+            raise ValueError('Must pass steps or epochs')
+        if max_grad_norm is not None:
+            raise NotImplementedError("the in-kernel Adam of drpo_ensemble_train_step has no gradient clip "
+                                      "(BatchedGaussianEnsemble.fit never passes max_grad_norm, src/dynamics.py:190-192)")
+        bs = self.total_batch_size
+        n_batches = -(-n // bs)
+        losses = []
+        for epoch in range(self.ensemble_size * epochs):
+            perm = torch.randperm(n).to(states.device)
+            ep = torch.empty(n_batches, device=states.device)
+            for b in range(n_batches):
+                idx = perm[b * bs:min((b + 1) * bs, n)]
+                if idx.numel() < self.ensemble_size:
+                    raise ValueError(f"the last batch of an epoch has {idx.numel()} rows: fewer than one per member")
+                ep[b] = self.train_step(states[idx], actions[idx], targets[idx])
+                if post_step_callback is not None:
+                    post_step_callback(epoch, b, n_batches)
+            losses.append(float(ep.double().mean().item()))
+            if post_epoch_callback is not None:
+                post_epoch_callback(epoch + 1)
+        return losses

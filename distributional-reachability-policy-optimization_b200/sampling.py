@@ -127,3 +127,13 @@ class RolloutView:
         if as_dict:
             return dict(zip(names, bufs))
         return bufs if len(bufs) > 1 else bufs[0]
+
+
+def shielded_actions(policy, states, eval=False, safe_shield_threshold=-0.1, shield_type="linear"):
+    """The per-step action selection of sample_episodes_batched (src/sampling.py:420-439): ``policy`` is the SSAC solver;
+    without ``eval`` it is plain ``policy.act``; with it the performance action goes through the safety shield
+    ("safe": switch to the safe actor where Qc > threshold; "linear": the mix of safe and performance action closest to
+    the performance action whose Qc is <= threshold).  One drpo_shield_act call; stepping the env stays with the caller."""
+    if not eval:
+        return policy.act(states, eval=False)
+    return policy.shield_act(states, eval=True, shield_type=shield_type, safe_shield_threshold=safe_shield_threshold)

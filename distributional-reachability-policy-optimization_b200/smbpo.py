@@ -88,6 +88,16 @@ class SMBPO(Configurable, nn.Module):
     def actor_safe(self):
         return self.solver.actor_safe
 
+    def shielded_act1(self, state, eps=None):
+        """The action of one training step (src/smbpo.py:124-136): a sampled performance action, replaced by the safe actor's
+        eval action when the shield is on and _get_qc(constraint_critic(s, a, uncertainty=distributional_qc)) exceeds
+        safe_shield_threshold.  One drpo_shield_act call on a single row."""
+        s = state.unsqueeze(0)
+        if not self.safe_shield:
+            return self.actor.act(s, False, eps)[0]
+        return self.solver.shield_act(s, eval=False, shield_type="safe", safe_shield_threshold=self.safe_shield_threshold,
+                                      uncertainty=self.solver.distributional_qc, eps=eps)[0]
+
     def _create_buffer(self, capacity, device=None):
         return ConstraintSafetySampleBuffer(self.state_dim, self.action_dim, capacity, con_dim=self.con_dim,
                                             device=device or self.virt_buffer.device)

@@ -408,6 +408,36 @@ class SSAC(Configurable, BasePolicy, nn.Module):
             return torch.max(qc_con_dim, dim=-1)[0]
         return qc_con_dim
 
+    def shield_act(self, states, eval=True, shield_type="linear", safe_shield_threshold=-0.1, uncertainty=False, eps=None,
+                   return_info=False):
+        """The safety shield in one C-ABI call (drpo_shield_act): the action-selection block of sample_episodes_batched
+        (src/sampling.py:420-439: ``eval=True``, Qc = mean head, shield_type "safe" / "linear" / anything else = none) and of
+        SMBPO.step_generator (src/smbpo.py:124-136: ``eval=False`` samples the performance action, ``uncertainty`` =
+        distributional_qc, shield_type "safe").  The safe actor always acts in eval mode, as at both call sites.
+        ``return_info`` adds (_get_qc of the performance action, choice) - see include/drpo_b200.h."""
+        lib = _lib.load()
+        states = states.contiguous().float()
+        n, A = states.shape[0], self.action_dim
+        actions = torch.empty((n, A), device=states.device)
+        qc_perf = torch.empty((n,), device=states.device) if return_info else None
+        choice = torch.empty((n,), dtype=torch.int32, device=states.device) if return_info else None
+        a = _lib.ShieldArgs()
+        actor, safe, qc = self.actor.as_struct(), self.actor_safe.as_struct(), self.constraint_critic.as_struct()
+        a.actor, a.actor_safe, a.qc = C_pointer(actor), C_pointer(safe), C_pointer(qc)
+        a.states, a.n, a.state_dim, a.action_dim, a.con_dim = _lib.ptr(states), n, self.state_dim, A, self.con_dim
+        a.shield_type = _lib.SHIELD_TYPES.get(shield_type, _lib.SHIELD_NONE)
+        a.eval_perf, a.uncertainty = int(bool(eval)), int(bool(uncertainty))
+        a.std_ratio, a.threshold = float(self.constraint_critic.std_ratio), float(safe_shield_threshold)
+        self.actor._noise_step += 1
+        noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, A, self.actor.noise_seed, 17, self.actor._noise_step)
+        a.noise_perf = C_pointer(noise)
+        a.actions, a.qc_perf, a.choice = _lib.ptr(actions), _lib.ptr(qc_perf), _lib.ptr(choice)
+        ws = self._ws.get(lib.drpo_shield_workspace_bytes(a.actor, n, self.state_dim, A, self.con_dim, self.constraint_critic.hidden_dim),
+                          states.device)
+        a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
+        _lib.check(lib.drpo_shield_act(a), "drpo_shield_act")
+        return (actions, qc_perf, choice) if return_info else actions
+
     def _dist(self):
         import torch.distributed as dist
         if self.data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -369,6 +369,43 @@ int drpo_qc_forward(const drpo_qc* qc, const float* states, const float* actions
                     const drpo_noise* noise, float* out_mean, float* out_std, float* out_sample,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Safety shield: the action-selection block of SMBPO.step_generator (src/smbpo.py:124-136) and of
+ * sample_episodes_batched (src/sampling.py:420-439).
+ *   shield_type DRPO_SHIELD_NONE   : actions = actor.act(states)
+ *               DRPO_SHIELD_SAFE   : actions = where(_get_qc(Qc(s, a_perf)) > threshold, actor_safe.act(s, eval), a_perf)
+ *               DRPO_SHIELD_LINEAR : actions = a_safe; for i in 0..10: mix = a_safe*r_i + a_perf*(1-r_i), r_i = (10-i)/10;
+ *                                    actions = where(_get_qc(Qc(s, mix)) <= threshold, mix, actions)   (one Qc pass over 11*n rows)
+ * eval_perf = 0 samples the performance action with noise_perf (the training step); the safe actor always acts in eval
+ * mode (both call sites).  uncertainty != 0 evaluates Qc as mean + std_ratio*std (src/ssac.py:85; the training step passes
+ * distributional_qc), else the mean head (the evaluation sampler).
+ * Outputs: actions [n,A]; optional qc_perf [n] (_get_qc of the performance action) and choice [n] (SAFE: 1 = safe action
+ * taken; LINEAR: the selected i, -1 = none passed and the safe action stands; NONE: 0).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { DRPO_SHIELD_NONE = 0, DRPO_SHIELD_SAFE = 1, DRPO_SHIELD_LINEAR = 2 };
+typedef struct drpo_shield_args {
+  const drpo_mlp3* actor;
+  const drpo_mlp3* actor_safe;
+  const drpo_qc* qc;
+  const float* states;             /* [n,S] */
+  int64_t n;
+  int32_t state_dim, action_dim, con_dim;
+  int32_t shield_type;
+  int32_t eval_perf;
+  int32_t uncertainty;
+  float std_ratio;
+  float threshold;
+  const drpo_noise* noise_perf;    /* needed when eval_perf == 0 */
+  float* actions;                  /* out [n,A] */
+  float* qc_perf;                  /* out [n] or NULL */
+  int32_t* choice;                 /* out [n] or NULL */
+  void* workspace; int64_t workspace_bytes;
+  void* stream;
+} drpo_shield_args;
+int64_t drpo_shield_workspace_bytes(const drpo_mlp3* actor, int64_t n, int32_t state_dim, int32_t action_dim, int32_t con_dim,
+                                    int32_t hidden);
+int drpo_shield_act(const drpo_shield_args* args);
+
 /* misc */
 const char* drpo_last_error(void);
 int drpo_abi_version(void);

@@ -352,6 +352,40 @@ def multiplier_forward(w: W, s: Tensor, qc: Tensor, ub: float = 50.0) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# safety shield  (src/smbpo.py:124-136 training step; src/sampling.py:420-439 batched evaluation)
+# ----------------------------------------------------------------------------------------------
+
+def shield_actions(w: W, states: Tensor, C: int, shield_type: str, threshold: float, eps_perf: Optional[Tensor] = None,
+                   uncertainty: bool = False, std_ratio: float = 2.0):
+    """The action-selection block of sample_episodes_batched (src/sampling.py:420-439; eval=True, Qc = mean head) and of
+    SMBPO.step_generator (src/smbpo.py:124-136: performance action SAMPLED with ``eps_perf``, Qc with
+    ``uncertainty=distributional_qc`` = mean + std_ratio*std, safe action in eval mode; that block is shield_type "safe").
+    Returns (actions, qc of the performance action, choice): choice = 1/0 (safe / performance action) for "safe"; the last
+    mixing step i in 0..10 whose Qc is <= threshold for "linear" (-1: none, the safe action stands; ratio = (10-i)/10)."""
+    a_perf = policy_act(w, "actor.", states, eps_perf)[0]
+
+    def qc_of(a):
+        mean, std = qc_forward(w, "constraint_critic.", states, a, need_std=uncertainty)
+        return get_qc(mean + torch.mul(std_ratio, std) if uncertainty else mean, C)       # src/ssac.py:85 ; :588-600
+    qcs = qc_of(a_perf)
+    a_safe = policy_act(w, "actor_safe.", states, None)[0]
+    A = a_perf.shape[1]
+    if shield_type == "safe":
+        danger = (qcs > threshold).tile((A, 1)).t()
+        return torch.where(danger, a_safe, a_perf), qcs, danger[:, 0].to(torch.int32)
+    if shield_type == "linear":
+        actions, choice = a_safe, torch.full((len(states),), -1, dtype=torch.int32)
+        for i in range(11):
+            ratio = (10 - i) / 10
+            mix = a_safe * ratio + a_perf * (1 - ratio)
+            safe = qc_of(mix) <= threshold
+            actions = torch.where(safe.tile((A, 1)).t(), mix, actions)
+            choice = torch.where(safe, torch.full_like(choice, i), choice)
+        return actions, qcs, choice
+    return a_perf, qcs, torch.zeros(len(states), dtype=torch.int32)
+
+
+# ----------------------------------------------------------------------------------------------
 # rollout  (src/smbpo.py:229-249)
 # ----------------------------------------------------------------------------------------------
 

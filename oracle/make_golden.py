@@ -514,6 +514,118 @@ def gen_ensemble_fit():
     np.savez_compressed(os.path.join(GOLD, "ensemble_fit.npz"), **out)
 
 
+def gen_shield():
+    """The safety shield of the batched evaluation sampler (src/sampling.py:420-439, run through the reference's own
+    sample_episodes_batched on a one-step recording env) and of the training step (src/smbpo.py:124-136, run through the
+    reference's own SMBPO.step_generator on the real PointRobot with the model fit / rollout / updates stubbed out)."""
+    import gym
+    from src.env.batch import BaseBatchedEnv
+    from src.sampling import sample_episodes_batched
+    out = {}
+    for tag, S, A, C, seed in [("point_robot", 11, 2, 1, 801), ("cartpole", 4, 1, 4, 802)]:
+        w = O.make_ssac_weights(seed, S, A, C)
+        solver = build_reference_ssac(w, S, A, C, 64, O.env_point_robot() if C == 1 else O.env_cartpole())
+        g = torch.Generator().manual_seed(seed + 1)
+        n = 96
+        states = torch.randn(n, S, generator=g) * 1.5
+
+        class Proto:
+            observation_space = gym.spaces.Box(-np.inf, np.inf, shape=(S,))
+            action_space = gym.spaces.Box(-1.0, 1.0, shape=(A,))
+            con_dim = C
+            _max_episode_steps = 1
+
+        class OneStep(BaseBatchedEnv):
+            def _reset_index(self, index):
+                return states[int(index)].clone()
+
+            def _step(self, actions):
+                self.taken = actions.clone()
+                k = len(actions)
+                return states.clone(), torch.zeros(k), torch.ones(k, dtype=torch.bool), [{"violation": False}] * k
+
+        with torch.no_grad():
+            a_perf = solver.actor.act(states, eval=True)
+            q_perf = solver._get_qc(solver.constraint_critic(states, a_perf))
+        thr = float(q_perf.median())                    # half of the performance actions are "dangerous"
+        out.update(t2n({f"{tag}.seed": seed, f"{tag}.wsum": O.weights_checksum(w), f"{tag}.states": states,
+                        f"{tag}.threshold": thr, f"{tag}.qc_perf": q_perf}))
+        for st in ("safe", "linear", "none"):
+            env = OneStep(Proto(), n)
+            with torch.no_grad():
+                sample_episodes_batched(env, solver, n, eval=True, safe_shield_threshold=thr, shield_type=st)
+            a_o, q_o, ch = O.shield_actions(w, states, C, st, thr)
+            assert torch.equal(a_o, env.taken) or maxrel(a_o, env.taken) < 1e-6, (tag, st, maxrel(a_o, env.taken))
+            print(f"shield[{tag},{st}]: oracle-vs-ref actions maxrel {maxrel(a_o, env.taken):.2e} bit-equal "
+                  f"{bool(torch.equal(a_o, env.taken))}; choices {np.bincount(ch.numpy() + 1, minlength=12).tolist()}")
+            out.update(t2n({f"{tag}.{st}.actions": env.taken}))
+
+    # ---- training-step shield: the reference's own step_generator on the real PointRobot ----
+    from src.env.point_robot import PointRobot
+    from src.env.torch_wrapper import TorchWrapper
+    from src.log import default_log as log
+    from src.smbpo import SMBPO
+    from src.checkpoint import CheckpointableData
+    log.setup(pathlib.Path(tempfile.mkdtemp()))
+    S, A, C, T = 11, 2, 1, 48
+    cfg = SMBPO.Config()
+    cfg.buffer_min = 0
+    alg = SMBPO(cfg, lambda id=None: TorchWrapper(PointRobot(id=id)), CheckpointableData(), 10)
+    ws = O.make_ssac_weights(803, S, A, C)
+    alg.solver.load_state_dict({k: v for k, v in ws.items()}, strict=False)
+    alg.update_models = lambda steps: None
+    alg.rollout_and_update = lambda: None
+    g = torch.Generator().manual_seed(804)
+    eps = torch.randn(T, A, generator=g)
+    seen = {"s": [], "a": [], "q": []}
+    real_step, real_get_qc = alg.real_env.step, alg.solver._get_qc
+
+    def step(action):
+        seen["a"].append(action.clone())
+        return real_step(action)
+
+    def get_qc(x):
+        q = real_get_qc(x)
+        seen["q"].append(q.clone())
+        return q
+    alg.real_env.step, alg.solver._get_qc = step, get_qc
+    # threshold = the median shielded Qc of a first pass, so that both branches are taken
+    def run(thr):
+        alg.safe_shield_threshold = thr
+        for k in seen:
+            seen[k].clear()
+        random.seed(11); np.random.seed(11); torch.manual_seed(11)
+        alg.steps_sampled.fill_(0)
+        with NoiseTape() as tape, torch.no_grad():
+            for t in range(T):
+                tape.normal.append(eps[t:t + 1])
+                tape.randn_like.append(None)
+            orig_reset = alg.real_env.reset
+            gen = alg.step_generator()
+            states = []
+            # the generator reads `state` right before acting: record it through policy.act1's input
+            orig_act = alg.actor.act
+
+            def act(s, eval):
+                states.append(s[0].clone())
+                return orig_act(s, eval)
+            alg.actor.act = act
+            for t in range(T):
+                next(gen)
+            alg.actor.act = orig_act
+        return torch.stack(states), torch.stack(seen["a"]), torch.cat([q.reshape(1) for q in seen["q"]])
+    _, _, q0 = run(1e9)
+    thr = float(q0.median())
+    st_s, st_a, st_q = run(thr)
+    a_o, q_o, ch = O.shield_actions(ws, st_s, C, "safe", thr, eps_perf=eps, uncertainty=True, std_ratio=alg.solver.constraint_critic.std_ratio)
+    print(f"shield[step_generator]: oracle-vs-ref actions maxrel {maxrel(a_o, st_a):.2e} qc {maxrel(q_o, st_q):.2e}; "
+          f"shielded {int(ch.sum())}/{T}")
+    out.update(t2n({"step.seed": 803, "step.wsum": O.weights_checksum(ws), "step.states": st_s, "step.eps": eps,
+                    "step.threshold": thr, "step.actions": st_a, "step.qc": st_q,
+                    "step.std_ratio": float(alg.solver.constraint_critic.std_ratio)}))
+    np.savez_compressed(os.path.join(GOLD, "shield.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.import_reference()
     torch.set_num_threads(4)
@@ -526,4 +638,5 @@ if __name__ == "__main__":
     gen_multiplier()
     gen_actor()
     gen_ensemble_fit()
+    gen_shield()
     print("golden vectors written to", GOLD)

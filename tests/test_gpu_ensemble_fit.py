@@ -1,6 +1,7 @@
 """drpo_ensemble_train_step (BatchedGaussianEnsemble.fit's loop, src/dynamics.py:143-189 - SURVEY.md section 8f "next" row 2)
 through the C ABI: normaliser fit, three Adam iterations and the holdout ranking against the reference's golden vectors; a
 larger batch against the oracle (loss, raw gradients of every tensor incl. the log-var bounds, updated parameters)."""
+import numpy as np
 import pytest
 import torch
 
@@ -77,3 +78,40 @@ def test_fit_runs_and_ranks_elites():
     losses = ens.fit(buf, steps=60)
     assert len(losses) == 60 and all(map(lambda x: x == x, losses)) and losses[-1] < losses[0]
     assert len(ens._elite_inds) == ens.num_elites and len(set(ens._elite_inds)) == ens.num_elites
+
+
+def test_fit_epochs_form_matches_the_oracle_loop():
+    """fit(epochs=...) (src/dynamics.py:186-194 -> epochal_training, src/train.py:58-101): ensemble_size x epochs shuffled passes
+    with a ragged last batch (its remainder modulo the ensemble size is dropped); per-epoch mean losses against the oracle's
+    train step run over the same permutations."""
+    from drpo_b200.sampling import ConstraintSafetySampleBuffer
+    S, A, C, n = 4, 1, 4, 2000                     # 2000 rows, batch 7 x 256 = 1792 -> batches of 1792 and 208 (= 7 x 29 + 5)
+    w = O.make_ensemble_weights(15, S, A)
+    ens = make_ensemble(w, S, A)
+    g = torch.Generator().manual_seed(16)
+    s = torch.randn(n, S, generator=g); a = torch.rand(n, A, generator=g) * 2 - 1
+    ns = s + 0.1 * a.sum(-1, keepdim=True); r = s[:, 0] * 0.5
+    buf = ConstraintSafetySampleBuffer(S, A, 4096, con_dim=C, device=dev())
+    buf.extend(states=to_dev(s), actions=to_dev(a), next_states=to_dev(ns), rewards=to_dev(r), dones=to_dev(torch.zeros(n, dtype=torch.bool)),
+               violations=to_dev(torch.zeros(n, dtype=torch.bool)), constraint_values=to_dev(torch.zeros(n, C)))
+    calls = []
+    torch.manual_seed(1234)
+    losses = ens.fit(buf, epochs=1, post_step_callback=lambda e, b, nb: calls.append((e, b, nb)))
+    assert len(losses) == ens.ensemble_size and len(calls) == 2 * ens.ensemble_size and calls[-1] == (ens.ensemble_size - 1, 1, 2)
+    # the oracle over the same permutations (torch.randperm on the CPU generator, as the reference draws them)
+    wo = {k: v.clone() for k, v in w.items()}
+    O.normalizer_fit(wo, s)
+    t = torch.cat([ns, r.unsqueeze(1)], dim=1)
+    adam = O.AdamState()
+    torch.manual_seed(1234)
+    want = []
+    for _ in range(ens.ensemble_size):
+        perm = torch.randperm(n)
+        ep = []
+        for b0 in (0, 1792):
+            idx = perm[b0:b0 + 1792]
+            ep.append(float(O.ensemble_train_step(wo, s[idx], a[idx], t[idx], adam)[0]))
+        want.append(float(np.mean(ep)))
+    assert_close(torch.tensor(losses), torch.tensor(want), 1e-4, "per-epoch mean losses")
+    with pytest.raises(ValueError):
+        ens.fit(buf)

@@ -161,3 +161,30 @@ def test_ensemble_fit(golden, tag, S, A):
     elites, losses = O.ensemble_holdout_ranking(w, states[hold], actions[hold], targets[hold])
     close(losses, g[f"{tag}.holdout_losses"], rtol=1e-5)
     assert elites == [int(x) for x in g[f"{tag}.elites"]]
+
+
+# ---- safety shield ----------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,S,A,C", [("point_robot", 11, 2, 1), ("cartpole", 4, 1, 4)])
+@pytest.mark.parametrize("shield_type", ["safe", "linear", "none"])
+def test_shield_eval_bit_exact(golden, tag, S, A, C, shield_type):
+    """sample_episodes_batched's action selection (src/sampling.py:420-439), recorded from the reference itself."""
+    g = golden("shield")
+    w = O.make_ssac_weights(int(g[f"{tag}.seed"]), S, A, C)
+    assert abs(O.weights_checksum(w) - float(g[f"{tag}.wsum"])) < 1e-6
+    a, q, choice = O.shield_actions(w, T(g[f"{tag}.states"]), C, shield_type, float(g[f"{tag}.threshold"]))
+    assert np.array_equal(a.numpy(), g[f"{tag}.{shield_type}.actions"])
+    close(q, g[f"{tag}.qc_perf"])
+    if shield_type == "safe":
+        assert 0 < int(choice.sum()) < len(choice)              # both branches are exercised
+
+
+def test_shield_training_step(golden):
+    """SMBPO.step_generator's shield (src/smbpo.py:124-136) over 48 consecutive real-env steps of the reference."""
+    g = golden("shield")
+    w = O.make_ssac_weights(int(g["step.seed"]), 11, 2, 1)
+    a, q, choice = O.shield_actions(w, T(g["step.states"]), 1, "safe", float(g["step.threshold"]), eps_perf=T(g["step.eps"]),
+                                    uncertainty=True, std_ratio=float(g["step.std_ratio"]))
+    close(q, g["step.qc"], rtol=1e-5, atol=1e-5)
+    margin = np.abs(g["step.qc"] - g["step.threshold"]) > 1e-4     # the reference ran row by row: decisions away from the threshold
+    close(a[T(margin)], g["step.actions"][margin], rtol=1e-5, atol=1e-5)
+    assert 0 < int(choice.sum()) < len(choice)
