@@ -292,6 +292,9 @@ def run_ours(args):
     # ---- ensemble training iterations/s (BatchedGaussianEnsemble.fit's loop body): replicas only ----------
     if not args.skip_critic:
         out["ensemble_fit"] = bench_ensemble_fit(args, alg, workload, device, world == 1 and not args.skip_cpu)
+    # ---- safety shield latency: latency-bound, rank 0's replica only ------------------------------------
+    if not args.skip_critic:
+        out["shield"] = bench_shield(alg, workload, device, world == 1 and not args.skip_cpu)
     # ---- CPU baseline (oracle port) on rank 0, N=1 only --------------------------------------------------------------
     if world == 1 and not args.skip_cpu:
         out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=5)
@@ -461,6 +464,48 @@ def bench_ensemble_fit(args, alg, workload, device, with_cpu):
         dt = (time.perf_counter() - t0) / reps
         res["cpu_baseline"] = {"value": 1.0 / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
                                "sample": f"{reps} x oracle ensemble_train_step at {n} rows ({workload} dims), torch CPU fp32 autograd, {threads} threads"}
+    return res
+
+
+def bench_shield(alg, workload, device, with_cpu):
+    """Latency of one shielded action selection: the training step's switch on one state (src/smbpo.py:124-136) and the
+    evaluation sampler's linear shield on the 10 evaluation envs (src/sampling.py:420-439, N_EVAL_TRAJ = 10)."""
+    from drpo_b200 import _lib, synthetic
+    lib = _lib.load()
+    _, S, A, C = synthetic.WORKLOADS[workload]
+    solver = alg.solver
+    g = torch.Generator().manual_seed(12)
+    s1, s10 = torch.randn(1, S, generator=g), torch.randn(10, S, generator=g)
+    d1, d10 = s1.to(device), s10.to(device)
+    cases = {"train_step_1_state": lambda: solver.shield_act(d1, eval=False, shield_type="safe", safe_shield_threshold=-0.1, uncertainty=True),
+             "eval_linear_10_envs": lambda: solver.shield_act(d10, eval=True, shield_type="linear", safe_shield_threshold=-0.05)}
+    res = {"metric": "shielded_action_latency", "unit": "us/call", "higher_is_better": False, "dtype": "f32", "scaling": "replicas only"}
+    for name, fn in cases.items():
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        k, l0 = 200, lib.drpo_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            a = fn()
+        a.cpu()                                        # the env needs the action on the host: the read-back is part of the latency
+        dt = (time.perf_counter() - t0) / k
+        res[name] = {"value": dt * 1e6, "gpu_launches_per_call": (lib.drpo_launch_count() - l0) / k}
+    if with_cpu:
+        from oracle import drpo_oracle as O
+        w = synthetic.make_ssac_weights(64578, S, A, C)
+        torch.set_num_threads(4)                       # the reference's own setting for this host-side path (src/cli.py:108)
+        eps = torch.randn(1, A, generator=g)
+        for name, fn in (("train_step_1_state", lambda: O.shield_actions(w, s1, C, "safe", -0.1, eps_perf=eps, uncertainty=True)),
+                         ("eval_linear_10_envs", lambda: O.shield_actions(w, s10, C, "linear", -0.05))):
+            with torch.no_grad():
+                fn()
+                t0, reps = time.perf_counter(), 50
+                for _ in range(reps):
+                    fn()
+            res[name]["cpu_baseline"] = {"value": (time.perf_counter() - t0) / reps * 1e6, "unit": "us/call", "cores": 4, "kind": "port",
+                                         "sample": f"{reps} x oracle shield_actions, torch CPU fp32, 4 threads"}
+        torch.set_num_threads(os.cpu_count() or 1)
     return res
 
 

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrpo_sm100.so")
+LIB_PATH = os.environ.get("DRPO_B200_LIB") or os.path.join(_HERE, "libdrpo_sm100.so")      # override: kernel experiments only
 
 PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 ENV_POINT_ROBOT, ENV_BOUNDED, ENV_TRACKING = 0, 1, 2
@@ -153,7 +153,7 @@ class ShieldArgs(C.Structure):
         ("actor", C.POINTER(Mlp3)), ("actor_safe", C.POINTER(Mlp3)), ("qc", C.POINTER(Qc)), ("states", C.c_void_p), ("n", C.c_int64),
         ("state_dim", C.c_int32), ("action_dim", C.c_int32), ("con_dim", C.c_int32), ("shield_type", C.c_int32),
         ("eval_perf", C.c_int32), ("uncertainty", C.c_int32), ("std_ratio", C.c_float), ("threshold", C.c_float),
-        ("noise_perf", C.POINTER(Noise)), ("actions", C.c_void_p), ("qc_perf", C.c_void_p), ("choice", C.c_void_p),
+        ("noise_perf", C.POINTER(Noise)), ("actions", C.c_void_p), ("qc_perf", C.c_void_p), ("choice", C.c_void_p), ("path", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
     ]
 

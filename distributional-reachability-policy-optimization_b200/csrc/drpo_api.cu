@@ -229,10 +229,40 @@ int drpo_shield_act(const drpo_shield_args* a) {
   DRPO_CHECK_ARG(a->actor->l0.in_dim == S && a->actor->l2.out_dim == 2 * A, "drpo_shield_act: actor dims do not match");
   DRPO_CHECK_ARG(C >= 1 && C <= DRPO_MAX_CON, "drpo_shield_act: con_dim out of range");
   if (n == 0) return DRPO_OK;
-  if (a->shield_type == DRPO_SHIELD_NONE) {
+  DRPO_CHECK_ARG(a->path >= 0 && a->path <= 2, "drpo_shield_act: path must be 0 (auto), 1 (latency kernels) or 2 (batched)");
+  const int n_mix_all = a->shield_type == DRPO_SHIELD_LINEAR ? SHIELD_MIX : (a->shield_type == DRPO_SHIELD_SAFE ? 1 : 0);
+  const bool fits = a->actor->l0.out_dim <= SHIELD_FUSED_THREADS && a->actor->l1.out_dim <= SHIELD_FUSED_THREADS && S + A <= SHIELD_FUSED_THREADS &&
+                    (n_mix_all == 0 || (a->qc && a->qc->trunk0.out_dim <= SHIELD_FUSED_THREADS && a->actor_safe &&
+                                        a->actor_safe->l0.out_dim <= SHIELD_FUSED_THREADS && a->actor_safe->l1.out_dim <= SHIELD_FUSED_THREADS));
+  DRPO_CHECK_ARG(a->path != 1 || fits, "drpo_shield_act: the latency kernels need hidden widths <= %d", SHIELD_FUSED_THREADS);
+  const bool fused = a->path == 1 || (a->path == 0 && fits && (int64_t)std::max(n_mix_all, 1) * n <= SHIELD_FUSED_MAX_ROWS);
+  if (a->shield_type == DRPO_SHIELD_NONE && !fused) {
     if ((rc = drpo_policy_act(a->actor, a->states, n, a->eval_perf, a->noise_perf, a->actions, nullptr, DRPO_PREC_FP32, a->workspace,
                               a->workspace_bytes, a->stream))) return rc;
     if (a->choice) DRPO_CUDA_OK(cudaMemsetAsync(a->choice, 0, n * sizeof(int32_t), (cudaStream_t)a->stream));
+    return DRPO_OK;
+  }
+  if (a->shield_type != DRPO_SHIELD_NONE) {
+    if ((rc = check_mlp3(a->actor_safe, "drpo_shield_act(actor_safe)"))) return rc;
+    if ((rc = check_qc(a->qc, "drpo_shield_act"))) return rc;
+    DRPO_CHECK_ARG(a->actor_safe->l0.in_dim == S && a->actor_safe->l2.out_dim == 2 * A, "drpo_shield_act: actor_safe dims do not match");
+    DRPO_CHECK_ARG(a->qc->trunk0.in_dim == S + A && a->qc->mean1.out_dim == C, "drpo_shield_act: constraint critic dims do not match");
+  }
+  if (fused) {
+    Arena ar(a->workspace, a->workspace_bytes);
+    ShieldFusedArgs f;
+    f.actor = *a->actor; f.actor_safe = n_mix_all ? *a->actor_safe : *a->actor; if (n_mix_all) f.qc = *a->qc; else f.qc = drpo_qc{};
+    f.states = a->states; f.n = (int)n; f.S = S; f.A = A; f.C = C; f.n_mix = n_mix_all; f.eval_perf = a->eval_perf; f.uncertainty = a->uncertainty;
+    f.std_ratio = a->std_ratio; f.threshold = a->threshold; f.ratios = shield_ratios();
+    f.noise = a->noise_perf ? make_noise(a->noise_perf->eps, a->noise_perf->row_stride, a->noise_perf->seed, a->noise_perf->stream_tag, a->noise_perf->step)
+                            : make_noise(nullptr, 0, 0, 0, 0);
+    f.a_perf = ar.take<float>(n * A); f.a_safe = ar.take<float>(n * A); f.qrow = ar.take<float>((int64_t)std::max(n_mix_all, 1) * n);
+    f.done_cnt = n_mix_all ? ar.take<int32_t>(n) : nullptr;
+    f.actions = a->actions; f.qc_perf = a->qc_perf; f.choice = a->choice;
+    if (!ar.ok()) { set_error("drpo_shield_act: workspace too small"); return DRPO_ERR_WORKSPACE; }
+    DRPO_LAUNCH(shield_policy_kernel, dim3((unsigned)n, n_mix_all ? 2 : 1), SHIELD_FUSED_THREADS, 0, a->stream, f);
+    if (n_mix_all) DRPO_LAUNCH(shield_qc_select_kernel, (unsigned)(n_mix_all * n), SHIELD_FUSED_THREADS, 0, a->stream, f);
+    else if (a->choice) DRPO_CUDA_OK(cudaMemsetAsync(a->choice, 0, n * sizeof(int32_t), (cudaStream_t)a->stream));
     return DRPO_OK;
   }
   if ((rc = check_mlp3(a->actor_safe, "drpo_shield_act(actor_safe)"))) return rc;

@@ -409,12 +409,13 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         return qc_con_dim
 
     def shield_act(self, states, eval=True, shield_type="linear", safe_shield_threshold=-0.1, uncertainty=False, eps=None,
-                   return_info=False):
+                   return_info=False, path=0):
         """The safety shield in one C-ABI call (drpo_shield_act): the action-selection block of sample_episodes_batched
         (src/sampling.py:420-439: ``eval=True``, Qc = mean head, shield_type "safe" / "linear" / anything else = none) and of
         SMBPO.step_generator (src/smbpo.py:124-136: ``eval=False`` samples the performance action, ``uncertainty`` =
         distributional_qc, shield_type "safe").  The safe actor always acts in eval mode, as at both call sites.
-        ``return_info`` adds (_get_qc of the performance action, choice) - see include/drpo_b200.h."""
+        ``return_info`` adds (_get_qc of the performance action, choice) - see include/drpo_b200.h.  ``path``: 0 = auto (two-launch
+        latency kernels for small batches, batched GEMM path for large ones), 1 / 2 force one of them."""
         lib = _lib.load()
         states = states.contiguous().float()
         n, A = states.shape[0], self.action_dim
@@ -431,7 +432,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self.actor._noise_step += 1
         noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, A, self.actor.noise_seed, 17, self.actor._noise_step)
         a.noise_perf = C_pointer(noise)
-        a.actions, a.qc_perf, a.choice = _lib.ptr(actions), _lib.ptr(qc_perf), _lib.ptr(choice)
+        a.actions, a.qc_perf, a.choice, a.path = _lib.ptr(actions), _lib.ptr(qc_perf), _lib.ptr(choice), int(path)
         ws = self._ws.get(lib.drpo_shield_workspace_bytes(a.actor, n, self.state_dim, A, self.con_dim, self.constraint_critic.hidden_dim),
                           states.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()

@@ -399,6 +399,8 @@ typedef struct drpo_shield_args {
   float* actions;                  /* out [n,A] */
   float* qc_perf;                  /* out [n] or NULL */
   int32_t* choice;                 /* out [n] or NULL */
+  int32_t path;                    /* 0 = auto: the two-launch latency kernels up to 256 candidate rows (1 state per training
+                                      step, 10 evaluation envs), else the batched GEMM path; 1 / 2 force one of them */
   void* workspace; int64_t workspace_bytes;
   void* stream;
 } drpo_shield_args;

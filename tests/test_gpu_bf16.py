@@ -79,11 +79,13 @@ def test_layer_accumulators(tag, S, A, C, B):
     print(tag, " ".join(report))
 
 
-@pytest.mark.parametrize("tag,S,A,C,B", [("quadrotor", 12, 2, 2, 5000), ("cartpole", 4, 1, 4, 3000), ("point_robot", 11, 2, 1, 2000)])
+@pytest.mark.parametrize("tag,S,A,C,B", [("quadrotor", 12, 2, 2, 5000), ("cartpole", 4, 1, 4, 3000), ("point_robot", 11, 2, 1, 2000),
+                                         ("tracking", 51, 2, 1, 1500), ("safetygym60", 60, 2, 1, 1500)])
 def test_bf16_rollout_vs_oracle(tag, S, A, C, B):
     """Step 0 of the bf16 rollout against the fp32 oracle: values within 2e-2; masks may differ only where the
     constraint margin is below that tolerance.  Later steps: the alive counts track the oracle's closely."""
-    spec, H = {"quadrotor": O.env_quadrotor(), "cartpole": O.env_cartpole(), "point_robot": O.env_point_robot()}[tag], 10
+    spec, H = {"quadrotor": O.env_quadrotor(), "cartpole": O.env_cartpole(), "point_robot": O.env_point_robot(),
+               "tracking": O.env_tracking(10, 1), "safetygym60": O.env_safetygym60()}[tag], 10
     wm, ws = O.make_ensemble_weights(31, S, A, diff_scale=0.05), O.make_ssac_weights(32, S, A, C)
     g = torch.Generator().manual_seed(33)
     init = torch.randn(B, S, generator=g) * 0.3
@@ -109,8 +111,16 @@ def test_bf16_rollout_vs_oracle(tag, S, A, C, B):
         assert abs(a - b) <= max(3, 0.02 * b), (got_counts, counts)
     # the masks stored are exactly the hooks of the stored next_states (bit-exact self-consistency)
     d, v, cv = O.hooks(spec, out["next_states"].cpu().numpy())
-    assert np.array_equal(d, out["dones"].cpu().numpy()) and np.array_equal(v, out["violations"].cpu().numpy())
-    assert np.array_equal(cv.reshape(-1), out["constraint_values"].cpu().numpy().reshape(-1))
+    got_cv = out["constraint_values"].cpu().numpy().reshape(-1)
+    assert np.array_equal(d, out["dones"].cpu().numpy())
+    if tag == "tracking":
+        # numpy's fp32 sin/cos are not reproduced bit for bit by CUDA's (tests/test_gpu_parity.py::test_hooks_tracking): 1e-5
+        assert np.abs(cv.reshape(-1) - got_cv).max() <= 1e-5
+        clear = np.abs(cv.reshape(len(v), -1)).min(axis=1) > 1e-5
+        assert np.array_equal(v[clear], out["violations"].cpu().numpy()[clear])
+    else:
+        assert np.array_equal(v, out["violations"].cpu().numpy())
+        assert np.array_equal(cv.reshape(-1), got_cv)
 
 
 def _philox_alg(spec, S, A, C, B, H, buffer_max=None, seed=0x5EED):

@@ -13,7 +13,7 @@ T = torch.from_numpy
 RTOL = 1e-5
 
 SPECS = {"point_robot": O.env_point_robot(), "cartpole": O.env_cartpole(), "quadrotor": O.env_quadrotor(),
-         "tracking1": O.env_tracking(10, 1), "tracking4": O.env_tracking(10, 4)}
+         "tracking1": O.env_tracking(10, 1), "tracking4": O.env_tracking(10, 4), "safetygym60": O.env_safetygym60()}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -160,7 +160,8 @@ def test_rollout_vs_golden(golden):
         assert_close(out[k], g[f"out.{k}"], RTOL, k)
 
 
-@pytest.mark.parametrize("tag,S,A,C,B", [("cartpole", 4, 1, 4, 3000), ("quadrotor", 12, 2, 2, 5000), ("point_robot", 11, 2, 1, 2500)])
+@pytest.mark.parametrize("tag,S,A,C,B", [("cartpole", 4, 1, 4, 3000), ("quadrotor", 12, 2, 2, 5000), ("point_robot", 11, 2, 1, 2500),
+                                         ("tracking1", 51, 2, 1, 1500), ("safetygym60", 60, 2, 1, 1500)])
 def test_rollout_vs_oracle(tag, S, A, C, B):
     """Free-running H=10 rollout with injected noise: per-step alive counts and total transition count equal, masks
     bit-exact, values within 1e-5; a divergence would have to be explained by a sub-tolerance margin at a boundary."""
