@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("DRPO_B200_LIB") or os.path.join(_HERE, "libdrpo_sm100.so")      # override: kernel experiments only
+LIB_PATH = os.path.join(_HERE, "libdrpo_sm100.so")
 
 PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 ENV_POINT_ROBOT, ENV_BOUNDED, ENV_TRACKING = 0, 1, 2
