@@ -132,3 +132,26 @@ def test_shield_edge_cases(path):
     assert torch.isnan(q[1]) and int(ch[1]) == 0
     _, q, ch = solver.shield_act(to_dev(s_nan), shield_type="linear", safe_shield_threshold=0.0, return_info=True, path=path)
     assert int(ch[1]) == -1
+
+
+def test_smbpo_shielded_act1_mirrors_the_training_step(golden):
+    """SMBPO.shielded_act1 (src/smbpo.py:124-136) on single states of the reference's recorded episode; safe_shield off = act1."""
+    import drpo_b200
+    from tests.util import dev
+    g = golden("shield")
+    S, A, C = 11, 2, 1
+    cfg = drpo_b200.SMBPO.Config()
+    cfg.buffer_max, cfg.safe_shield_threshold = 4096, float(g["step.threshold"])
+    alg = drpo_b200.SMBPO(cfg, drpo_b200.device_env("point-robot"), device=dev())
+    alg.solver.load_state_dict(O.make_ssac_weights(int(g["step.seed"]), S, A, C), strict=False)
+    assert float(alg.solver.constraint_critic.std_ratio) == float(g["step.std_ratio"])
+    s, eps = to_dev(g["step.states"]), to_dev(g["step.eps"])
+    clear = np.abs(g["step.qc"] - float(g["step.threshold"])) > MARGIN
+    for r in range(0, len(s), 5):
+        a = alg.shielded_act1(s[r], eps=eps[r:r + 1])
+        assert a.shape == (A,)
+        if clear[r]:
+            assert_close(a.cpu(), torch.from_numpy(g["step.actions"][r]), RTOL, f"step {r}")
+    alg.safe_shield = False
+    a = alg.shielded_act1(s[0], eps=eps[0:1])
+    assert_close(a, alg.actor.act(s[0:1], False, eps[0:1])[0], RTOL, "unshielded act1")
