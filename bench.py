@@ -30,6 +30,9 @@ CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload, from the
 # `ncu --set full` capture summarised in profiles/r1_rollout.md (null when no capture exists for the workload)
 TRAFFIC_BYTES_PER_LAUNCH = {"quadrotor": 164961024}
+# the same for one critic_fused_kernel launch at B = 65 536, tracking dims (profiles/r1_ncu_full_critic_fused_64k_raw.csv:
+# 44.2 MB read + 378.2 MB written: the saved bf16 activations the dW kernel consumes)
+CRITIC_TRAFFIC_BYTES_PER_LAUNCH = {("tracking", 65536): 422400000}
 
 
 def flops_per_transition(S, A):
@@ -350,7 +353,9 @@ def bench_critic(args, device, world, rank, pk):
                      "tf32": "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer", "fp32": "f32"}[cprec],
            "gpu_launches": int(lib.drpo_launch_count() - l0), "loss_q": float(lq), "loss_c": float(lc),
            "roofline": {"bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                        "frac": round(ach / pk["tensor_sustained"], 5), "traffic": None,
+                        "frac": round(ach / pk["tensor_sustained"], 5),
+                        "traffic": CRITIC_TRAFFIC_BYTES_PER_LAUNCH.get((CRITIC_WORKLOAD, B)) if cprec == "bf16" else None,
+                        "kernel": "critic_fused_kernel (traffic) ; achieved = whole update incl. dW, reductions, clip/Adam/EMA",
                         "algorithmic_flops_per_sample": flops_per_critic_sample(S, A, C)}}
     if world == 1 and not args.skip_cpu:
         res["cpu_baseline"] = cpu_critic_baseline(args.cpu_critic_batch)
