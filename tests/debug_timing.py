@@ -19,9 +19,10 @@ st = out.flatten().view(torch.int32).cpu().numpy().astype("int64").reshape(-1, 8
 names = ["P1"] * 4 + ["P2"] * 4 + ["P3"] + ["M1"] * 4 + ["M2"] * 4 + ["D0"] * 4 + ["L0"] * 4 + ["D1", "L1"]
 for tile in range(1, 3):
     t0 = st[tile, 0, 6]
-    print(f"tile {tile}: E0 {st[tile,0,7]-t0} cycles; next tile E0 starts at {st[tile+1,0,6]-t0}")
-    print(" slab      mma_deps_ok weights_ok  issued | epi_wait_begin acc_ready epi_done")
+    print(f"tile {tile}: prologue {st[tile,0,7]-t0} cycles; next tile's prologue starts at {st[tile+1,0,6]-t0}")
+    print(" chunk      loop_top drained weights token issued | epi_wait acc_ready epi_done")
     for c in range(27):
         r = st[tile, c] - t0
-        inner = f" ld {r[6]-r[1]} math {r[7]-r[6]} st+arrive {r[2]-r[7]}" if c > 0 else ""
-        print(f" {c:2d} {names[c]:3s} {r[3]:10d} {r[4]:10d} {r[5]:8d} | {r[0]:12d} {r[1]:9d} {r[2]:8d}   (mma wait {r[1]-r[5]}, epi {r[2]-r[1]}{inner})")
+        top = r[6] if c > 0 else -1
+        wts = r[7] if c > 0 else -1
+        print(f" {c:2d} {names[c]:3s} {top:8d} {r[3]:8d} {wts:8d} {r[4]:8d} {r[5]:8d} | {r[0]:8d} {r[1]:8d} {r[2]:8d}")
