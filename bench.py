@@ -27,9 +27,10 @@ import torch  # noqa: E402
 HORIZON = 10
 DEFAULT_B0 = {"quadrotor": 1_000_000, "cartpole-move": 100_000, "safetygym-point-synthetic": 400_000, "point-robot": 100_000}
 CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
-# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload, from the
-# `ncu --set full` capture summarised in profiles/r1_rollout.md (null when no capture exists for the workload)
-TRAFFIC_BYTES_PER_LAUNCH = {"quadrotor": 164961024}
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload (1 M rows), from the
+# `ncu --set full` capture of the final round-1 kernel (profiles/r1_ncu_full_rollout_step_1M_final_raw.csv: 52.9 MB read + 17.2 MB
+# written - 48 MB of states in; most of the 60 MB of outputs is still in L2 when the kernel ends); null when no capture exists
+TRAFFIC_BYTES_PER_LAUNCH = {"quadrotor": 70104064}
 # the same for one critic_fused_kernel launch at B = 65 536, tracking dims (profiles/r1_ncu_full_critic_fused_64k_raw.csv:
 # 44.2 MB read + 378.2 MB written: the saved bf16 activations the dW kernel consumes)
 CRITIC_TRAFFIC_BYTES_PER_LAUNCH = {("tracking", 65536): 422400000}
