@@ -104,14 +104,30 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
     def _trainable(self):
         return [*self.trunk.parameters(), *self.diff_head.parameters(), *self.log_var_head.parameters(), self.min_log_var, self.max_log_var]
 
+    def _apply(self, fn, *args, **kwargs):
+        """``.to()`` / ``.cuda()`` replace parameter storage: re-validate the arena and rebuild the cached struct on next use."""
+        out = super()._apply(fn, *args, **kwargs)
+        self._arena_checked, self._struct = False, None
+        return out
+
     def _ensure_arena(self):
         from .ssac import _arena_ok, _flatten_into_arena
+        if getattr(self, "_arena_checked", False):
+            # steady state: the first and last trainable tensor still sit where the arena put them (two data_ptr() calls instead of
+            # the full walk, which costs a sizeable part of a 0.4 ms training iteration)
+            a0, n = self._arena.data_ptr(), 4 * self._arena.numel()
+            first, last = self._sentinels
+            if first.data_ptr() == a0 and a0 <= last.data_ptr() and last.data_ptr() + 4 * last.numel() <= a0 + n:
+                return
+        self._struct = None
         if not _arena_ok(self._arena, self._trainable()):
             self._arena = _flatten_into_arena(self._trainable())
             opt = self.optimizer
             if opt.m.device != self._arena.device:
                 opt.m, opt.v, opt.grad = opt.m.to(self._arena.device), opt.v.to(self._arena.device), opt.grad.to(self._arena.device)
             self._fit_losses = self._fit_losses.to(self._arena.device)
+        tr = self._trainable()
+        self._sentinels, self._arena_checked = (tr[0], tr[-1]), True
 
     def arena_views(self, arena):
         """name -> view of ``arena`` (parameter / gradient / Adam arena) in the order of ``_trainable``."""
@@ -129,14 +145,17 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         return self.ensemble_size * self.batch_size
 
     def as_struct(self) -> "_lib.Ensemble":
+        if getattr(self, "_struct", None) is not None and getattr(self, "_arena_checked", False):
+            return self._struct
         p = _lib.ptr
-        return _lib.Ensemble(
+        self._struct = _lib.Ensemble(
             self.state_dim, self.action_dim, self.ensemble_size, self.hidden_dim,
             p(self.state_normalizer.mean), p(self.state_normalizer.std), p(self.min_log_var.data), p(self.max_log_var.data),
             p(self.trunk[0].weight.data), p(self.trunk[0].bias.data), p(self.trunk[2].weight.data), p(self.trunk[2].bias.data),
             p(self.diff_head[0].weight.data), p(self.diff_head[0].bias.data), p(self.diff_head[2].weight.data),
             p(self.diff_head[2].bias.data), p(self.log_var_head[0].weight.data), p(self.log_var_head[0].bias.data),
             p(self.log_var_head[2].weight.data), p(self.log_var_head[2].bias.data), None)
+        return self._struct
 
     def _workspace(self, lib, ens, batch, device):
         return self._ws.get(lib.drpo_ensemble_workspace_bytes(ens, batch), device)

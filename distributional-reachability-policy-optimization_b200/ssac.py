@@ -355,7 +355,24 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self._n_qc = total - self._n_q
         self._structs = None
 
+    def _apply(self, fn, *args, **kwargs):
+        """``.to()`` / ``.cuda()`` / ``.float()`` replace parameter storage: re-validate the arenas and rebuild the structs on next use."""
+        out = super()._apply(fn, *args, **kwargs)
+        self._arenas_checked, self._structs = False, None
+        return out
+
+    def _arena_sentinels_ok(self):
+        """First and last parameter of every arena still sit where the arena put them (a few data_ptr() calls instead of the ~60 of the
+        full check, which cost ~0.1 ms per update - as much as the GPU work of a small-batch step)."""
+        for arena, first, last in self._sentinels:
+            if first.data_ptr() != arena.data_ptr() or last.data_ptr() + 4 * last.numel() > arena.data_ptr() + 4 * arena.numel() \
+                    or last.data_ptr() < arena.data_ptr():
+                return False
+        return True
+
     def _ensure_arenas(self):
+        if getattr(self, "_arenas_checked", False) and self._structs is not None and self._arena_sentinels_ok():
+            return self._structs
         if not (_arena_ok(self._critic_arena, self._critic_params()) and _arena_ok(self._target_arena, self._target_params())
                 and _arena_ok(self._mult_arena, list(self.multiplier.parameters()))
                 and _arena_ok(self._actor_arena, list(self.actor.parameters()))
@@ -365,6 +382,11 @@ class SSAC(Configurable, BasePolicy, nn.Module):
             for opt, arena in zip(old, (self._critic_arena, self._mult_arena, self._actor_arena, self._safe_arena)):
                 if opt.m.device != arena.device:
                     opt.m, opt.v, opt.grad = opt.m.to(arena.device), opt.v.to(arena.device), opt.grad.to(arena.device)
+        groups = ((self._critic_arena, self._critic_params()), (self._target_arena, self._target_params()),
+                  (self._mult_arena, list(self.multiplier.parameters())), (self._actor_arena, list(self.actor.parameters())),
+                  (self._safe_arena, list(self.actor_safe.parameters())))
+        self._sentinels = [(arena, ps[0], ps[-1]) for arena, ps in groups]
+        self._arenas_checked = True
         if self._structs is None:
             self._structs = dict(
                 actor=self.actor.as_struct(), actor_safe=self.actor_safe.as_struct(),
@@ -383,7 +405,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
 
     def invalidate_structs(self):
         """Call after replacing parameter storage by hand (``load_state_dict`` copies in place and needs nothing)."""
-        self._structs = None
+        self._structs, self._arenas_checked = None, False
 
     # ---- reference API -------------------------------------------------------------------------------------
     def act(self, states, eval):
@@ -423,7 +445,10 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         qc_perf = torch.empty((n,), device=states.device) if return_info else None
         choice = torch.empty((n,), dtype=torch.int32, device=states.device) if return_info else None
         a = _lib.ShieldArgs()
-        actor, safe, qc = self.actor.as_struct(), self.actor_safe.as_struct(), self.constraint_critic.as_struct()
+        # the network structs are cached with the update steps' (parameters are views of flat arenas): on a 1-row call building
+        # them costs more than the two launches
+        st = self._ensure_arenas()
+        actor, safe, qc = st["actor"], st["actor_safe"], st["qc"]
         a.actor, a.actor_safe, a.qc = C_pointer(actor), C_pointer(safe), C_pointer(qc)
         a.states, a.n, a.state_dim, a.action_dim, a.con_dim = _lib.ptr(states), n, self.state_dim, A, self.con_dim
         a.shield_type = _lib.SHIELD_TYPES.get(shield_type, _lib.SHIELD_NONE)
