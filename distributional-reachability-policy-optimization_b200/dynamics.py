@@ -221,7 +221,9 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         samples = means + stds * (torch.randn_like(means) if eps is None else eps)
         return samples[:, :, :-1], samples[:, :, -1]
 
-    # ---- training of the ensemble: SURVEY.md §8f "next" row 2 — host-side torch for now ------------------------
+    # ---- training of the ensemble: SURVEY.md §8f "next" row 2 -------------------------------------------------------------
+    # _mse_loss / compute_loss are public in the reference and return differentiable losses: the torch expressions below mirror
+    # them for callers that bring their own optimiser.  fit() / train_step() do NOT use them: they run drpo_ensemble_train_step.
     def _forward_all_torch(self, states, actions):
         x = torch.cat([self.state_normalizer(states), actions], dim=-1)
         h = self.trunk(x)

@@ -32,7 +32,8 @@ class SquashedGaussianPolicy(BasePolicy, nn.Module):
                          _lib.linear_of(n[4].weight.data, n[4].bias.data), None)
 
     def mu_std(self, states):
-        """Differentiable torch form of _distr (src/policy.py:89-96); used by the not-yet-native actor update."""
+        """Differentiable torch form of _distr (src/policy.py:89-96) for callers that need autograd through the policy
+        (``SSAC.actor_loss``); ``act`` and the update steps go through the C ABI."""
         mu, raw = self.net(states).chunk(2, dim=-1)
         log_std = -6.0 + 10.0 * torch.sigmoid(raw)
         return mu, log_std.exp()

@@ -112,7 +112,8 @@ class ConstraintCritic(Configurable, nn.Module):
                        lin(l[0].weight.data, l[0].bias.data), lin(l[2].weight.data, l[2].bias.data))
 
     def forward_torch(self, state, action, uncertainty=False, sample=False):
-        """Differentiable torch form (used only by the not-yet-native actor update)."""
+        """Differentiable torch form for callers that backpropagate through the constraint critic themselves (``actor_loss``); the
+        update steps and every no-grad call go through the C ABI."""
         h = self.trunk(torch.cat([state, action], -1))
         mean = self.mean_head(h)
         if (not uncertainty) and (not sample):
@@ -566,9 +567,10 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self.multiplier_lr_scheduler.step()
         return self._losses[4].clone()
 
-    # ---- SURVEY §8f "next" row 1: actor / alpha update — eager torch autograd for now ---------------------------
+    # ---- SURVEY §8f "next" row 1: actor / alpha update ------------------------------------------------------------
     def actor_loss(self, obs, include_alpha=True):
-        """src/ssac.py:458-505."""
+        """src/ssac.py:458-505 as a differentiable expression (the reference exposes it and callers may backpropagate through the
+        returned losses).  API mirror only: ``update_actor_and_alpha`` below does NOT use it - the update runs in drpo_actor_step."""
         def rsample(pol):
             mu, std = pol.mu_std(obs)
             x = mu + std * torch.randn_like(mu)
