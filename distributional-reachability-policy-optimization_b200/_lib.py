@@ -164,6 +164,7 @@ SYMBOLS = [
     ("drpo_abi_version", C.c_int, []),
     ("drpo_launch_count", C.c_int64, []),
     ("drpo_kernel_status", C.c_int, []),
+    ("drpo_kernel_status_peek", C.c_int, []),
     ("drpo_timing_enable", None, [C.c_int32]),
     ("drpo_timing_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     ("drpo_philox_normal", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
@@ -216,7 +217,7 @@ def load():
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = restype, argtypes
-    if lib.drpo_abi_version() != 1:
+    if lib.drpo_abi_version() != 2:
         raise RuntimeError("libdrpo_sm100.so ABI version mismatch")
     _lib = lib
     return lib
@@ -233,6 +234,17 @@ def check_kernel_status(what):
     code = lib.drpo_kernel_status()
     if code != 0:
         raise RuntimeError(f"{what}: {lib.drpo_last_error().decode()}")
+
+
+def peek_kernel_status(what):
+    """Non-blocking: raise if any earlier bf16 launch has reported a watchdog time-out (sticky pinned status words).  Called at
+    the top of every update / rollout call, so a failure surfaces at the next call after the failing kernel completed."""
+    lib = load()
+    if lib.drpo_kernel_status_peek() != 0:
+        raise RuntimeError(f"{what}: {lib.drpo_last_error().decode()}")
+
+
+LOSSES_LEN, LOSS_ERR_SLOT = 16, 15
 
 
 def ptr(t):

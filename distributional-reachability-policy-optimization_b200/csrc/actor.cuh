@@ -175,6 +175,7 @@ static inline int actor_step_fp32(const drpo_actor_args& a) {
   const float inv_bg = (float)(1.0 / (double)a.global_batch_size);
 
   if (a.phases & 1) {
+    DRPO_CUDA_OK(cudaMemsetAsync(a.losses + DRPO_LOSS_ERR_SLOT, 0, sizeof(float), (cudaStream_t)stream));   // watchdog slot: no fused kernel on this path
     // ---- forward ------------------------------------------------------------------------------------------------------
     // action = actor.distr(obs).rsample(), log_prob                                  src/ssac.py:459-461
     if ((rc = mlp3_fwd(a.actor, a.obs, S, (int)B, ACT_RELU, ahA, ahB, apout, nullptr, stream))) return rc;
@@ -231,13 +232,13 @@ static inline int actor_step_fp32(const drpo_actor_args& a) {
     DRPO_LAUNCH(clip_coef_kernel, 1, 32, 0, stream, nrm_part, nb, (float)a.grad_norm, a.losses + 3, coef);
     AdamScalars s = adam_scalars(a.adam_actor, 0.0);
     DRPO_LAUNCH(adam_ema_kernel, grid_for(a.n_actor), 256, 0, stream, a.params_actor, a.grads_actor, a.m_actor, a.v_actor, (float*)nullptr,
-                a.n_actor, a.n_actor, coef, s);
+                a.n_actor, a.n_actor, coef, s, (const float*)(a.losses + DRPO_LOSS_ERR_SLOT));
     DRPO_LAUNCH(alpha_adam_kernel, 1, 32, 0, stream, a.log_alpha, a.losses + 5, a.alpha_m, a.alpha_v, adam_scalars(a.adam_alpha, 0.0));
     DRPO_LAUNCH(sumsq_kernel, nb, 256, 0, stream, a.grads_safe, a.n_safe, (int64_t)0, nrm_part);
     DRPO_LAUNCH(clip_coef_kernel, 1, 32, 0, stream, nrm_part, nb, (float)a.grad_norm, a.losses + 6, coef + 2);
     AdamScalars s2 = adam_scalars(a.adam_safe, 0.0);
     DRPO_LAUNCH(adam_ema_kernel, grid_for(a.n_safe), 256, 0, stream, a.params_safe, a.grads_safe, a.m_safe, a.v_safe, (float*)nullptr,
-                a.n_safe, a.n_safe, coef + 2, s2);
+                a.n_safe, a.n_safe, coef + 2, s2, (const float*)(a.losses + DRPO_LOSS_ERR_SLOT));
   }
   return DRPO_OK;
 }

@@ -14,6 +14,16 @@ namespace drpo {
 void set_error(const char* fmt, ...);
 extern int64_t g_launch_count;
 
+// In-kernel watchdog plumbing of the tcgen05 kernels (every wait inside them is bounded; a protocol bug is reported, never a hang).
+// Two pinned, device-mapped host words (0 = rollout kernels, 1 = update-step kernels) are STICKY: the device writes a word only
+// when a launch sequence flagged a time-out and nothing ever clears it, so a later successful launch cannot hide the failure.
+// publish_status() enqueues that write for `err_flag` (device int, non-zero = failing wait's code) and, when `loss_flag` is given,
+// stores 0/1 into the update step's losses[DRPO_LOSS_ERR_SLOT], which phase 2 and the gradient all-reduce consume.
+int* status_words_host();
+int publish_status(const int* err_flag, int which, float* loss_flag, void* stream);
+int kernel_status_peek();          // non-blocking: the sticky words as the host sees them now
+int kernel_status_sync();          // device-synchronising (drpo_kernel_status)
+
 #define DRPO_CHECK_ARG(cond, ...)                                                  \
   do {                                                                             \
     if (!(cond)) { ::drpo::set_error(__VA_ARGS__); return DRPO_ERR_ARG; }          \

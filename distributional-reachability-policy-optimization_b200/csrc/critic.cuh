@@ -129,7 +129,10 @@ static inline AdamScalars adam_scalars(const drpo_adam& a, double tau) {
 // torch.optim.Adam (coupled L2, src/ssac.py:199-203) + update_ema (src/torch_util.py:223-226) in one pass
 static __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ tgt, int64_t n0, int64_t n,
-                                                       const float* __restrict__ coef, AdamScalars s) {
+                                                       const float* __restrict__ coef, AdamScalars s, const float* __restrict__ skip = nullptr) {
+  // `skip` = the update's watchdog slot (losses[DRPO_LOSS_ERR_SLOT], summed over ranks by the gradient all-reduce): non-zero means a
+  // fused kernel of phase 1 reported a pipeline time-out on some rank - the gradients are garbage and NO rank may apply them
+  if (skip && *skip != 0.f) return;
   const float c0 = coef[0], c1 = coef[1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i];
@@ -210,6 +213,7 @@ static inline int critic_step_fp32(const drpo_critic_args& a) {
   const int64_t n_all = a.n_params_q + a.n_params_qc;
 
   if (a.phases & 1) {
+    DRPO_CUDA_OK(cudaMemsetAsync(a.losses + DRPO_LOSS_ERR_SLOT, 0, sizeof(float), (cudaStream_t)stream));   // watchdog slot: no fused kernel on this path
     const drpo_batch& b = a.batch;
     // ---- no-grad passes -------------------------------------------------------------------------------------
     // actor.distr(next_obs).sample(), log_prob                                  src/ssac.py:286-288
@@ -276,7 +280,7 @@ static inline int critic_step_fp32(const drpo_critic_args& a) {
     DRPO_LAUNCH(clip_coef_kernel, 1, 32, 0, stream, nrm_part, nb, (float)a.grad_norm, a.losses + 2, coef);
     AdamScalars s = adam_scalars(a.adam, a.tau);
     DRPO_LAUNCH(adam_ema_kernel, grid_for(n_all), 256, 0, stream, a.params, a.grads, a.adam_m, a.adam_v, a.target_params,
-                a.n_params_q, n_all, coef, s);
+                a.n_params_q, n_all, coef, s, (const float*)(a.losses + DRPO_LOSS_ERR_SLOT));
   }
   return DRPO_OK;
 }
@@ -349,6 +353,7 @@ static inline int multiplier_step_fp32(const drpo_multiplier_args& a) {
   if (!ar.ok()) { set_error("drpo_multiplier_step: workspace too small (%lld needed, %lld given)", (long long)ar.off, (long long)a.workspace_bytes); return DRPO_ERR_WORKSPACE; }
   NoiseView none = make_noise(nullptr, 0, 0, 0, 0);
   if (a.phases & 1) {
+    DRPO_CUDA_OK(cudaMemsetAsync(a.losses + DRPO_LOSS_ERR_SLOT, 0, sizeof(float), (cudaStream_t)stream));   // watchdog slot: no fused kernel on this path
     // action = actor.distr(obs).rsample()                                       src/ssac.py:530-531
     if ((rc = mlp3_fwd(*a.actor, a.obs, S, (int)B, ACT_RELU, phA, phB, pout, nullptr, stream))) return rc;
     NoiseView n1 = make_noise(a.eps_actor, A, a.seed, TAG_MULT_ACTOR, a.noise_step, a.row_id_offset);
@@ -382,7 +387,7 @@ static inline int multiplier_step_fp32(const drpo_multiplier_args& a) {
     DRPO_LAUNCH(clip_coef_kernel, 1, 32, 0, stream, nrm_part, nb, (float)a.grad_norm, a.losses + 1, coef);
     AdamScalars s = adam_scalars(a.adam, 0.0);
     DRPO_LAUNCH(adam_ema_kernel, grid_for(a.n_params), 256, 0, stream, a.params, a.grads, a.adam_m, a.adam_v, (float*)nullptr,
-                a.n_params, a.n_params, coef, s);
+                a.n_params, a.n_params, coef, s, (const float*)(a.losses + DRPO_LOSS_ERR_SLOT));
   }
   return DRPO_OK;
 }

@@ -13,5 +13,4 @@ void critic_set_prof(long long* p);     // profiling aid: per-op clock stamps [2
 int critic_debug_dw(const void* a_oct, const void* b_oct, int b_octets, int64_t rows_padded, int ksplit, float* partial, float* out,
                     int* err_flag, void* stream);
 }  // namespace cu
-int* umma_status_words();      // pinned host words [0] rollout, [1] critic: in-kernel watchdog codes of the last bf16 launches
 }  // namespace drpo

@@ -28,6 +28,42 @@ void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 
+// ---- sticky watchdog status (see common.cuh) ----------------------------------------------------------------------------------
+static int* g_status_host = nullptr;
+static int* g_status_dev = nullptr;
+int* status_words_host() {
+  if (!g_status_host) {
+    if (cudaHostAlloc((void**)&g_status_host, 2 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); g_status_host = nullptr; return nullptr; }
+    g_status_host[0] = g_status_host[1] = 0;
+    if (cudaHostGetDevicePointer((void**)&g_status_dev, g_status_host, 0) != cudaSuccess) { cudaGetLastError(); g_status_dev = g_status_host; }
+  }
+  return g_status_host;
+}
+__global__ void publish_status_kernel(const int* __restrict__ err_flag, int* host_word, float* loss_flag) {
+  const int code = *err_flag;
+  if (code != 0) { *(volatile int*)host_word = code; __threadfence_system(); }
+  if (loss_flag) *loss_flag = code != 0 ? 1.f : 0.f;
+}
+int publish_status(const int* err_flag, int which, float* loss_flag, void* stream) {
+  if (!status_words_host()) { set_error("cannot allocate the pinned status words"); return DRPO_ERR_CUDA; }
+  DRPO_LAUNCH(publish_status_kernel, 1, 1, 0, stream, err_flag, g_status_dev + which, loss_flag);
+  return DRPO_OK;
+}
+static int status_report() {
+  if (!g_status_host) return 0;
+  const int r = ((volatile int*)g_status_host)[0], c = ((volatile int*)g_status_host)[1];
+  const int code = r ? r : c;
+  if (code) set_error("bf16 %s kernel: an in-kernel wait timed out (code %d): pipeline protocol bug, the results of that call are invalid "
+                      "(the rollout did not advance the ring pointer / the update step applied no parameter update)", r ? "rollout" : "update-step", code);
+  return code;
+}
+int kernel_status_peek() { return status_report(); }
+int kernel_status_sync() {
+  if (!g_status_host) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("drpo_kernel_status: %s", cudaGetErrorString(cudaGetLastError())); return DRPO_ERR_CUDA; }
+  return status_report();
+}
+
 __global__ void philox_fill_kernel(float* out, int64_t n, int cols, const int32_t* row_ids, uint64_t seed, uint32_t tag, uint32_t step) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * cols; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols; const int c = (int)(i % cols);
@@ -43,7 +79,8 @@ extern "C" {
 const char* drpo_last_error(void) { return g_err; }
 int drpo_abi_version(void) { return DRPO_ABI_VERSION; }
 int64_t drpo_launch_count(void) { return g_launch_count; }
-int drpo_kernel_status(void) { return umma_kernel_status(); }
+int drpo_kernel_status(void) { return kernel_status_sync(); }
+int drpo_kernel_status_peek(void) { return kernel_status_peek(); }
 void drpo_timing_enable(int32_t on) { umma_timing_enable(on); }
 int drpo_timing_read(double* total_ms_host, int64_t* launches_host, double* satellites_ms_host) {
   DRPO_CHECK_ARG(total_ms_host && launches_host, "drpo_timing_read: NULL output");
@@ -86,7 +123,8 @@ int drpo_hooks_eval(const drpo_env_params* env, const float* states, int64_t n, 
 }
 
 static int check_ens(const drpo_ensemble* e) {
-  DRPO_CHECK_ARG(e && e->state_dim > 0 && e->action_dim > 0 && e->ensemble_size > 0 && e->hidden > 0, "bad ensemble dims");
+  DRPO_CHECK_ARG(e && e->state_dim > 0 && e->action_dim > 0 && e->ensemble_size > 0 && e->ensemble_size <= 64 && e->hidden > 0,
+                 "bad ensemble dims (ensemble_size must be 1..64)");
   DRPO_CHECK_ARG(e->norm_mean && e->norm_std && e->min_log_var && e->max_log_var && e->trunk0_w && e->trunk0_b && e->trunk1_w &&
                  e->trunk1_b && e->diff0_w && e->diff0_b && e->diff1_w && e->diff1_b && e->lvar0_w && e->lvar0_b && e->lvar1_w && e->lvar1_b,
                  "ensemble weight pointer is NULL");
@@ -392,14 +430,12 @@ int drpo_critic_step(const drpo_critic_args* a) {
     // fused tcgen05 path: phase 1 = pack + fused forward/loss/dX kernel + dW kernel + gradient assembly; phase 2 is shared
     drpo_critic_args b = *a;
     if (a->phases & 1) {
-      int* words = umma_status_words();
-      DRPO_CHECK_ARG(words, "drpo_critic_step: cannot allocate the pinned status words");
       DRPO_CHECK_ARG(a->workspace_bytes >= 4096, "drpo_critic_step: workspace too small");
       int* err_flag = (int*)a->workspace;                       // first 4 KB of the workspace: in-kernel watchdog flag
       b.workspace = (char*)a->workspace + 4096; b.workspace_bytes = a->workspace_bytes - 4096;
       DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)a->stream));
       if ((rc = cu::critic_phase1(b, err_flag))) return rc;
-      DRPO_CUDA_OK(cudaMemcpyAsync(words + 1, err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)a->stream));
+      if ((rc = publish_status(err_flag, 1, a->losses + DRPO_LOSS_ERR_SLOT, a->stream))) return rc;
     }
     if (a->phases & 2) { b = *a; b.phases = 2; return critic_step_fp32(b); }
     return DRPO_OK;
@@ -499,13 +535,11 @@ int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets,
                          float* out, void* stream) {
   DRPO_CHECK_ARG(a_oct && b_oct && partial && out && b_octets >= 2 && b_octets <= 32 && (b_octets & 1) == 0 && rows_padded % 128 == 0 &&
                      ksplit >= 1 && ksplit <= rows_padded / 64, "drpo_debug_critic_dw: bad arguments");
-  int* words = umma_status_words();
-  DRPO_CHECK_ARG(words, "drpo_debug_critic_dw: cannot allocate the pinned status words");
   int* err_flag = (int*)partial;                                // first 16 bytes of the partial scratch
   DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));
   int rc = cu::critic_debug_dw(a_oct, b_oct, b_octets, rows_padded, ksplit, partial + 4, out, err_flag, stream);
   if (rc) return rc;
-  DRPO_CUDA_OK(cudaMemcpyAsync(words + 1, err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (rc == DRPO_OK) rc = publish_status(err_flag, 1, nullptr, stream);
   return DRPO_OK;
 }
 

@@ -146,7 +146,11 @@ static __global__ void __launch_bounds__(CBLK) compact_scatter_kernel(const uint
   }
 }
 
-static __global__ void rollout_finish_kernel(int64_t* pointer, const RolloutState* st, int32_t* step_counts, int horizon) {
+// err_flag (bf16 path): a non-zero watchdog flag means the fused kernel reported a pipeline time-out - the rows it wrote are garbage,
+// so the ring pointer does NOT advance and the rollout reports zero transitions (the host raises at its next status check)
+static __global__ void rollout_finish_kernel(int64_t* pointer, const RolloutState* st, int32_t* step_counts, int horizon,
+                                             const int* err_flag = nullptr) {
+  if (err_flag && *err_flag != 0) { step_counts[horizon] = 0; return; }
   int total = 0;
   for (int t = 0; t < horizon; ++t) total += step_counts[t];
   step_counts[horizon] = total;

@@ -5,7 +5,6 @@ namespace drpo {
 int64_t umma_rollout_ws_bytes(const drpo_rollout_args& a);
 int umma_rollout(const drpo_rollout_args& a);
 int umma_debug_layer(const drpo_rollout_args& a, int layer, float* out);
-int umma_kernel_status();               // blocking read of the last rollout's in-kernel error flag (0 = ok)
 // optional kernel timing for bench.py's roofline: CUDA events around every fused step-kernel launch
 void umma_timing_enable(int on);
 int umma_timing_read(double* total_ms, int64_t* launches, double* tail_ms);

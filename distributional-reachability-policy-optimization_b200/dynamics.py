@@ -195,8 +195,8 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         next_states = torch.empty((B, self.state_dim), device=states.device)
         rewards = torch.empty((B,), device=states.device)
         self._noise_step += 1
-        noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, self.state_dim + 1, self.noise_seed,
-                           16, self._noise_step)
+        eps = eps.contiguous().float() if eps is not None else None        # a named local: the copy must outlive the launch
+        noise = _lib.Noise(_lib.ptr(eps), self.state_dim + 1, self.noise_seed, 16, self._noise_step)
         ens = self.as_struct()
         ws = self._workspace(lib, ens, B, states.device)
         _lib.check(lib.drpo_ensemble_sample(ens, index, _lib.ptr(states), _lib.ptr(actions), B, noise, _lib.ptr(next_states),

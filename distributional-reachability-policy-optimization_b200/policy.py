@@ -45,7 +45,8 @@ class SquashedGaussianPolicy(BasePolicy, nn.Module):
         actions = torch.empty((B, A), device=states.device)
         logp = torch.empty((B,), device=states.device) if want_log_prob else None
         self._noise_step += 1
-        noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, A, self.noise_seed, 17, self._noise_step)
+        eps = eps.contiguous().float() if eps is not None else None        # a named local: the copy must outlive the launch
+        noise = _lib.Noise(_lib.ptr(eps), A, self.noise_seed, 17, self._noise_step)
         s = self.as_struct()
         ws = self._ws.get(lib.drpo_policy_workspace_bytes(s, B), states.device)
         _lib.check(lib.drpo_policy_act(s, _lib.ptr(states), B, int(bool(eval)), noise, _lib.ptr(actions), _lib.ptr(logp),

@@ -108,6 +108,7 @@ class SMBPO(Configurable, nn.Module):
         and returns a view of them.  ``noise=(eps_policy [H,B,A], eps_model [H,B,S+1])`` injects the Gaussian draws
         indexed by original trajectory id (parity); ``member_idx`` overrides the per-step elite picks."""
         lib = _lib.load()
+        _lib.peek_kernel_status("SMBPO.rollout")
         if initial_states is None:
             states = self.replay_buffer.get('states')
             idx = torch.randperm(states.shape[0], device=states.device)[:self.rollout_batch_size]
@@ -179,6 +180,7 @@ class SMBPO(Configurable, nn.Module):
     def sample_batch(self, batch_size=None):
         """replay/virtual mix + reward and constraint scaling in one gather kernel (src/smbpo.py:253-270)."""
         lib = _lib.load()
+        _lib.peek_kernel_status("SMBPO.sample_batch")
         solver = self.solver
         B = batch_size or solver.batch_size
         n_real = int(self.real_fraction * B)
@@ -213,6 +215,24 @@ class SMBPO(Configurable, nn.Module):
         for step in range(self.solver_updates_per_step):
             self.update_solver(update_actor=(step % self.sac_cfg.actor_update_interval == 0),
                                update_multiplier=(step % self.sac_cfg.multiplier_update_interval == 0))
+
+    # ---- Philox stream positions (not part of the reference's state_dict; a checkpointing caller saves them beside it) --------
+    def noise_state(self):
+        """Counters that key the in-kernel Philox streams.  A resumed run that restores them continues the streams instead of
+        replaying them (the reference has no equivalent: torch's global generator is not checkpointed there either)."""
+        sv = self.solver
+        return dict(rollouts_done=self._rollouts_done, rollout_seed=self.rollout_seed, solver_seed=sv.noise_seed,
+                    actor_step=sv.actor._noise_step, actor_safe_step=sv.actor_safe._noise_step,
+                    qc_step=sv.constraint_critic._noise_step, ensemble_step=self.model_ensemble._noise_step,
+                    opt_steps=[o.step_count for o in (sv.critic_optimizer, sv.multiplier_optimizer, sv.actor_optimizer, sv.actor_safe_optimizer)])
+
+    def load_noise_state(self, st):
+        sv = self.solver
+        self._rollouts_done, self.rollout_seed, sv.noise_seed = st["rollouts_done"], st["rollout_seed"], st["solver_seed"]
+        sv.actor._noise_step, sv.actor_safe._noise_step = st["actor_step"], st["actor_safe_step"]
+        sv.constraint_critic._noise_step, self.model_ensemble._noise_step = st["qc_step"], st["ensemble_step"]
+        for o, n in zip((sv.critic_optimizer, sv.multiplier_optimizer, sv.actor_optimizer, sv.actor_safe_optimizer), st["opt_steps"]):
+            o.step_count = n
 
     def update_models(self, model_steps):
         """src/smbpo.py:214-227."""

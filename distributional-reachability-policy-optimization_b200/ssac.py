@@ -128,6 +128,10 @@ class ConstraintCritic(Configurable, nn.Module):
 
     def forward(self, state, action, uncertainty=False, sample=False, eps=None):
         assert not (uncertainty and sample), "Uncertainty bound and sample cannot be True simultaneously."
+        # Inputs that carry autograd history get the differentiable torch form.  Every other call runs through the C ABI and its
+        # outputs are DETACHED from the critic's weights: a caller that wants d(loss)/d(weights) must call forward_torch
+        # explicitly (the reference's own weight-gradient users, cons_critic_loss_given_target and actor_loss, are
+        # drpo_critic_step / drpo_actor_step here).
         if torch.is_grad_enabled() and (state.requires_grad or action.requires_grad):
             return self.forward_torch(state, action, uncertainty, sample)
         lib = _lib.load()
@@ -138,7 +142,8 @@ class ConstraintCritic(Configurable, nn.Module):
         std = torch.empty((B, C), device=state.device) if mode == 2 else None
         out = torch.empty((B, C), device=state.device) if mode else None
         self._noise_step += 1
-        noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, C, self.noise_seed, 18, self._noise_step)
+        eps = eps.contiguous().float() if eps is not None else None        # a named local: the copy must outlive the launch
+        noise = _lib.Noise(_lib.ptr(eps), C, self.noise_seed, 18, self._noise_step)
         ws = self._ws.get(lib.drpo_qc_workspace_bytes(B, self.hidden_dim), state.device)
         _lib.check(lib.drpo_qc_forward(self.as_struct(), _lib.ptr(state), _lib.ptr(action), B, self.state_dim, self.action_dim, C,
                                        mode, float(self.std_ratio), noise, _lib.ptr(mean), _lib.ptr(std), _lib.ptr(out),
@@ -193,10 +198,22 @@ class CosineLR:
 class FusedAdam:
     """State of the in-kernel Adam (torch.optim.Adam semantics, coupled L2): flat m/v arenas + step count."""
 
-    def __init__(self, arena, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, arena, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, grad_storage=None):
+        """``grad_storage`` (optional): a flat tensor of ``arena.numel() + LOSSES_LEN`` floats to carve the gradient arena from.  The
+        step's ``losses`` array (incl. the watchdog slot) is the TAIL of the gradient storage, so a data-parallel step all-reduces
+        gradients, losses and the watchdog flag in ONE NCCL message (``grad_full``)."""
         self.param_groups = [dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)]
-        self.m, self.v, self.grad = torch.zeros_like(arena), torch.zeros_like(arena), torch.zeros_like(arena)
+        self.m, self.v = torch.zeros_like(arena), torch.zeros_like(arena)
+        n = arena.numel()
+        self.grad_full = grad_storage if grad_storage is not None else torch.zeros(n + _lib.LOSSES_LEN, dtype=arena.dtype, device=arena.device)
+        self.grad, self.losses = self.grad_full[:n], self.grad_full[n:n + _lib.LOSSES_LEN]
         self.step_count = 0
+
+    def to(self, device):
+        if self.m.device != device:
+            n = self.grad.numel()
+            self.m, self.v, self.grad_full = self.m.to(device), self.v.to(device), self.grad_full.to(device)
+            self.grad, self.losses = self.grad_full[:n], self.grad_full[n:n + _lib.LOSSES_LEN]
 
     def zero_grad(self):
         pass                                   # every gradient element is overwritten by the backward kernels
@@ -287,6 +304,9 @@ class SSAC(Configurable, BasePolicy, nn.Module):
                  constraint_scale, env_factory=None, model_ensemble=None, optimizer_factory=torch.optim.Adam, device=None):
         Configurable.__init__(self, config)
         nn.Module.__init__(self)
+        if self.use_log_alpha_loss:
+            raise NotImplementedError("drpo_actor_step implements the reference default use_log_alpha_loss=False (alpha-coefficient "
+                                      "temperature loss, src/ssac.py:497-500)")
         if not (self.constrained_fcn == 'reachability' and self.mlp_multiplier and self.qc_under_uncertainty
                 and self.distributional_qc and not self.deterministic_backup):
             raise NotImplementedError("the CUDA SSAC implements DRPO mode: reachability + mlp_multiplier + "
@@ -318,9 +338,16 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self.multiplier_lr_scheduler = CosineLR(self.multiplier_optimizer, self.lam_updates_num, self.multiplier_lr_end)
 
         # actors / alpha (SURVEY §8f "next" row 1): in-kernel Adam over flat arenas as well (src/ssac.py:210-228)
-        self.actor_optimizer = FusedAdam(self._actor_arena, self.actor_lr, weight_decay=1e-4)
+        # the two actor gradient arenas share ONE storage [actor | safe | losses]: one all-reduce message per data-parallel actor step
+        na, ns = self._actor_arena.numel(), self._safe_arena.numel()
+        self._actor_grad_joint = torch.zeros(na + ns + _lib.LOSSES_LEN, device=device)
+        self.actor_optimizer = FusedAdam(self._actor_arena, self.actor_lr, weight_decay=1e-4,
+                                         grad_storage=self._actor_grad_joint[:na + _lib.LOSSES_LEN])
+        self.actor_optimizer.grad, self.actor_optimizer.losses = self._actor_grad_joint[:na], self._actor_grad_joint[na + ns:]
         self.actor_lr_scheduler = CosineLR(self.actor_optimizer, max(self.actor_updates_num, 1), self.actor_lr_end)
-        self.actor_safe_optimizer = FusedAdam(self._safe_arena, self.actor_lr, weight_decay=1e-4)
+        self.actor_safe_optimizer = FusedAdam(self._safe_arena, self.actor_lr, weight_decay=1e-4,
+                                              grad_storage=self._actor_grad_joint[na:])
+        self.actor_safe_optimizer.grad, self.actor_safe_optimizer.losses = self._actor_grad_joint[na:na + ns], self._actor_grad_joint[na + ns:]
         self.actor_safe_lr_scheduler = CosineLR(self.actor_safe_optimizer, max(self.actor_updates_num, 1), self.actor_lr_end)
         self.log_alpha = torch.tensor(math.log(self.init_alpha), device=device, requires_grad=True)
         if self.autotune_alpha:
@@ -329,13 +356,57 @@ class SSAC(Configurable, BasePolicy, nn.Module):
             self.target_entropy = -action_dim
 
         self.register_buffer('total_updates', torch.zeros([], device=device))
-        self._losses = torch.zeros(8, device=device)
-        self._actor_losses = torch.zeros(8, device=device)
         self._ws = _lib.Workspace()
         self.noise_seed = 0xD2B0
         self.precision = _lib.PREC_FP32
         self.data_parallel = False          # set True under torchrun: gradients are all-reduced between backward and Adam
+        self._dp_synced = False             # replicas are made identical (rank 0's state) at the first data-parallel step
+        self._dp_rng = random.Random(0xD2B0)  # critic pick of the actor step under data parallelism: identical on every rank
         self._structs = None
+
+    # the steps' losses live in the tail of the gradient storage (FusedAdam): [0..] losses / norms, [15] watchdog flag
+    @property
+    def _losses(self):
+        return self.critic_optimizer.losses
+
+    @property
+    def _mult_losses(self):
+        return self.multiplier_optimizer.losses
+
+    @property
+    def _actor_losses(self):
+        return self.actor_optimizer.losses
+
+    def sync_replicas(self, src=0):
+        """Make every data-parallel replica identical to rank ``src``: the five parameter arenas, both target nets, Adam m / v and
+        step counts, log_alpha and its Adam state, learning rates, the noise seeds and the host RNG that picks the actor step's
+        critic (the reference draws it with ``random.choice``, src/ssac.py:41-43).  Called automatically at the first
+        data-parallel update; call it again after loading a checkpoint on one rank only."""
+        dist = self._dist()
+        if dist is None:
+            return
+        self._ensure_arenas()
+        opts = [self.critic_optimizer, self.multiplier_optimizer, self.actor_optimizer, self.actor_safe_optimizer]
+        if self.autotune_alpha:
+            opts.append(self.alpha_optimizer)
+        tensors = [self._critic_arena, self._target_arena, self._mult_arena, self._actor_arena, self._safe_arena, self.log_alpha.data]
+        for o in opts:
+            tensors += [o.m, o.v]
+        for t in tensors:
+            dist.broadcast(t, src=src)
+        scheds = [self.critic_lr_scheduler, self.multiplier_lr_scheduler, self.actor_lr_scheduler, self.actor_safe_lr_scheduler]
+        host = [dict(steps=[o.step_count for o in opts], lrs=[o.param_groups[0]["lr"] for o in opts],
+                     epochs=[sc.last_epoch for sc in scheds], seed=self.noise_seed, rng=self._dp_rng.getstate(),
+                     qc_seed=self.constraint_critic.noise_seed, actor_seed=self.actor.noise_seed)]
+        dist.broadcast_object_list(host, src=src)
+        h = host[0]
+        for o, st, lr in zip(opts, h["steps"], h["lrs"]):
+            o.step_count, o.param_groups[0]["lr"] = st, lr
+        for sc, e in zip(scheds, h["epochs"]):
+            sc.last_epoch = e
+        self.noise_seed, self.constraint_critic.noise_seed, self.actor.noise_seed = h["seed"], h["qc_seed"], h["actor_seed"]
+        self._dp_rng.setstate(h["rng"])
+        self._dp_synced = True
 
     # ------------------------------------------------------------------------------------------------------
     def _critic_params(self):
@@ -380,9 +451,15 @@ class SSAC(Configurable, BasePolicy, nn.Module):
                 and _arena_ok(self._safe_arena, list(self.actor_safe.parameters()))):
             old = (self.critic_optimizer, self.multiplier_optimizer, self.actor_optimizer, self.actor_safe_optimizer)
             self._build_arenas()
-            for opt, arena in zip(old, (self._critic_arena, self._mult_arena, self._actor_arena, self._safe_arena)):
-                if opt.m.device != arena.device:
-                    opt.m, opt.v, opt.grad = opt.m.to(arena.device), opt.v.to(arena.device), opt.grad.to(arena.device)
+            if self._actor_grad_joint.device != self._actor_arena.device:
+                na, ns = self._actor_arena.numel(), self._safe_arena.numel()
+                self._actor_grad_joint = self._actor_grad_joint.to(self._actor_arena.device)
+                for o in (self.actor_optimizer, self.actor_safe_optimizer):
+                    o.m, o.v = o.m.to(self._actor_arena.device), o.v.to(self._actor_arena.device)
+                    o.losses = self._actor_grad_joint[na + ns:]
+                self.actor_optimizer.grad, self.actor_safe_optimizer.grad = self._actor_grad_joint[:na], self._actor_grad_joint[na:na + ns]
+            for opt, arena in zip(old[:2], (self._critic_arena, self._mult_arena)):
+                opt.to(arena.device)
         groups = ((self._critic_arena, self._critic_params()), (self._target_arena, self._target_params()),
                   (self._mult_arena, list(self.multiplier.parameters())), (self._actor_arena, list(self.actor.parameters())),
                   (self._safe_arena, list(self.actor_safe.parameters())))
@@ -456,7 +533,8 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         a.eval_perf, a.uncertainty = int(bool(eval)), int(bool(uncertainty))
         a.std_ratio, a.threshold = float(self.constraint_critic.std_ratio), float(safe_shield_threshold)
         self.actor._noise_step += 1
-        noise = _lib.Noise(_lib.ptr(eps.contiguous()) if eps is not None else None, A, self.actor.noise_seed, 17, self.actor._noise_step)
+        eps = eps.contiguous().float() if eps is not None else None        # a named local: the copy must outlive the launch
+        noise = _lib.Noise(_lib.ptr(eps), A, self.actor.noise_seed, 17, self.actor._noise_step)
         a.noise_perf = C_pointer(noise)
         a.actions, a.qc_perf, a.choice, a.path = _lib.ptr(actions), _lib.ptr(qc_perf), _lib.ptr(choice), int(path)
         ws = self._ws.get(lib.drpo_shield_workspace_bytes(a.actor, n, self.state_dim, A, self.con_dim, self.constraint_critic.hidden_dim),
@@ -476,8 +554,11 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         injects the three Gaussian draws (parity); otherwise the in-kernel Philox stream is used.  ``phases`` (tests) runs only
         the given phases of drpo_critic_step (1 = forward/backward into the gradient arena, 2 = clip/Adam/EMA)."""
         lib = _lib.load()
+        _lib.peek_kernel_status("SSAC.update_critic")
         st = self._ensure_arenas()
         dist = self._dist()
+        if dist is not None and not self._dp_synced:
+            self.sync_replicas()
         world = dist.get_world_size() if dist else 1
         rank = dist.get_rank() if dist else 0
         B = obs.shape[0]
@@ -518,8 +599,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         else:
             a.phases = 1
             _lib.check(lib.drpo_critic_step(a), "drpo_critic_step(forward/backward)")
-            dist.all_reduce(opt.grad)                       # NCCL sum over NVLink; losses ride in a second tiny message
-            dist.all_reduce(self._losses[:2])
+            dist.all_reduce(opt.grad_full)                  # ONE NCCL sum over NVLink: gradients + losses + watchdog flag (the tail)
             a.phases = 2
             _lib.check(lib.drpo_critic_step(a), "drpo_critic_step(optimizer)")
         self.critic_lr_scheduler.step()
@@ -529,8 +609,11 @@ class SSAC(Configurable, BasePolicy, nn.Module):
     def update_multiplier(self, obs, eps=None):
         """SSAC.update_multiplier (src/ssac.py:570-578)."""
         lib = _lib.load()
+        _lib.peek_kernel_status("SSAC.update_multiplier")
         st = self._ensure_arenas()
         dist = self._dist()
+        if dist is not None and not self._dp_synced:
+            self.sync_replicas()
         world = dist.get_world_size() if dist else 1
         rank = dist.get_rank() if dist else 0
         obs = obs.contiguous().float()
@@ -551,7 +634,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         a.constraint_threshold, a.penalty_lb, a.penalty_ub = self.constraint_threshold, self.penalty_lb, self.penalty_ub
         a.upper_bound, a.lam_epsilon, a.grad_norm = self.multiplier.upper_bound, self.lam_epsilon, self.grad_norm
         a.adam = opt.as_struct()
-        a.losses, a.precision = _lib.ptr(self._losses[4:]), self.precision
+        a.losses, a.precision = _lib.ptr(self._mult_losses), self.precision
         ws = self._ws.get(lib.drpo_multiplier_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim), obs.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
         if dist is None:
@@ -560,12 +643,11 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         else:
             a.phases = 1
             _lib.check(lib.drpo_multiplier_step(a), "drpo_multiplier_step(forward/backward)")
-            dist.all_reduce(opt.grad)
-            dist.all_reduce(self._losses[4:5])
+            dist.all_reduce(opt.grad_full)                  # gradients + loss + watchdog flag in one message
             a.phases = 2
             _lib.check(lib.drpo_multiplier_step(a), "drpo_multiplier_step(optimizer)")
         self.multiplier_lr_scheduler.step()
-        return self._losses[4].clone()
+        return self._mult_losses[0].clone()
 
     # ---- SURVEY §8f "next" row 1: actor / alpha update ------------------------------------------------------------
     def actor_loss(self, obs, include_alpha=True):
@@ -602,14 +684,19 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         in-kernel Philox stream is used; ``q_index`` is the critic `random.choice` picks (src/ssac.py:41-43)."""
         assert self.autotune_alpha, "drpo_actor_step implements the autotune_alpha configuration of the reference"
         lib = _lib.load()
+        _lib.peek_kernel_status("SSAC.update_actor_and_alpha")
         st = self._ensure_arenas()
         dist = self._dist()
+        if dist is not None and not self._dp_synced:
+            self.sync_replicas()
         world = dist.get_world_size() if dist else 1
         rank = dist.get_rank() if dist else 0
         obs = obs.contiguous().float()
         B = obs.shape[0]
         if q_index is None:
-            q_index = random.choice(range(len(self.critic.qs)))          # same draw from the host RNG as random.choice(self.qs)
+            # same draw as random.choice(self.qs) (src/ssac.py:41-43); under data parallelism from the replica-synchronised RNG, so
+            # that every rank back-propagates through the SAME critic before the gradients are summed
+            q_index = (self._dp_rng if dist is not None else random).choice(range(len(self.critic.qs)))
         oa, os_, oal = self.actor_optimizer, self.actor_safe_optimizer, self.alpha_optimizer
         for o in (oa, os_, oal):
             o.step_count += 1
@@ -643,10 +730,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         else:
             a.phases = 1
             _lib.check(lib.drpo_actor_step(a), "drpo_actor_step(forward/backward)")
-            dist.all_reduce(oa.grad); dist.all_reduce(os_.grad)
-            red = torch.cat([self._actor_losses[:3], self._actor_losses[5:6]])
-            dist.all_reduce(red)
-            self._actor_losses[:3] = red[:3]; self._actor_losses[5] = red[3]
+            dist.all_reduce(self._actor_grad_joint)         # [actor grads | safe grads | losses + watchdog flag]: one message
             a.phases = 2
             _lib.check(lib.drpo_actor_step(a), "drpo_actor_step(optimizer)")
         self.actor_lr_scheduler.step()

@@ -11,11 +11,14 @@
  *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are contiguous row-major fp32,
  *     masks are uint8 (torch.bool storage), nn.Linear weights are [out,in] (y = x W^T + b) exactly as in the
  *     reference state_dict, so checkpoints interchange;
- *   - the library owns no memory (but one 4-byte pinned status word, see drpo_kernel_status): parameters, replay buffers
- *     and workspaces are allocated by the caller (PyTorch);
+ *   - the library owns no device memory: parameters, replay buffers and workspaces are allocated by the caller (PyTorch).  Its only
+ *     allocations are two pinned, device-mapped host status words (cudaHostAlloc on first use, see drpo_kernel_status) and, in
+ *     DRPO_PREC_TF32 only, one cuBLAS handle bound to the first device that uses it;
  *     `*_workspace_bytes` tells how much scratch a call needs;
- *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no call synchronises,
- *     allocates or frees, so every call is CUDA-graph capturable;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no call synchronises the device
+ *     (drpo_kernel_status and drpo_timing_read are the exceptions: they exist to synchronise).  The launches themselves are
+ *     capturable, but calls are NOT advertised as CUDA-graph capturable: the first call of each kind sets function attributes
+ *     (cudaFuncSetAttribute) and the first bf16 call allocates the status words;
  *   - return value 0 = ok, negative = error (message from drpo_last_error(), thread-local); nothing throws across
  *     the boundary;
  *   - not re-entrant per device; one process per GPU (torchrun), called from the single training thread.
@@ -29,7 +32,15 @@
 extern "C" {
 #endif
 
-#define DRPO_ABI_VERSION 1
+#define DRPO_ABI_VERSION 2
+
+/* Every update step's `losses` array holds DRPO_LOSSES_LEN floats.  Slot DRPO_LOSS_ERR_SLOT is the step's watchdog flag: phase 1
+ * (bit0) writes 0, or 1 when a fused tcgen05 kernel of that phase reported an in-kernel pipeline time-out; phase 2 (bit1) applies
+ * NO parameter update when the slot is non-zero.  Multi-GPU callers all-reduce (sum) the slot together with the gradients (the
+ * Python mirror keeps `losses` in the tail of the gradient arena: ONE NCCL message), so a time-out on any rank vetoes the step on
+ * every rank and replicas stay identical.  The host sees the time-out through drpo_kernel_status / drpo_kernel_status_peek. */
+#define DRPO_LOSSES_LEN 16
+#define DRPO_LOSS_ERR_SLOT 15
 
 enum { DRPO_OK = 0, DRPO_ERR_ARG = -1, DRPO_ERR_CUDA = -2, DRPO_ERR_WORKSPACE = -3, DRPO_ERR_UNSUPPORTED = -4 };
 
@@ -262,9 +273,10 @@ typedef struct drpo_critic_args {
   double discount, tau, grad_norm, qc_td_bound;
   drpo_adam adam;
   /* phases: bit0 = forward+backward (fills grads, losses), bit1 = clip+Adam+EMA.  Multi-GPU callers run bit0,
-   * all-reduce `grads` and `losses` (NCCL), then run bit1. */
+   * all-reduce `grads` and `losses[0..1]`, `losses[15]` (NCCL sum; one message when `losses` is the tail of the gradient arena),
+   * then run bit1. */
   int32_t phases;
-  float* losses;               /* device [4]: loss_Q, loss_C, grad-norm Q, grad-norm Qc */
+  float* losses;               /* device [DRPO_LOSSES_LEN]: loss_Q, loss_C, grad-norm Q, grad-norm Qc, ..., [15] watchdog flag */
   int32_t precision;
   void* workspace; int64_t workspace_bytes; void* stream;
 } drpo_critic_args;
@@ -297,7 +309,7 @@ typedef struct drpo_multiplier_args {
   double std_ratio, constraint_threshold, penalty_lb, penalty_ub, upper_bound, lam_epsilon, grad_norm;
   drpo_adam adam;
   int32_t phases;
-  float* losses;               /* device [4]: loss, grad norm, (unused), (unused) */
+  float* losses;               /* device [DRPO_LOSSES_LEN]: loss, grad norm, ..., [15] watchdog flag */
   int32_t precision;
   void* workspace; int64_t workspace_bytes; void* stream;
 } drpo_multiplier_args;
@@ -329,7 +341,7 @@ typedef struct drpo_actor_args {
   /* phases: bit0 = forward+backward (fills grads_actor, grads_safe, losses[0..2] and losses[5]), bit1 = clips + Adam.
    * Multi-GPU callers all-reduce the two gradient arenas and losses[0..2], losses[5] between the phases. */
   int32_t phases;
-  float* losses;   /* device [8]: actor loss, alpha loss, safe-actor loss, actor grad norm, -, d alpha_loss/d log_alpha, safe grad norm, - */
+  float* losses;   /* device [DRPO_LOSSES_LEN]: actor loss, alpha loss, safe-actor loss, actor grad norm, -, d alpha_loss/d log_alpha, safe grad norm, -, ..., [15] watchdog flag */
   int32_t precision;                       /* DRPO_PREC_FP32, or DRPO_PREC_TF32 / DRPO_PREC_BF16 = TF32 tensor-op GEMMs */
   void* workspace; int64_t workspace_bytes; void* stream;
 } drpo_actor_args;
@@ -411,10 +423,13 @@ int drpo_shield_act(const drpo_shield_args* args);
 /* misc */
 const char* drpo_last_error(void);
 int drpo_abi_version(void);
-/* Blocking check of the last drpo_rollout(DRPO_PREC_BF16) launch sequence of this thread: 0 = ok, else the code of the first
- * in-kernel wait that timed out (a protocol bug: the kernel reports it and runs to completion instead of hanging the GPU;
- * the results of that rollout are invalid).  Synchronises the device; message via drpo_last_error(). */
+/* Watchdog status of the DRPO_PREC_BF16 (tcgen05) kernels: 0 = ok, else the code of the first in-kernel wait that timed out (a
+ * pipeline-protocol bug: the kernel reports it and runs to completion instead of hanging the GPU).  The status is STICKY for the
+ * life of the process.  A flagged rollout leaves the ring pointer where it was and reports zero transitions; a flagged update
+ * step applies no parameter update (DRPO_LOSS_ERR_SLOT).  drpo_kernel_status synchronises the device first;
+ * drpo_kernel_status_peek only reads the pinned words (what has been reported so far).  Message via drpo_last_error(). */
 int drpo_kernel_status(void);
+int drpo_kernel_status_peek(void);
 /* Measurement aid (bench.py's roofline): while enabled, every launch of the fused rollout step kernel is bracketed by CUDA
  * events on the caller's stream, and a third event follows the step's HBM-bound satellites (hooks + ring store, compaction);
  * drpo_timing_read synchronises them and returns the summed kernel duration, the launch count and (optional) the summed

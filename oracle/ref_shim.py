@@ -8,8 +8,9 @@ vectors can be generated from the reference itself.  Nothing of the reference is
 edited or copied: we only inject stand-ins for three third-party packages the image
 does not have (``gym``, ``h5py``, ``matplotlib``) into ``sys.modules``.
 
-This file must never be imported by the product package, ``bench.py`` (GPU arm) or
-the ``-m gpu`` tests: ``/root/reference`` does not exist on the GPU box.
+This file must never be imported by the product package or by the timed GPU region of ``bench.py``.  On the GPU box
+``/root/reference`` does not exist; ``bench.py``'s CPU-baseline legs (``cpu_baseline`` / ``--impl reference``) and the drop-in
+test resolve the staged copy ``baseline/_ref/`` instead (see ``_find_reference``).
 """
 import os
 import sys
@@ -17,7 +18,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("DRPO_REF", "/root/reference")
+def _find_reference() -> str:
+    """$DRPO_REF, else /root/reference (build container), else the staged copy baseline/_ref/ (git-ignored, shipped to the GPU
+    box by gpurun; written by oracle/stage_reference.py) - BASELINE.md §4."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for c in (os.environ.get("DRPO_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "src")):
+            return c
+    return os.environ.get("DRPO_REF", "/root/reference")
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/drpo_b200.h but not exported by {_lib.LIB_PATH}"
     assert sorted(s[0] for s in _lib.SYMBOLS) == names
-    assert _lib.load().drpo_abi_version() == 1
+    assert _lib.load().drpo_abi_version() == 2
 
 
 def test_missing_library_fails_loudly(monkeypatch):

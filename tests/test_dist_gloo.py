@@ -27,8 +27,12 @@ def _free_port():
 class _OracleLib:
     """Stand-in for libdrpo_sm100.so: drpo_critic_step evaluated by the CPU oracle, phase by phase."""
 
-    def __init__(self, solver, stash):
+    def __init__(self, solver, stash, fail_on_call=None):
         self.solver, self.stash, self.adam, self.calls = solver, stash, O.AdamState(), []
+        self.fail_on_call = fail_on_call                  # index of the phase-1 call whose (emulated) watchdog fires on this rank
+
+    def drpo_kernel_status_peek(self):
+        return 0
 
     def drpo_critic_workspace_bytes(self, *a):
         return 1024
@@ -55,7 +59,11 @@ class _OracleLib:
             for k in names:
                 gviews[k].copy_(w[k].grad * scale)
             solver._losses[0], solver._losses[1] = float(lq) * scale, float(lc) * scale
+            n1 = sum(1 for c in self.calls if c[0] & 1)
+            solver._losses[15] = 1.0 if self.fail_on_call is not None and n1 - 1 == self.fail_on_call else 0.0   # DRPO_LOSS_ERR_SLOT
         if args.phases & 2:
+            if float(solver._losses[15]) != 0.0:             # the library applies no update when any rank's watchdog fired
+                return 0
             gviews = solver.critic_arena_views(solver.critic_optimizer.grad)
             grads = {k: gviews[k].clone() for k in names}
             O.clip_grad_norm([grads[k] for k in names if k.startswith("critic.")], 5.0)
@@ -77,7 +85,7 @@ def _make_inputs():
     return [obs, act, nobs, rew, done, viol, cv], noise
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, veto=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -86,22 +94,31 @@ def _worker(rank, world, port, out):
         cfg = drpo_b200.SSAC.Config()
         cfg.batch_size = BG // world
         solver = drpo_b200.SSAC(cfg, S, A, C, 10, 100, 300, 10, 10.0, device="cpu")
-        solver.load_state_dict(O.make_ssac_weights(7, S, A, C), strict=False)
+        # every rank starts from DIFFERENT weights and a different host RNG: the first data-parallel step must broadcast rank 0's
+        # state (sync_replicas), or the replicas would silently diverge
+        solver.load_state_dict(O.make_ssac_weights(7 + 100 * rank, S, A, C), strict=False)
+        solver._dp_rng.seed(1234 + rank)
         solver.data_parallel = world > 1
         batch, noise = _make_inputs()
         lo, hi = rank * (BG // world), (rank + 1) * (BG // world)
         stash = dict(batch=[t[lo:hi] for t in batch], noise=tuple(n[lo:hi] for n in noise))
-        fake = _OracleLib(solver, stash)
+        fake = _OracleLib(solver, stash, fail_on_call=(1 if (veto and rank == 1) else None))
         _lib.load = lambda: fake                                           # the stand-in library
         _lib.ptr = lambda t: None if t is None else t.data_ptr()           # (the real one insists on CUDA tensors)
         _lib.stream_ptr = lambda: None
-        losses = []
+        losses, snaps = [], []
         for _ in range(2):                                                 # two updates: Adam state and lr schedule carry over
             lq, lc = solver.update_critic(*stash["batch"], noise=stash["noise"])
             losses.append((float(lq), float(lc)))
+            snaps.append(solver._critic_arena.clone())
         sd = {k: v.clone() for k, v in solver.state_dict().items() if k.startswith(("critic", "constraint_critic"))}
+        picks = [solver._dp_rng.choice(range(2)) for _ in range(8)]        # the actor step's critic pick: same sequence on every rank
         if rank == 0:
-            torch.save(dict(sd=sd, losses=losses, calls=fake.calls), out)
+            torch.save(dict(sd=sd, losses=losses, calls=fake.calls, second_update_moved=bool((snaps[1] != snaps[0]).any())), out)
+        pk = torch.tensor(picks)
+        gp = [torch.empty_like(pk) for _ in range(world)]
+        dist.all_gather(gp, pk)
+        assert all(torch.equal(gp[0], x) for x in gp), "critic picks differ across ranks"
         # every rank must hold bit-identical parameters after the step
         flat = torch.cat([v.reshape(-1) for v in sd.values()])
         gathered = [torch.empty_like(flat) for _ in range(world)]
@@ -136,6 +153,17 @@ def test_critic_two_phase_allreduce_matches_single_rank(tmp_path):
     # protocol: per update phase 1 (local rows, global normaliser, global row offset of the shard) then phase 2
     assert [c[0] for c in got["calls"]] == [1, 2, 1, 2]
     assert all(c[1] == BG // 2 and c[2] == BG and c[3] == 0 for c in got["calls"])
+    assert got["second_update_moved"]
+
+
+@pytest.mark.timeout(300)
+def test_watchdog_flag_on_one_rank_vetoes_the_step_on_every_rank(tmp_path):
+    """The watchdog slot rides in the gradient all-reduce (tail of the gradient storage): a time-out reported by rank 1 during the
+    second update leaves the parameters of EVERY rank untouched by that update, and the replicas stay identical."""
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, True), nprocs=2, join=True)
+    got = torch.load(out)
+    assert not got["second_update_moved"]
 
 
 def test_rollout_sharding_offsets():

@@ -264,3 +264,88 @@ def test_rollout_from_pinned_host_states_streams_and_matches():
                      alg.virt_buffer._bufs["states"][:int(view.step_counts[-1])].cpu(), alg.virt_buffer._bufs["dones"][:int(view.step_counts[-1])].cpu()))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def _export_philox(alg, B, H, S, A):
+    """The rollout's own Gaussian streams through the C ABI's exporter: seed = rollout_seed + _rollouts_done (SMBPO.rollout),
+    tags 1 / 2 = policy / model draws, step = rollout step, row = global trajectory id (umma_rollout*.cu: make_noise call sites)."""
+    from drpo_b200 import _lib
+    lib = _lib.load()
+    seed = alg.rollout_seed + alg._rollouts_done
+    eps_p, eps_m = torch.empty(H, B, A, device=dev()), torch.empty(H, B, S + 1, device=dev())
+    for t in range(H):
+        _lib.check(lib.drpo_philox_normal(eps_p[t].data_ptr(), B, A, None, seed, 1, t, None), "philox")
+        _lib.check(lib.drpo_philox_normal(eps_m[t].data_ptr(), B, S + 1, None, seed, 2, t, None), "philox")
+    torch.cuda.synchronize()
+    return eps_p.cpu(), eps_m.cpu()
+
+
+@pytest.mark.parametrize("tag,S,A,C,B", [("quadrotor", 12, 2, 2, 5000), ("cartpole", 4, 1, 4, 3000), ("safetygym60", 60, 2, 1, 1500)])
+def test_bf16_philox_rollout_vs_oracle(tag, S, A, C, B):
+    """The configuration bench.py times (bf16 GEMMs + IN-KERNEL Philox draws) value-checked against the oracle: the oracle is fed
+    the exported stream of the same (seed, tag, step, trajectory id) keys.  Step 0 within 2e-2, masks equal outside the margin,
+    per-step counts within 2 %; then every later step teacher-forced (the oracle steps from the GPU's own stored states of that
+    step, with the draws of the surviving trajectory ids) so that every step's values are held to 2e-2, not only step 0."""
+    spec, H = {"quadrotor": O.env_quadrotor(), "cartpole": O.env_cartpole(), "safetygym60": O.env_safetygym60()}[tag], 10
+    g = torch.Generator().manual_seed(133)
+    init = torch.randn(B, S, generator=g) * 0.3
+    if tag == "quadrotor":
+        init[:, 2] = 0.55 + 0.9 * torch.rand(B, generator=g)
+    members = [int(x) for x in torch.randint(0, 5, (H,), generator=g)]
+    alg = _philox_alg(spec, S, A, C, B, H)
+    wm, ws = O.make_ensemble_weights(41, S, A, diff_scale=0.05), O.make_ssac_weights(42, S, A, C)
+    view = alg.rollout(alg.actor, initial_states=to_dev(init), member_idx=members)
+    torch.cuda.synchronize()
+    eps_p, eps_m = _export_philox(alg, B, H, S, A)
+    assert abs(float(eps_m.mean())) < 0.02 and abs(float(eps_m.std()) - 1) < 0.02 and abs(float(eps_p.std()) - 1) < 0.03
+    ref, counts, _ = O.rollout(ws, wm, spec, init, H, eps_p, eps_m, members)
+    steps, got_counts = _steps(view)
+    assert got_counts[0] == B
+    for k in ("states", "actions", "next_states", "rewards"):
+        assert_close(steps[0][k], ref[k][:B], 2e-2, f"{tag}.{k} step 0 (philox)")
+    cv_ref = ref["constraint_values"][:B].reshape(B, -1)
+    margin = cv_ref.abs().min(dim=1).values > 0.05
+    assert torch.equal(steps[0]["violations"].cpu()[margin], ref["violations"][:B][margin])
+    for a, b in zip(got_counts, counts):
+        assert abs(a - b) <= max(3, 0.02 * b), (got_counts, counts)
+    # teacher-forced: step t of the oracle from the GPU's stored states of step t
+    ids = torch.arange(B)
+    for t in range(H):
+        if got_counts[t] == 0:
+            break
+        st = {k: v.cpu() for k, v in steps[t].items()}
+        assert len(ids) == got_counts[t]
+        act, _, _, _ = O.policy_act(ws, "actor.", st["states"], eps_p[t][ids])
+        nxt, rew = O.ensemble_sample(wm, st["states"], act, members[t], eps_m[t][ids])
+        assert_close(st["actions"], act, 2e-2, f"{tag} step {t} actions (teacher-forced)")
+        assert_close(st["next_states"], nxt, 2e-2, f"{tag} step {t} next_states (teacher-forced)")
+        assert_close(st["rewards"], rew, 2e-2, f"{tag} step {t} rewards (teacher-forced)")
+        ids = ids[~st["dones"]]
+
+
+@pytest.mark.parametrize("tag,S,A,C,B", [("quadrotor", 12, 2, 2, 4000), ("tracking", 51, 2, 1, 1200)])
+def test_bf16_injected_rollout_teacher_forced_every_step(tag, S, A, C, B):
+    """Injected-noise bf16 rollout: every step (not only step 0) against the oracle stepping from the stored states."""
+    spec, H = {"quadrotor": O.env_quadrotor(), "tracking": O.env_tracking(10, 1)}[tag], 10
+    wm, ws = O.make_ensemble_weights(31, S, A, diff_scale=0.05), O.make_ssac_weights(32, S, A, C)
+    g = torch.Generator().manual_seed(233)
+    init = torch.randn(B, S, generator=g) * 0.3
+    if tag == "quadrotor":
+        init[:, 2] = 0.55 + 0.9 * torch.rand(B, generator=g)
+    eps_p, eps_m = torch.randn(H, B, A, generator=g), torch.randn(H, B, S + 1, generator=g)
+    members = [int(x) for x in torch.randint(0, 5, (H,), generator=g)]
+    alg = _alg(spec, wm, ws, B, S, A)
+    alg.horizon = H
+    view = alg.rollout(alg.actor, initial_states=to_dev(init), noise=(to_dev(eps_p), to_dev(eps_m)), member_idx=members)
+    torch.cuda.synchronize()
+    steps, got_counts = _steps(view)
+    ids = torch.arange(B)
+    for t in range(H):
+        if got_counts[t] == 0:
+            break
+        st = {k: v.cpu() for k, v in steps[t].items()}
+        act, _, _, _ = O.policy_act(ws, "actor.", st["states"], eps_p[t][ids])
+        nxt, rew = O.ensemble_sample(wm, st["states"], act, members[t], eps_m[t][ids])
+        for k, want in (("actions", act), ("next_states", nxt), ("rewards", rew)):
+            assert_close(st[k], want, 2e-2, f"{tag} step {t} {k} (teacher-forced)")
+        ids = ids[~st["dones"]]

@@ -41,18 +41,24 @@ def oracle_spec_to_device_env(spec):
 
 
 def assert_close(got, want, rtol=1e-5, what="", max_outlier_frac=0.0):
-    """|got-want| <= rtol*|want| + rtol*max|want|  — "within rtol relative" to the tensor's scale."""
+    """Scale-relative closeness: every element must satisfy |got-want| <= rtol*|want| + rtol*max|want|, i.e. the error is
+    bounded by rtol of the element plus rtol of the tensor's largest magnitude (at most 2*rtol of the scale).  This is NOT a
+    pure per-element relative error: values much smaller than the tensor's scale are held to the scale's tolerance.  NaNs must
+    sit in the same places.  Returns max|err| / max|want|."""
     got = torch.as_tensor(got).detach().double().cpu()
     want = torch.as_tensor(want).detach().double().cpu()
     assert got.shape == want.shape, (what, got.shape, want.shape)
     if want.numel() == 0:
         return 0.0
-    scale = float(want.abs().max())
+    nan_g, nan_w = torch.isnan(got), torch.isnan(want)
+    finite_w = want[~nan_w]
+    scale = float(finite_w.abs().max()) if finite_w.numel() else 0.0
     err = (got - want).abs()
     tol = rtol * want.abs() + rtol * max(scale, 1e-30)
-    bad = (err > tol) | torch.isnan(got) != torch.isnan(want)
+    bad = ((err > tol) & ~nan_g & ~nan_w) | (nan_g != nan_w)
     frac = float(bad.double().mean())
-    rel = float(err.max() / max(scale, 1e-30))
+    ok = ~nan_g & ~nan_w
+    rel = float(err[ok].max() / max(scale, 1e-30)) if bool(ok.any()) else 0.0
     assert frac <= max_outlier_frac, f"{what}: {int(bad.sum())}/{bad.numel()} elements off, max err/scale {rel:.3e} (rtol {rtol})"
     return rel
 
