@@ -30,7 +30,7 @@ CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload (1 M rows), from the
 # `ncu --set full` capture of the final round-1 kernel (profiles/r1_ncu_full_rollout_step_1M_final_raw.csv: 52.9 MB read + 17.2 MB
 # written - 48 MB of states in; most of the 60 MB of outputs is still in L2 when the kernel ends); null when no capture exists
-TRAFFIC_BYTES_PER_LAUNCH = {"quadrotor": 70104064}
+TRAFFIC_BYTES_PER_LAUNCH = {("quadrotor", 1_000_000): 70104064}
 # the same for one critic_fused_kernel launch at B = 65 536, tracking dims (profiles/r1_ncu_full_critic_fused_64k_raw.csv:
 # 44.2 MB read + 378.2 MB written: the saved bf16 activations the dW kernel consumes)
 CRITIC_TRAFFIC_BYTES_PER_LAUNCH = {("tracking", 65536): 422400000}
@@ -103,8 +103,8 @@ class ClockSampler:
             except Exception:
                 pass
             # every NVML query perturbs the run it observes (driver locks; a sample landing inside a 0.25 s timed region was
-            # measured to cost ~1 ms per rollout step): one sample early in the region, then one per second
-            self._stop.wait(float(os.environ.get("DRPO_BENCH_CLOCK_INTERVAL", "1.0")))
+            # measured to cost ~1 ms per rollout step): one sample early in the region, then one every 100 ms (~1 % of the region)
+            self._stop.wait(float(os.environ.get("DRPO_BENCH_CLOCK_INTERVAL", "0.1")))
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -142,30 +142,30 @@ def build_alg(workload, B0, device, precision):
     return alg
 
 
-def run_ours(args):
-    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) go to stderr
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
+def shard_rows(B_global, rank, world):
+    """rank r rolls out rows [r*B0/N, (r+1)*B0/N) of the global start-state matrix."""
+    B = B_global // world
+    return rank * B, B
+
+
+def measure_rollout(args, lib, workload, B_global, scaling, device, rank, world, precision, with_e2e=True, steps=None, prewarm=0.5):
+    """Device-resident value, end-to-end value and the dominant kernel's roofline for one workload.  `scaling` = "strong": the
+    B_global start states are split over the ranks (same global matrix, global trajectory ids) ; "weak": B_global per rank."""
+    import ctypes
     import torch.distributed as dist
     import drpo_b200
     from drpo_b200 import _lib, synthetic
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
-    lib = _lib.load()
-    precision = {"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16}[args.precision]
-    workload = args.workload
     _, S, A, C = synthetic.WORKLOADS[workload]
-    B0 = args.batch or DEFAULT_B0[workload]
-    alg = build_alg(workload, B0, device, precision)
-    alg.shard_rank, alg.shard_world = rank, world          # weak scaling: every rank rolls out its own B0 start states
-    init_host = synthetic.make_start_states(workload, B0, 4354 + rank).pin_memory()
+    steps = steps or args.steps
+    if scaling == "strong":
+        lo, B = shard_rows(B_global, rank, world)
+        init_host = synthetic.make_start_states(workload, B_global, 4354)[lo:lo + B].contiguous().pin_memory()
+    else:
+        lo, B = rank * B_global, B_global
+        init_host = synthetic.make_start_states(workload, B, 4354 + rank).pin_memory()
+    alg = build_alg(workload, B, device, precision)
+    alg.shard_rank, alg.shard_world = rank, world
+    alg._traj_id_offset_override = lo                  # global id of this shard's row 0: Philox draws do not depend on N
     init_dev = init_host.to(device)
     members = [i % 5 for i in range(HORIZON)]
 
@@ -187,7 +187,7 @@ def run_ours(args):
         return view.step_counts.to("cpu", non_blocking=False)                  # D2H of the step's result
 
     t_pre = time.perf_counter()                       # untimed pre-warm: bring the SM clocks up before the W warm-up steps
-    while time.perf_counter() - t_pre < 0.5:
+    while time.perf_counter() - t_pre < prewarm:
         step_device(); torch.cuda.synchronize()
     total = torch.zeros((), dtype=torch.int64, device=device)
     for _ in range(args.warmup):
@@ -198,10 +198,10 @@ def run_ours(args):
     # ---- device-resident timing: K steps between two events ---------------------------------------------------
     launches0 = lib.drpo_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(device.index or 0) as clocks:
         barrier()
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             view = step_device()
             total += view.step_counts[-1]
         ev1.record()
@@ -212,36 +212,37 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
-    ms_total = float(ms)
-    transitions = int(tot)
-    value = transitions / (ms_total * 1e-3)
+    ms_total, transitions = float(ms), int(tot)
+    res = {"value": transitions / (ms_total * 1e-3), "ms_per_step": ms_total / steps, "transitions_per_step": transitions / steps,
+           "gpu_launches": int(launches), "clocks": clocks.summary(), "rows_per_gpu": B, "steps": steps}
 
     # ---- end-to-end timing through the public API with host inputs ------------------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    barrier()
-    tot_e = 0
-    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_ev0.record()
-    for _ in range(args.steps):
-        tot_e += int(step_e2e()[-1])
-    t_ev1.record()
-    barrier()
-    ms_e = torch.tensor([t_ev0.elapsed_time(t_ev1)], device=device, dtype=torch.float64)
-    te = torch.tensor([tot_e], device=device, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(te)
-    e2e_value = int(te) / (float(ms_e) * 1e-3)
+    if with_e2e:
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        barrier()
+        tot_e = 0
+        t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_ev0.record()
+        for _ in range(steps):
+            tot_e += int(step_e2e()[-1])
+        t_ev1.record()
+        barrier()
+        ms_e = torch.tensor([t_ev0.elapsed_time(t_ev1)], device=device, dtype=torch.float64)
+        te = torch.tensor([tot_e], device=device, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(te)
+        res["e2e"] = {"value": int(te) / (float(ms_e) * 1e-3), "unit": "transitions/s", "h2d_bytes_per_step": int(init_host.numel() * 4),
+                      "d2h_bytes_per_step": int((HORIZON + 1) * 4)}
 
-    # ---- roofline of the dominant kernel: rollout_step_umma_kernel, one launch per rollout step.  Its launches are bracketed
+    # ---- roofline of the dominant kernel: the fused rollout step kernel, one launch per rollout step.  Its launches are bracketed
     #      by CUDA events on the launching stream (drpo_timing_enable) over K more steps of the same workload ----------------
     pk = peaks()
-    step_ms = ms_total / args.steps
-    import ctypes
+    step_ms = ms_total / steps
     rows_launched, kt, kn, ksat = 0, ctypes.c_double(0.0), ctypes.c_int64(0), ctypes.c_double(0.0)
     lib.drpo_timing_enable(1)
-    for _ in range(args.steps):
+    for _ in range(steps):
         v = step_device()
         rows_launched += int(v.step_counts[:-1].sum())               # alive rows of every step = rows each launch processed
     torch.cuda.synchronize()
@@ -252,10 +253,10 @@ def run_ours(args):
         flops_per_launch = flops_per_transition(S, A) * rows_launched / kn.value
         achieved_tf = flops_per_launch / (avg_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                    "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(workload),
+                    "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": TRAFFIC_BYTES_PER_LAUNCH.get((workload, B)),
                     "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                    "kernel": "rollout_step_umma_kernel (policy + ensemble-member GEMM chain + epilogues), one launch per rollout step",
-                    "avg_launch_ms": round(avg_ms, 4), "launches_timed": int(kn.value), "kernel_share_of_step": round(kt.value / (step_ms * args.steps), 3),
+                    "kernel": "rollout_step kernel (policy + ensemble-member tcgen05 GEMM chain + epilogues), one launch per rollout step",
+                    "avg_launch_ms": round(avg_ms, 4), "launches_timed": int(kn.value), "kernel_share_of_step": round(kt.value / (step_ms * steps), 3),
                     "algorithmic_flops_per_transition": flops_per_transition(S, A), "rows_per_launch": round(rows_launched / kn.value, 1)}
         # the step's HBM-bound satellites (hooks + ring store, order-preserving compaction): algorithmic bytes per row =
         # read 4(2S+A+1) + write record 4(2S+A+1+C)+2 + done flag 1 (store), read done 1 + 4S + id 4, write survivors 4S+4 (compaction)
@@ -266,42 +267,176 @@ def run_ours(args):
                                        "peak": pk["hbm"], "unit": "GB/s", "frac": round(sat_gbs / pk["hbm"], 4),
                                        "avg_ms_per_step": round(ksat.value / kn.value, 4), "algorithmic_bytes_per_row": sat_bytes_row}
     else:
-        per_gpu_tr_per_step = transitions / world / args.steps
+        per_gpu_tr_per_step = transitions / world / steps
         achieved_tf = flops_per_transition(S, A) * per_gpu_tr_per_step / (step_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                     "frac": round(achieved_tf / pk["tensor_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " (sustained)",
                     "kernel": "whole rollout step (fp32 path: GEMM + elementwise kernel chain)",
                     "algorithmic_flops_per_transition": flops_per_transition(S, A)}
-
-    out = {
-        "metric": "model_rollout_transitions_per_s", "value": value, "unit": "transitions/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"{workload} DRPO rollout: {B0} start states/GPU x horizon {HORIZON}, 7x4x200 ensemble + 256x2 actor",
-                   "state_dim": S, "action_dim": A, "con_dim": C, "start_states_per_gpu": B0, "horizon": HORIZON,
-                   "precision": args.precision, "parallelism": f"dp{world} (start states sharded, no collective)",
-                   "l2": "per-step working set (states in + records out) exceeds the 126 MB L2"},
-        "transitions_per_step": transitions / args.steps,
-        "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": int(init_host.numel() * 4),
-                "d2h_bytes_per_step": int((HORIZON + 1) * 4)},
-        "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
-        "roofline": roofline,
-    }
-
+    res["roofline"] = roofline
     _lib.check_kernel_status("bench rollout")        # a pipeline-protocol time-out inside the fused kernel would invalidate the numbers
+    del alg
+    return res
+
+
+def multi_rank_check(device, rank, world, precision):
+    """N-rank result == 1-rank result (SURVEY.md §8e "Parity across N"), run inside the scaling bench itself on the real GPUs / NCCL:
+    (1) rollout: every rank rolls out its row shard of a 65 536-row global matrix AND the whole matrix; its shard's rows must be
+        bit-identical to its block of the full run at every step (Philox draws keyed by global trajectory id, rows independent);
+    (2) critic: 3 data-parallel updates from DIFFERENT initial weights per rank (the first step broadcasts rank 0's state) must leave
+        bit-identical parameters on every rank, equal to 3 single-process updates on the full batch up to fp32 summation order."""
+    import torch.distributed as dist
+    import drpo_b200
+    from drpo_b200 import synthetic
+    out = {}
+    # ---- (1) rollout shards ----
+    workload, Bg, H = "quadrotor", 65536, 5
+    _, S, A, C = synthetic.WORKLOADS[workload]
+    init = synthetic.make_start_states(workload, Bg, 977)
+    members = [3, 1, 4, 0, 2]
+
+    def roll(rows_lo, rows_n):
+        alg = build_alg(workload, rows_n, device, precision)
+        alg.horizon = H
+        alg._traj_id_offset_override = rows_lo
+        view = alg.rollout(alg.actor, initial_states=init[rows_lo:rows_lo + rows_n].to(device), member_idx=members)
+        counts = view.counts()
+        rows = view.get(as_dict=True)
+        return counts, rows
+    lo, n = shard_rows(Bg, rank, world)
+    c_shard, r_shard = roll(lo, n)
+    c_full, r_full = roll(0, Bg)
+    allc = [torch.zeros(H, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(allc, torch.tensor(c_shard, dtype=torch.int64, device=device))
+    allc = torch.stack(allc).cpu()                                   # [world, H]
+    ok = allc.sum(0).tolist() == c_full
+    off_s = off_f = 0
+    for t in range(H):
+        before = int(allc[:rank, t].sum())
+        for k, v in r_shard.items():
+            ok = ok and torch.equal(v[off_s:off_s + c_shard[t]], r_full[k][off_f + before:off_f + before + c_shard[t]])
+        off_s += c_shard[t]; off_f += c_full[t]
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["rollout_shard_rows_bit_identical_to_single_rank"] = bool(int(flag))
+    out["rollout_counts_full"] = c_full
+    # ---- (2) critic replicas ----
+    wl, Bc = "tracking", 8192
+    _, S, A, C = synthetic.WORKLOADS[wl]
+    full = synthetic.make_critic_batch(wl, Bc, 8101)
+
+    def make(seed, B):
+        cfg = drpo_b200.SSAC.Config(); cfg.batch_size = B; cfg.constraint_critic_cfg.std_ratio = 1.0
+        sv = drpo_b200.SSAC(cfg, S, A, C, HORIZON, 100, 1000, 10, 5.0, device=device)
+        sv.load_state_dict(synthetic.make_ssac_weights(seed, S, A, C), strict=False)
+        sv.precision = precision
+        return sv
+    Bl = Bc // world
+    dp = make(500 + rank, Bl)                                        # rank-dependent start: sync_replicas must fix it
+    dp.data_parallel = True
+    one = make(500, Bc)
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    for _ in range(3):
+        dp.update_critic(*[t[sl].to(device) for t in full])
+        one.update_critic(*[t.to(device) for t in full])
+    mine = torch.cat([dp._critic_arena, dp._target_arena, dp.critic_optimizer.m, dp.critic_optimizer.v])
+    ref0 = mine.clone()
+    dist.broadcast(ref0, src=0)
+    same = torch.tensor([1 if torch.equal(ref0, mine) else 0], device=device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out["critic_params_bit_identical_across_ranks"] = bool(int(same))
+    diff = (dp._critic_arena - one._critic_arena).abs()
+    lr = 3e-4
+    out["critic_vs_single_rank"] = {"max_abs_param_diff": float(diff.max()), "frac_within_1e-5": float((diff <= 1e-5 * one._critic_arena.abs().clamp_min(1e-3)).float().mean()),
+                                    "bound": "Adam's first steps move a weight by ~lr*sign(g): fp32 summation order can flip only weights with |g| ~ eps; <= 3 steps * lr",
+                                    "updates": 3, "global_batch": Bc}
+    ok2 = float(diff.max()) <= 3.5 * lr and out["critic_vs_single_rank"]["frac_within_1e-5"] > 0.98
+    out["pass"] = bool(out["rollout_shard_rows_bit_identical_to_single_rank"] and out["critic_params_bit_identical_across_ranks"] and ok2)
+    if not out["pass"]:
+        raise RuntimeError(f"multi-rank parity check failed on rank {rank}: {out}")
+    return out
+
+
+def run_ours(args):
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch.distributed as dist
+    import drpo_b200
+    from drpo_b200 import _lib, synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
+    lib = _lib.load()
+    precision = {"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16}[args.precision]
+    workload = args.workload
+    _, S, A, C = synthetic.WORKLOADS[workload]
+    B0 = args.batch or DEFAULT_B0[workload]
+    scaling = args.scaling
+    if scaling == "strong" and B0 % world:
+        raise SystemExit(f"--scaling strong needs the {B0} start states to divide by {world} ranks")
+
+    # ---- headline: the BASELINE split (SURVEY.md §8d/e): B0 GLOBAL start states, B0/N rows per rank, no collective --------------
+    head = measure_rollout(args, lib, workload, B0, scaling, device, rank, world, precision)
+    rows = head["rows_per_gpu"]
+    out = {
+        "metric": "model_rollout_transitions_per_s", "value": head["value"], "unit": "transitions/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"{workload} DRPO rollout: {B0 if scaling == 'strong' else B0 * world} start states in total "
+                               f"({rows} per GPU) x horizon {HORIZON}, 7x4x200 ensemble + 256x2 actor",
+                   "state_dim": S, "action_dim": A, "con_dim": C, "start_states_global": B0 if scaling == "strong" else B0 * world,
+                   "start_states_per_gpu": rows, "horizon": HORIZON,
+                   "precision": args.precision, "parallelism": f"dp{world} (start-state rows [r*B0/N, (r+1)*B0/N) per rank, global trajectory ids, no collective)",
+                   "l2": "per-step working set (states in + records out) exceeds the 126 MB L2" if rows * (8 * S + 4 * A + 12) > 126e6 else
+                         "inputs are rewritten every step by the previous step's kernels; the ring (records out) is larger than one step's working set"},
+        "transitions_per_step": head["transitions_per_step"],
+        "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"],
+        "clocks": head["clocks"],
+        "roofline": head["roofline"],
+    }
+    # ---- second field under N > 1: the weak split (B0 per GPU), short -----------------------------------------------------------
+    if world > 1 and scaling == "strong" and not args.skip_extra:
+        wk = measure_rollout(args, lib, workload, B0, "weak", device, rank, world, precision, with_e2e=False, steps=min(args.steps, 10), prewarm=0.1)
+        out["weak"] = {"scaling": "weak", "value": wk["value"], "unit": "transitions/s", "ms_per_step": wk["ms_per_step"],
+                       "start_states_per_gpu": B0, "roofline_frac": wk["roofline"]["frac"]}
+    # ---- N > 1: N-rank == 1-rank parity on the real GPUs / NCCL -----------------------------------------------------------------
+    if world > 1 and not args.skip_check:
+        out["multi_rank_check"] = multi_rank_check(device, rank, world, precision)
+    # ---- the other BASELINE rollout configs (cartpole 100 k x 10, safetygym-60 400 k x 10), N = 1 only ---------------------------
+    if world == 1 and not args.skip_extra:
+        out["other_workloads"] = {}
+        for wl in ("cartpole-move", "safetygym-point-synthetic"):
+            if wl == workload:
+                continue
+            r = measure_rollout(args, lib, wl, DEFAULT_B0[wl], "strong", device, rank, world, precision, steps=min(args.steps, 20), prewarm=0.1)
+            _, s2, a2, c2 = synthetic.WORKLOADS[wl]
+            out["other_workloads"][wl] = {"value": r["value"], "unit": "transitions/s", "ms_per_step": r["ms_per_step"],
+                                          "start_states": DEFAULT_B0[wl], "horizon": HORIZON, "state_dim": s2, "action_dim": a2, "con_dim": c2,
+                                          "transitions_per_step": r["transitions_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
+                                          "gpu_launches": r["gpu_launches"]}
     # ---- SSAC critic updates/s (second half of the metric) -------------------------------------------------------------
     if not args.skip_critic:
-        out["critic"] = bench_critic(args, device, world, rank, pk)
-    # ---- ensemble training iterations/s (BatchedGaussianEnsemble.fit's loop body): replicas only ----------
-    if not args.skip_critic:
-        out["ensemble_fit"] = bench_ensemble_fit(args, alg, workload, device, world == 1 and not args.skip_cpu)
-    # ---- safety shield latency: latency-bound, rank 0's replica only ------------------------------------
-    if not args.skip_critic:
-        out["shield"] = bench_shield(alg, workload, device, world == 1 and not args.skip_cpu)
-    # ---- CPU baseline (oracle port) on rank 0, N=1 only --------------------------------------------------------------
+        out["critic"] = bench_critic(args, device, world, rank, peaks())
+    alg = None
+    if not args.skip_critic and world == 1:
+        alg = build_alg(workload, 4096, device, precision)
+        # ---- ensemble training iterations/s (BatchedGaussianEnsemble.fit's loop body, SURVEY.md §8f row 2): replicas only ----------
+        out["ensemble_fit"] = bench_ensemble_fit(args, alg, workload, device, not args.skip_cpu)
+        # ---- safety shield latency (SURVEY.md §8f row 4): latency-bound, rank 0's replica only ------------------------------------
+        out["shield"] = bench_shield(alg, workload, device, not args.skip_cpu)
+    # ---- CPU baseline on rank 0, N=1 only: the reference itself when it is staged, else the oracle port -------------------------
     if world == 1 and not args.skip_cpu:
-        out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=5)
+        out["cpu_baseline"] = cpu_rollout_baseline(workload, args.cpu_batch, reps=3)
+        if not args.skip_extra:
+            out["reference_on_gpu"] = reference_on_gpu(workload, B0)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -388,49 +523,151 @@ def bench_critic(args, device, world, rank, pk):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU legs: the oracle port of the reference's algorithm (the reference itself is Python and cannot travel to the box)
+# CPU legs: the UNMODIFIED reference (staged under baseline/_ref by oracle/stage_reference.py, or /root/reference) driven by
+# oracle/ref_runner.py - kind "reference"; if neither exists, the oracle port (oracle/drpo_oracle.py) - kind "port".
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_rollout_baseline(workload, B0, reps):
-    from oracle import drpo_oracle as O
+def host_threads():
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _reference_rollout_callable(workload, B0):
+    """callable() -> transitions of one rollout of B0 start states x HORIZON on the host cores, and its kind."""
     from drpo_b200 import synthetic
     env_name, S, A, C = synthetic.WORKLOADS[workload]
-    spec = {"quadrotor": O.env_quadrotor, "cartpole-move": O.env_cartpole, "point-robot": O.env_point_robot,
-            "safetygym-point-synthetic": O.env_safetygym60}[workload]()
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     wm, ws = synthetic.make_ensemble_weights(64578, S, A), synthetic.make_ssac_weights(219803, S, A, C)
     init = synthetic.make_start_states(workload, B0, 4354)
+    from oracle import ref_runner
+    if ref_runner.available():
+        return ref_runner.rollout_runner(workload, S, A, C, B0, HORIZON, wm, ws, init), "reference"
+    from oracle import drpo_oracle as O
+    spec = {"quadrotor": O.env_quadrotor, "cartpole-move": O.env_cartpole, "point-robot": O.env_point_robot,
+            "safetygym-point-synthetic": O.env_safetygym60}[workload]()
     g = torch.Generator().manual_seed(1)
     eps_p, eps_m = torch.randn(HORIZON, B0, A, generator=g), torch.randn(HORIZON, B0, S + 1, generator=g)
     members = [i % 5 for i in range(HORIZON)]
-    O.rollout(ws, wm, spec, init[:2000], HORIZON, eps_p[:, :2000], eps_m[:, :2000], members)        # warm-up
-    t0, n = time.perf_counter(), 0
+    return (lambda: sum(O.rollout(ws, wm, spec, init, HORIZON, eps_p, eps_m, members)[1])), "port"
+
+
+def _time_rollouts(run, reps, threads):
+    torch.set_num_threads(threads)
+    run()                                                   # full-size warm-up: first-touch of the 1e6-slot buffers, MKL thread pool
+    best, n = None, 0
+    t_all = time.perf_counter()
     for _ in range(reps):
-        res, counts, _ = O.rollout(ws, wm, spec, init, HORIZON, eps_p, eps_m, members)
-        n += sum(counts)
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
-            "sample": f"{reps} x oracle rollout of {B0} start states x horizon {HORIZON} ({workload} dims), torch CPU fp32, {threads} threads, {dt:.1f}s"}
+        t0 = time.perf_counter()
+        n = run()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n / best, time.perf_counter() - t_all
+
+
+def cpu_rollout_baseline(workload, B0, reps):
+    """SMBPO.rollout (src/smbpo.py:229-249) of the reference on the box's host cores: all threads (`value`) and the reference's own
+    setting of 4 threads (src/cli.py:108).  Best of `reps` after a full-size warm-up (the first run on a fresh box is 2x slower)."""
+    run, kind = _reference_rollout_callable(workload, B0)
+    threads = host_threads()
+    v_all, t1 = _time_rollouts(run, reps, threads)
+    v_4, t2 = _time_rollouts(run, reps, min(4, threads))
+    torch.set_num_threads(threads)
+    what = "the reference's own SMBPO.rollout (unmodified src/, eager torch CPU fp32 + numpy hooks)" if kind == "reference" else "oracle port rollout (torch CPU fp32)"
+    return {"value": v_all, "unit": "transitions/s", "cores": threads, "kind": kind, "cpu": _cpu_model(), "host_cpus": os.cpu_count(),
+            "threads_4": {"value": v_4, "cores": min(4, threads), "note": "torch.set_num_threads(4): the reference's own setting (src/cli.py:108)"},
+            "sample": f"best of {reps} x {what} of {B0} start states x horizon {HORIZON} ({workload} dims) per thread setting, {t1 + t2:.1f}s"}
+
+
+def reference_on_gpu(workload, B0):
+    """Second, clearly labelled baseline: the UNMODIFIED reference's SMBPO.rollout in eager PyTorch ON THE B200 (cuBLAS GEMMs, one
+    ATen launch per op, 3 device->host->device hook round trips per step) at the bench's own config.  Runs in a child process
+    because the reference binds its device at import (src/torch_util.py:9)."""
+    code = r"""
+import json, sys, time, torch
+sys.path.insert(0, %r)
+from oracle import ref_shim
+if not ref_shim.reference_available():
+    print(json.dumps({"unavailable": "reference not staged"})); sys.exit(0)
+ref_shim.import_reference(device="cuda")
+from oracle import ref_runner
+from drpo_b200 import synthetic
+wl, B0, H = %r, %d, %d
+_, S, A, C = synthetic.WORKLOADS[wl]
+wm, ws = synthetic.make_ensemble_weights(64578, S, A), synthetic.make_ssac_weights(219803, S, A, C)
+init = synthetic.make_start_states(wl, B0, 4354).cuda()
+run = ref_runner.rollout_runner(wl, S, A, C, B0, H, wm, ws, init, device="cuda")
+run(); torch.cuda.synchronize()
+best = None
+for _ in range(3):
+    t0 = time.perf_counter(); n = run(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+print(json.dumps({"value": n / best, "unit": "transitions/s", "ms_per_step": best * 1e3, "transitions_per_step": n,
+                  "kind": "reference, eager PyTorch on the B200 (not the graded CPU baseline)", "start_states": B0, "horizon": H}))
+""" % (ROOT, workload, B0, HORIZON)
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": (r.stderr or "no output")[-300:]}
+    except Exception as e:                                   # a reported baseline: its failure must not void the measurement
+        return {"unavailable": repr(e)[:300]}
+
+
+def _cpu_update_baseline(which, B):
+    """One SSAC update step of the reference at minibatch B (tracking dims) on the host cores: which = 0 critic, 1 actor, 2 multiplier."""
+    from drpo_b200 import synthetic
+    _, S, A, C = synthetic.WORKLOADS[CRITIC_WORKLOAD]
+    threads = host_threads()
+    w = synthetic.make_ssac_weights(43567, S, A, C)
+    batch = synthetic.make_critic_batch(CRITIC_WORKLOAD, B, 49283)
+    from oracle import ref_runner
+    name = ("update_critic", "update_actor_and_alpha", "update_multiplier")[which]
+    if ref_runner.available():
+        fn, kind = ref_runner.critic_runner(S, A, C, B, w, batch, std_ratio=1.0)[which], "reference"
+        what = f"the reference's own SSAC.{name} (unmodified src/ssac.py, torch CPU fp32 autograd)"
+    else:
+        from oracle import drpo_oracle as O
+        g = torch.Generator().manual_seed(2)
+        hp = O.SSACHyper(std_ratio=1.0)
+        if which == 0:
+            noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g), torch.randn(B, generator=g))
+            adam = O.AdamState()
+            fn = lambda: O.critic_update(w, batch, noise, hp, 0.0, adam, 3e-4)
+        elif which == 1:
+            noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g))
+            la, adams = torch.tensor(0.0), {k: O.AdamState() for k in ("actor", "alpha", "safe")}
+            fn = lambda: O.actor_update(w, batch[0], noise, hp, la, 0, C, -float(A), adams, dict(actor=8e-5, alpha=8e-5, safe=8e-5))
+        else:
+            eps, adam = torch.randn(B, A, generator=g), O.AdamState()
+            fn = lambda: O.multiplier_update(w, batch[0], eps, hp, C, adam, 3e-4)
+        kind, what = "port", f"oracle {name} (torch CPU fp32 autograd)"
+    res = {}
+    for th in (threads, min(4, threads)):
+        torch.set_num_threads(th)
+        fn()
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        res[th] = best
+    torch.set_num_threads(threads)
+    dt = res[threads]
+    return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads, "kind": kind,
+            "threads_4": {"value": (B / res[min(4, threads)]) / CRITIC_B, "cores": min(4, threads)},
+            "sample": f"best of 3 x {what} at B={B} (tracking dims) per thread setting"}
 
 
 def cpu_critic_baseline(B):
-    from oracle import drpo_oracle as O
-    from drpo_b200 import synthetic
-    _, S, A, C = synthetic.WORKLOADS[CRITIC_WORKLOAD]
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    w = synthetic.make_ssac_weights(43567, S, A, C)
-    batch = synthetic.make_critic_batch(CRITIC_WORKLOAD, B, 49283)
-    g = torch.Generator().manual_seed(2)
-    noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g), torch.randn(B, generator=g))
-    adam, hp = O.AdamState(), O.SSACHyper(std_ratio=1.0)
-    O.critic_update(w, batch, noise, hp, 0.0, adam, 3e-4)
-    t0, reps = time.perf_counter(), 3
-    for _ in range(reps):
-        O.critic_update(w, batch, noise, hp, 0.0, adam, 3e-4)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads,
-            "kind": "port", "sample": f"{reps} x oracle critic_update at B={B} (tracking dims), torch CPU fp32 autograd, {threads} threads"}
+    return _cpu_update_baseline(0, B)
 
 
 def bench_ensemble_fit(args, alg, workload, device, with_cpu):
@@ -516,49 +753,47 @@ def bench_shield(alg, workload, device, with_cpu):
 
 
 def cpu_actor_baseline(B):
-    from oracle import drpo_oracle as O
-    from drpo_b200 import synthetic
-    _, S, A, C = synthetic.WORKLOADS[CRITIC_WORKLOAD]
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    w = synthetic.make_ssac_weights(43567, S, A, C)
-    obs = synthetic.make_critic_batch(CRITIC_WORKLOAD, B, 49283)[0]
-    g = torch.Generator().manual_seed(3)
-    noise = (torch.randn(B, A, generator=g), torch.randn(B, A, generator=g))
-    la, hp = torch.tensor(0.0), O.SSACHyper(std_ratio=1.0)
-    adams = {k: O.AdamState() for k in ("actor", "alpha", "safe")}
-    lrs = dict(actor=8e-5, alpha=8e-5, safe=8e-5)
-    O.actor_update(w, obs, noise, hp, la, 0, C, -float(A), adams, lrs)
-    t0, reps = time.perf_counter(), 3
-    for _ in range(reps):
-        O.actor_update(w, obs, noise, hp, la, 0, C, -float(A), adams, lrs)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": (B / dt) / CRITIC_B, "unit": "updates/s (64k-sample equivalents)", "samples_per_s": B / dt, "cores": threads,
-            "kind": "port", "sample": f"{reps} x oracle actor_update at B={B} (tracking dims), torch CPU fp32 autograd, {threads} threads"}
+    return _cpu_update_baseline(1, B)
 
 
 def run_reference(args):
-    """The reference's algorithm on the host cores: the oracle port (the reference is pure Python + torch; its files cannot
-    travel to the GPU box, oracle/drpo_oracle.py restates it and is pinned to it by tests/golden)."""
+    """The reference arm: the reference's own CPU implementation of the path (SMBPO.rollout, unmodified, from baseline/_ref or
+    /root/reference; the oracle port only if neither is present) on the box's host cores with every host thread, on our arm's
+    metric / unit; each step is a bounded sample of the workload (--cpu-batch start states x horizon 10), shrunk if K steps would
+    not finish within a few minutes.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from drpo_b200 import synthetic
     workload = args.workload
     _, S, A, C = synthetic.WORKLOADS[workload]
+    threads = host_threads()
+    torch.set_num_threads(threads)
     B0 = args.cpu_batch
+    run, kind = _reference_rollout_callable(workload, B0)
+    t0 = time.perf_counter(); run(); first = time.perf_counter() - t0        # warm-up 1 (also sizes the sample)
+    budget = 150.0
+    if first * (args.steps + max(args.warmup - 1, 0)) > budget and B0 > 2000:
+        B0 = max(2000, int(B0 * budget / (first * (args.steps + args.warmup))))
+        run, kind = _reference_rollout_callable(workload, B0)
+        run()
     for _ in range(max(args.warmup - 1, 0)):
-        cpu_rollout_baseline(workload, min(B0, 5000), 1)
-    t0 = time.perf_counter()
-    res = cpu_rollout_baseline(workload, B0, max(args.steps, 1))
+        run()
+    n, t0 = 0, time.perf_counter()
+    for _ in range(max(args.steps, 1)):
+        n += run()
     dt = time.perf_counter() - t0
-    out = {"impl": "reference", "metric": "model_rollout_transitions_per_s", "value": res["value"], "unit": "transitions/s",
+    value = n / dt
+    what = "the reference's own SMBPO.rollout (unmodified src/, eager torch CPU fp32 + numpy hooks)" if kind == "reference" else "oracle port rollout"
+    res = {"value": value, "unit": "transitions/s", "cores": threads, "kind": kind, "cpu": _cpu_model(), "host_cpus": os.cpu_count(),
+           "sample": f"{max(args.steps, 1)} x {what} of {B0} start states x horizon {HORIZON} ({workload} dims), {threads} threads, {dt:.1f}s"}
+    out = {"impl": "reference", "metric": "model_rollout_transitions_per_s", "value": value, "unit": "transitions/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{workload} DRPO rollout: bounded CPU sample of {B0} start states x horizon {HORIZON} per step",
                       "state_dim": S, "action_dim": A, "con_dim": C, "horizon": HORIZON},
            "cpu_baseline": res,
-           "e2e": {"value": res["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -575,6 +810,10 @@ def main():
     ap.add_argument("--critic-steps", type=int, default=20)
     ap.add_argument("--cpu-batch", type=int, default=100_000)
     ap.add_argument("--cpu-critic-batch", type=int, default=16384)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, SURVEY.md 8d/e): the workload's start states are split over the ranks; weak: that many per rank")
+    ap.add_argument("--skip-check", action="store_true", help="skip the N-rank == 1-rank parity check of the multi-GPU run")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the secondary measurements (other workloads, weak split, reference on GPU)")
     ap.add_argument("--skip-critic", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

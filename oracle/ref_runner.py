@@ -73,9 +73,9 @@ class HookEnv:
         return [seed]
 
 
-def make_reference_smbpo(workload, S, A, C, B0, H, w_model, w_ssac, critic_batch=256, std_ratio=2.0):
-    """The reference's own SMBPO (CPU) with the given seeded weights loaded."""
-    ref_shim.import_reference()
+def make_reference_smbpo(workload, S, A, C, B0, H, w_model, w_ssac, critic_batch=256, std_ratio=2.0, device="cpu"):
+    """The reference's own SMBPO with the given seeded weights loaded (CPU unless bench.py's reference-on-GPU leg asks otherwise)."""
+    ref_shim.import_reference(device)
     from src.checkpoint import CheckpointableData
     from src.env.torch_wrapper import TorchWrapper
     from src.log import default_log as log
@@ -95,15 +95,16 @@ def make_reference_smbpo(workload, S, A, C, B0, H, w_model, w_ssac, critic_batch
     else:
         factory = lambda id=None: TorchWrapper(HookEnv(spec, A, id=id))
     alg = SMBPO(cfg, factory, CheckpointableData(), 10)
+    alg.to(device)
     alg.model_ensemble.load_state_dict(w_model, strict=True)
     alg.solver.load_state_dict(dict(w_ssac), strict=False)
     alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
     return alg
 
 
-def rollout_runner(workload, S, A, C, B0, H, w_model, w_ssac, init):
+def rollout_runner(workload, S, A, C, B0, H, w_model, w_ssac, init, device="cpu"):
     """callable() -> transitions written by ONE reference SMBPO.rollout of ``init`` (virt_buffer reset before every call)."""
-    alg = make_reference_smbpo(workload, S, A, C, B0, H, w_model, w_ssac)
+    alg = make_reference_smbpo(workload, S, A, C, B0, H, w_model, w_ssac, device=device)
 
     def run():
         alg.virt_buffer._pointer = 0 if isinstance(alg.virt_buffer._pointer, int) else alg.virt_buffer._pointer * 0

@@ -139,8 +139,10 @@ def _install_stubs():
     sys.modules.setdefault("matplotlib", mpl)
 
 
-def import_reference():
-    """Make ``import src.*`` resolve to the unmodified reference, forced onto the CPU."""
+def import_reference(device="cpu"):
+    """Make ``import src.*`` resolve to the unmodified reference, forced onto ``device`` (the CPU for every parity / baseline use;
+    "cuda" only for bench.py's clearly labelled reference-on-GPU number).  The reference binds its device at import time
+    (src/torch_util.py:9), so the choice holds for the life of the process."""
     if not reference_available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
     _install_stubs()
@@ -148,5 +150,8 @@ def import_reference():
         sys.path.insert(0, REFERENCE_ROOT)
     import torch
     import src.torch_util as tu  # noqa: E402
-    tu.device = torch.device("cpu")
+    if getattr(tu, "_drpo_forced", None) not in (None, device):
+        raise RuntimeError(f"the reference is already imported on {tu._drpo_forced}")
+    tu.device = torch.device(device)
+    tu._drpo_forced = device
     return sys.modules["src"]

@@ -178,6 +178,9 @@ def test_rollout_sharding_offsets():
     seen = {}
 
     class Fake:
+        def drpo_kernel_status_peek(self):
+            return 0
+
         def drpo_rollout_workspace_bytes(self, a):
             return 1024
 

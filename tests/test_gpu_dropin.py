@@ -1,0 +1,67 @@
+"""Drop-in proof: the REFERENCE's own driver - ``SMBPO.setup()``, ``step_generator`` with its real-env stepping,
+safety-shield call sites and runtime asserts (src/smbpo.py:111-212, 293-325), ``rollout_and_update``, ``update_models``, ``evaluate``
+- runs on top of the B200 components (``drpo_b200.dropin.make_dropin``).  The reference travels to the GPU box as the staged,
+git-ignored copy ``baseline/_ref`` (oracle/stage_reference.py); the test is skipped only when no copy of the reference exists."""
+import pathlib
+import tempfile
+
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="no copy of the reference (baseline/_ref or /root/reference)")
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_reference_driver_runs_on_b200_components(prec):
+    import drpo_b200
+    from drpo_b200 import _lib, dropin
+    ref_shim.import_reference(device="cuda")               # the deployment the drop-in targets: reference driver on the GPU box
+    from src import smbpo as ref
+    from src.checkpoint import CheckpointableData
+    from src.env.point_robot import PointRobot
+    from src.env.torch_wrapper import TorchWrapper
+    from src.log import default_log as log
+    if getattr(log, "dir", None) is None:
+        log.setup(pathlib.Path(tempfile.mkdtemp()))
+    SMBPO = dropin.make_dropin(ref, precision={"fp32": drpo_b200.PREC_FP32, "bf16": drpo_b200.PREC_BF16}[prec])
+    cfg = ref.SMBPO.Config()
+    cfg.buffer_min, cfg.model_initial_steps, cfg.model_steps, cfg.model_update_period = 300, 40, 10, 20
+    cfg.rollout_batch_size, cfg.horizon, cfg.buffer_max, cfg.steps_per_epoch = 128, 5, 20000, 12
+    cfg.solver_updates_per_step = 5
+    cfg.sac_cfg.target_entropy = -2.0
+    torch.manual_seed(0)
+    alg = SMBPO(cfg, lambda id=None: TorchWrapper(PointRobot(id=id)), CheckpointableData(), 3)
+    alg.to(torch.device("cuda"))
+    assert isinstance(alg.model_ensemble, drpo_b200.BatchedGaussianEnsemble) and isinstance(alg.solver, drpo_b200.SSAC)
+    before = alg.solver._critic_arena.clone()
+    alg.setup()                                             # the reference's own setup: uniform-policy collection + initial model fit
+    assert len(alg.replay_buffer) == cfg.buffer_min and int(alg.steps_sampled) == cfg.buffer_min
+    assert alg.model_ensemble._elite_inds is not None and len(alg.model_ensemble._elite_inds) == 5
+    v0 = len(alg.virt_buffer)
+    for _ in range(25):                                     # real steps: model refits, rollout_and_update, shielded action, env asserts
+        next(alg.stepper)
+    torch.cuda.synchronize()
+    _lib.check_kernel_status("drop-in run")
+    assert int(alg.steps_sampled) == cfg.buffer_min + 25 and len(alg.replay_buffer) == cfg.buffer_min + 25
+    assert len(alg.virt_buffer) > v0 and len(alg.virt_buffer) >= 25 * cfg.rollout_batch_size
+    assert len(alg.recent_critic_losses) == 25 * cfg.solver_updates_per_step
+    losses = torch.stack([torch.as_tensor(x) for x in alg.recent_critic_losses]).float()
+    assert torch.isfinite(losses).all()
+    assert not torch.equal(before, alg.solver._critic_arena)
+    for k, v in alg.virt_buffer.get(as_dict=True).items():
+        assert torch.isfinite(v.float()).all(), k
+    # the hooks of the stored virtual transitions agree with the reference env's own numpy hooks (what step_generator asserts per real step)
+    ns = alg.virt_buffer.get("next_states")[-2000:]
+    assert torch.equal(alg.check_done(ns).cpu(), alg.virt_buffer.get("dones")[-2000:].cpu())
+    assert torch.equal(alg.check_violation(ns).cpu(), alg.virt_buffer.get("violations")[-2000:].cpu())
+    # the reference's epoch() (incl. log_statistics / evaluate_models) and evaluate() (shielded eval episodes) on top of it
+    alg.epoch()
+    res = alg.evaluate()
+    assert "eval return mean" in res
+    # state_dict round trip with the reference's key names
+    sd = alg.state_dict()
+    assert "solver.critic.qs.0.0.weight" in sd and "model_ensemble.trunk.0.weight" in sd and "steps_sampled" in sd
+    assert not any(k.startswith(("replay_buffer", "virt_buffer")) for k in sd)
