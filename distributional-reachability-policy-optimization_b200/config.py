@@ -56,11 +56,30 @@ class BaseConfig:
                 setattr(self, key, None)
 
 
+def adopt_config(own_cls, foreign):
+    """An own ``Config`` carrying the field values of a foreign config object that follows the same protocol (the reference's
+    src/config.py classes: ``vars()``, nested configs, ``Optional`` placeholders) - how the reference's driver hands its
+    ``model_cfg`` / ``sac_cfg`` to the drop-in classes.  Unknown fields are an error, exactly like ``update``."""
+    own = own_cls()
+    for key, val in foreign.vars().items():
+        assert hasattr(own, key), f"{own_cls.__qualname__} has no field {key!r} (got it from {type(foreign).__qualname__})"
+        cur = getattr(own, key)
+        if isinstance(cur, BaseConfig) and hasattr(val, "vars"):
+            setattr(own, key, adopt_config(type(cur), val))
+        elif type(val).__name__ == "Optional" and hasattr(val, "dtype"):
+            setattr(own, key, Optional(val.dtype))
+        else:
+            setattr(own, key, copy.deepcopy(val))
+    return own
+
+
 class Configurable:
     """Subclasses define a nested ``Config``; its fields become attributes of the instance."""
 
     def __init__(self, config):
-        assert type(config) is self.__class__.Config, f"expected {self.__class__.Config}, got {type(config)}"
+        if type(config) is not self.__class__.Config:
+            assert hasattr(config, "vars") and type(config).__name__ == "Config", f"expected {self.__class__.Config}, got {type(config)}"
+            config = adopt_config(self.__class__.Config, config)
         self.config = copy.deepcopy(config)
         self.config.verify()
         for key, val in self.config.vars().items():

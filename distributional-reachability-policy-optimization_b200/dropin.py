@@ -73,9 +73,6 @@ def make_dropin(ref, precision=_lib.PREC_BF16, device=None):
             return _BufferHandle(ConstraintSafetySampleBuffer(self.state_dim, self.action_dim, capacity, con_dim=self.con_dim,
                                                               device=self._b200_device))
 
-        def to(self, *a, **k):                                  # main.py calls alg.to(device): the B200 modules already live there
-            return self
-
         rollout = _B200SMBPO.rollout
         sample_batch = _B200SMBPO.sample_batch
         update_solver = _B200SMBPO.update_solver

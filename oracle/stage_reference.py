@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.environ.get("DRPO_REF_SOURCE", "/root/reference")
 DST = os.path.join(ROOT, "baseline", "_ref")
 KEEP_EXT = (".py", ".yaml", ".yml", ".json")
-SKIP_DIRS = {"viz_cartpole", "viz_quadrotor", "viz_tracking", "resources", "offline", "__pycache__"}
+SKIP_REL = {"src/viz_cartpole", "src/viz_quadrotor", "src/viz_tracking", "src/resources", "src/offline"}   # plots, fonts, offline tooling
 
 
 def stage(verbose=False):
@@ -25,8 +25,8 @@ def stage(verbose=False):
         return None
     n = 0
     for base, dirs, files in os.walk(SRC):
-        dirs[:] = [d for d in dirs if d not in SKIP_DIRS and not d.startswith(".")]
         rel = os.path.relpath(base, SRC)
+        dirs[:] = [d for d in dirs if d != "__pycache__" and not d.startswith(".") and os.path.normpath(os.path.join(rel, d)) not in SKIP_REL]
         if rel != "." and not (rel == "src" or rel.startswith("src" + os.sep) or rel == "config"):
             continue
         for f in files:

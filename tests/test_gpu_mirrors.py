@@ -67,10 +67,11 @@ def test_ensemble_loss_mirrors_match_oracle():
     ens = make_ensemble(w, S, A)
     g = torch.Generator().manual_seed(92)
     E, B = 7, 40
-    s, a = torch.randn(E, B, S, generator=g), torch.rand(E, B, A, generator=g) * 2 - 1
-    t = torch.cat([s + 0.05 * torch.randn(E, B, S, generator=g), torch.randn(E, B, 1, generator=g)], -1)
+    s, a = torch.randn(E * B + 3, S, generator=g), torch.rand(E * B + 3, A, generator=g) * 2 - 1         # + a remainder that is dropped
+    t = torch.cat([s + 0.05 * torch.randn(E * B + 3, S, generator=g), torch.randn(E * B + 3, 1, generator=g)], -1)
     assert_close(ens.compute_loss(to_dev(s), to_dev(a), to_dev(t)), O.ensemble_compute_loss(w, s, a, t), 1e-5, "compute_loss")
-    assert_close(ens._mse_loss(to_dev(s), to_dev(a), to_dev(t)), O.ensemble_mse_loss(w, s, a, t), 1e-5, "_mse_loss")
+    rb = lambda x: x[:E * B].reshape(E, B, -1)
+    assert_close(ens._mse_loss(to_dev(rb(s)), to_dev(rb(a)), to_dev(rb(t))), O.ensemble_mse_loss(w, rb(s), rb(a), rb(t)), 1e-5, "_mse_loss")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
