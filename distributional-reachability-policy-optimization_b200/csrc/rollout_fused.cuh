@@ -139,7 +139,7 @@ __device__ __forceinline__ bool cnt_reached(const uint4* c, uint32_t want) {
   return a >= want && b >= want && cc >= want && d >= want;
 }
 // bounded like every other wait of this library: a protocol bug is reported through err_flag, never a hang
-__device__ __noinline__ void cnt_wait_slow(const uint4* c, uint32_t want, int* err_flag, int code) {
+static __device__ __noinline__ void cnt_wait_slow(const uint4* c, uint32_t want, int* err_flag, int code) {
   long long t0 = 0;
 #pragma unroll 1
   for (uint32_t it = 0;; ++it) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 
 // Streamed start states: block until the row blocks that contain rows [r0, r1] have landed (their flags are written by the
 // copy engine right after the rows, in stream order).  Bounded like every other wait of this kernel.
-__device__ __noinline__ void wait_rows_ready(const int32_t* flags, int shift, int r0, int r1, int* err_flag) {
+static __device__ __noinline__ void wait_rows_ready(const int32_t* flags, int shift, int r0, int r1, int* err_flag) {
   const int c0 = r0 >> shift, c1 = r1 >> shift;
   long long t0 = 0;
   for (int c = c0; c <= c1; ++c) {
@@ -188,7 +188,7 @@ __device__ __noinline__ void wait_rows_ready(const int32_t* flags, int shift, in
 template <int W, bool kSilu>
 __device__ __forceinline__ void hidden_piece(uint32_t src, uint32_t dst, int one, bool last, uint4* drain, int q, uint32_t stamp, int lane) {
   uint32_t r[W];
-  if (W == 32) tmem_ld32(src, reinterpret_cast<uint32_t(&)[32]>(r)); else tmem_ld16(src, reinterpret_cast<uint32_t(&)[16]>(r));
+  if constexpr (W == 32) tmem_ld32(src, r); else tmem_ld16(src, r);
   tmem_ld_wait();
   if (last) {                                                   // the chunk's accumulator columns are in registers: the slot may be reused
     tc_fence_before();
@@ -207,16 +207,19 @@ __device__ __forceinline__ void hidden_piece(uint32_t src, uint32_t dst, int one
       if (one == 2 * j + 1) pk[j] = (pk[j] & 0x0000FFFFu) | 0x3F800000u;
     }
   }
-  if (W == 32) tmem_st16(dst, reinterpret_cast<const uint32_t(&)[16]>(pk)); else tmem_st8(dst, reinterpret_cast<const uint32_t(&)[8]>(pk));
+  if constexpr (W == 32) tmem_st16(dst, pk); else tmem_st8(dst, pk);
 }
 
-// one row of a staged layer input ([.., 1, 0 ..] up to kp, fp32) -> bf16 K-major canonical tile in shared memory:
-// element (row, k) at (k/8) * 2048 + row * 16 + (k%8) * 2  (A operand of an SS-mode MMA: LBO = 2048, SBO = 128)
-__device__ __forceinline__ void write_input_tile(uint8_t* tile, int row, const float* src, int kp) {
-  for (int o = 0; o < (kp >> 3); ++o) {
+// octets [o0, o1) of one row of a layer input -> bf16 K-major canonical tile in shared memory: element (row, k) at
+// (k/8) * 2048 + row * 16 + (k%8) * 2  (A operand of an SS-mode MMA: LBO = 2048, SBO = 128); `val(k)` yields element k
+template <typename F>
+__device__ __forceinline__ void write_input_octets(uint8_t* tile, int row, int o0, int o1, F val) {
+  for (int o = o0; o < o1; ++o) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = val(8 * o + e);
     uint4 v;
-    v.x = pack_bf16(src[8 * o], src[8 * o + 1]); v.y = pack_bf16(src[8 * o + 2], src[8 * o + 3]);
-    v.z = pack_bf16(src[8 * o + 4], src[8 * o + 5]); v.w = pack_bf16(src[8 * o + 6], src[8 * o + 7]);
+    v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]); v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
     *reinterpret_cast<uint4*>(tile + o * 2048 + row * 16) = v;
   }
 }
@@ -227,15 +230,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const PlanDev& plan = p.plan;
   const int S = p.S, A = p.A, O = S + 1;
-  // shared memory: [weight ring | xp | xm | ones | raw states x2 | staging rows x2 | policy noise x2 | model noise x2 | control]
+  // shared memory: [weight ring | xp | xm x2 | ones | raw states x2 | output rows | policy noise x2 | model noise x2 | control]
   uint8_t* ring = smem_raw;
   const uint32_t slot_bytes = plan.slot_bytes;
   uint8_t* xp = ring + (size_t)slot_bytes * p.stages;
   uint8_t* xm = xp + TILE_M * plan.K0p * 2;
-  uint8_t* ones = xm + TILE_M * plan.K0m * 2;
-  float* st_s = reinterpret_cast<float*>(ones + TILE_M * 16 * 2);                    // [2][128][SPs] raw states (fp32), zero tail up to K0p
-  float* st_o = st_s + 2 * TILE_M * p.SPs;                                           // [2][128][OPs] [norm s, a, 1, 0..] then [next state, reward]
-  float* st_np = st_o + 2 * TILE_M * p.OPs;                                          // [2][128][4]  policy noise
+  const uint32_t xm_bytes = TILE_M * plan.K0m * 2;                                    // xm is double-buffered: tile i+1's state part is staged during tile i
+  uint8_t* ones = xm + 2 * xm_bytes;
+  float* st_s = reinterpret_cast<float*>(ones + TILE_M * 16 * 2);                    // [2][128][SPs] raw states (fp32)
+  float* st_o = st_s + 2 * TILE_M * p.SPs;                                           // [128][OPs] means, then [next state, reward] of the current tile
+  float* st_np = st_o + TILE_M * p.OPs;                                              // [2][128][4]  policy noise
   float* st_nm = st_np + 2 * TILE_M * 4;                                             // [2][128][NM] model noise (NM = 0: drawn in place)
   SmemCtl* sm = reinterpret_cast<SmemCtl*>(st_nm + 2 * TILE_M * p.NM);
   int* err = p.err_flag;
@@ -268,9 +272,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
     for (int i = t0; i < MAX_IG; i += NUM_THREADS) sm->ig[i] = plan.ig[i];
     for (int i = t0; i < MAX_BLOCKS; i += NUM_THREADS) sm->blk[i] = plan.blk[i];
     for (int i = t0; i < N_HID * N_GROUPS; i += NUM_THREADS) sm->epi[i] = plan.epi[i];
-    // constant tails of the staging rows: [.., 1, 0, 0 ..] = bias slot and K padding of the two input layers
-    for (int i = t0; i < 2 * TILE_M * p.SPs; i += NUM_THREADS) { const int c = i % p.SPs; st_s[i] = c == plan.xp_one ? 1.f : 0.f; }
-    for (int i = t0; i < 2 * TILE_M * p.OPs; i += NUM_THREADS) { const int c = i % p.OPs; st_o[i] = c == plan.xm_one ? 1.f : 0.f; }
+    for (int i = t0; i < 2 * TILE_M * p.SPs; i += NUM_THREADS) st_s[i] = 0.f;      // rows past the end of the batch stay finite
+    for (int i = t0; i < TILE_M * p.OPs; i += NUM_THREADS) st_o[i] = 0.f;
     for (int i = t0; i < TILE_M * 16; i += NUM_THREADS) {       // ones tile: element (row, k) at (k/8)*2048 + row*16 + (k%8)*2, k = 0, 1 -> 1.0
       const int k = (i >> 10) * 8 + (i & 7);
       reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(k < 2 ? 1.f : 0.f);
@@ -309,7 +312,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       int b = (int)me, s = (int)me % p.stages;
       uint32_t ring_par = ((int)me / p.stages) & 1u;
       const uint32_t full_base = smem_u32(&sm->half_full[0][0]), out_base = smem_u32(&sm->out_full[0]);
-      const uint32_t xp_a = smem_u32(xp) >> 4, xm_a = smem_u32(xm) >> 4, ones_a = smem_u32(ones) >> 4;
+      const uint32_t xp_a = smem_u32(xp) >> 4, xm_a = smem_u32(xm) >> 4, ones_a = smem_u32(ones) >> 4, xm_step = xm_bytes >> 4;
       uint32_t L0 = 0;                                           // hidden layers completed before this tile: 6 * t
       for (uint32_t g = me; g < total; g += 2u) {
         const BlockRec blk = sm->blk[b];
@@ -328,7 +331,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           const int nk = r.nk;
           if (r.flags & IGF_SS) {
             const uint32_t src = (r.flags >> IGF_SRC_SHIFT) & 3u;
-            const uint32_t a_lo = (((src == 0 ? xp_a : (src == 1 ? xm_a : ones_a)) + r.a_src) & 0x3FFFu) | (128u << 16);   // LBO 2048 B
+            const uint32_t a_lo = (((src == 0 ? xp_a : (src == 1 ? xm_a + (t & 1u) * xm_step : ones_a)) + r.a_src) & 0x3FFFu) | (128u << 16);   // LBO 2048 B
             const uint32_t a_hi = 8u | (1u << 14);                                                                          // SBO 128 B
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -401,13 +404,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       cp_async_commit();
     };
     auto prologue = [&](int tile, int buf, uint32_t it) {
-      // ---- policy input [s, 1] -> shared-memory A tile; normalised state -> staging row; the tile's Gaussian draws ----
+      // ---- policy input [s, 1] and the state part of the member input [(s - mean)/(std + 1e-6), ..] -> shared-memory A tiles ----
       cp_async_wait_all();
       named_bar_sync(1, GROUP_THREADS);                                   // the tile's states landed (all of the group's copies)
       const float* ps = st_s + buf * TILE_M * p.SPs + t * p.SPs;
-      float* po = st_o + buf * TILE_M * p.OPs + t * p.OPs;
-      write_input_tile(xp, t, ps, plan.K0p);
-      for (int cc = 0; cc < S; ++cc) po[cc] = (ps[cc] - sm->norm_mean[cc]) * sm->norm_inv[cc];        // src/dynamics.py:113
+      const int xp_one = plan.xp_one;
+      write_input_octets(xp, t, 0, plan.K0p >> 3, [&](int k) { return k < S ? ps[k] : (k == xp_one ? 1.f : 0.f); });
+      write_input_octets(xm + (it & 1u) * xm_bytes, t, 0, S >> 3, [&](int k) { return (ps[k] - sm->norm_mean[k]) * sm->norm_inv[k]; });   // src/dynamics.py:113
       fence_proxy_async();                                                // generic-proxy writes of xp -> visible to the tensor core
       if (lane == 0) cnt_publish(&sm->cnt[CNT_TILE], q, it + 1u);
       // torch.normal in policy.act, randn_like in ensemble.sample: keyed by the row's global trajectory id (independent of sharding
@@ -430,7 +433,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       const bool valid = t < rows;
       const int64_t row = row0 + t;
       const float* my_s = st_s + buf * TILE_M * p.SPs + t * p.SPs;
-      float* my_o = st_o + buf * TILE_M * p.OPs + t * p.OPs;
+      float* my_o = st_o + t * p.OPs;
       // ---- policy head: [mu, raw] -> a = tanh(mu + exp(-6 + 10 sigmoid(raw)) eps)      src/policy.py:89-97 ----
       mbar_wait(&sm->out_full[0], it & 1, err, 7);
       tc_fence_after();
@@ -445,17 +448,24 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         else if (A == 2) { raw4[0] = __uint_as_float(r[2]); raw4[1] = __uint_as_float(r[3]); }
         else if (A == 3) { raw4[0] = __uint_as_float(r[3]); raw4[1] = __uint_as_float(r[4]); raw4[2] = __uint_as_float(r[5]); }
         else { raw4[0] = __uint_as_float(r[4]); raw4[1] = __uint_as_float(r[5]); raw4[2] = __uint_as_float(r[6]); raw4[3] = __uint_as_float(r[7]); }
+        float act4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           if (jj < A) {
             const float sd = __expf(-6.f + __fdividef(10.f, 1.f + __expf(-raw4[jj])));
-            const float a = tanh_fast(fmaf(ev[jj], sd, mu4[jj]));
-            my_o[S + jj] = a;
-            if (valid) p.actions[row * A + jj] = a;
+            act4[jj] = tanh_fast(fmaf(ev[jj], sd, mu4[jj]));
+            if (valid) p.actions[row * A + jj] = act4[jj];
           }
         }
-        // model input x0 = [(s - mean)/(std + 1e-6), a, 1]: the normalised part was written by the prologue  (src/dynamics.py:113-114)
-        write_input_tile(xm, t, my_o, plan.K0m);
+        // member input x0 = [(s - mean)/(std + 1e-6), a, 1]  (src/dynamics.py:113-114): the octets that hold only state elements were
+        // staged by the prologue; the ones from the first action element on are written here
+        const int xm_one = plan.xm_one;
+        write_input_octets(xm + (it & 1) * xm_bytes, t, S >> 3, plan.K0m >> 3, [&](int k) {
+          if (k < S) return (my_s[k] - sm->norm_mean[k]) * sm->norm_inv[k];
+          const int ja = k - S;
+          const float av = ja == 0 ? act4[0] : (ja == 1 ? act4[1] : (ja == 2 ? act4[2] : (ja == 3 ? act4[3] : 0.f)));     // 0 beyond the A real actions
+          return k == xm_one ? 1.f : av;
+        });
         fence_proxy_async();
         tc_fence_before();
         if (lane == 0) cnt_publish(&sm->cnt[CNT_XM], q, (uint32_t)it + 1u);   // also: the head accumulator has been read
@@ -508,14 +518,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       }
       if (valid) p.rewards[row] = my_o[S];
       named_bar_sync(2, GROUP_THREADS);                                  // every row of the tile is final in st_o
-      const float* so = st_o + buf * TILE_M * p.OPs;
+      const float* so = st_o;
       for (int i = ct; i < rows * S; i += GROUP_THREADS) {                // coalesced store of the tile's next states
         const int r = i / S, cc = i - r * S;
         p.next_states[row0 * S + i] = so[r * p.OPs + cc];
       }
-      named_bar_sync(2, GROUP_THREADS);                                  // st_o[buf] / st_s[buf] are rewritten from here on
-      if (plan.xm_one >= 0) my_o[plan.xm_one] = 1.f;                     // restore the bias slot the reward / state columns may have overwritten
-      for (int cc = S + A + 1; cc < plan.K0m; ++cc) my_o[cc] = 0.f;      // ... and the zero K padding (wide states: O > S + A)
+      named_bar_sync(2, GROUP_THREADS);                                  // st_o / st_s[buf] are rewritten from here on
       if (it + 2 < my_tiles) prefetch(tile_of(it + 2), buf);              // this tile's buffers are free again
     }
   }
@@ -730,11 +738,11 @@ static int build_plan(const drpo_rollout_args& a, Plan& P) {
 }
 
 static int smem_bytes_for(const Plan& P, int S, int A, int stages, int& SPs, int& OPs, int& NM) {
-  SPs = std::max(P.d.K0p, S) | 1;                          // raw state row [s, 1, 0..] padded to the first layer's K (odd stride: conflict-free)
-  OPs = std::max(P.d.K0m, S + 1) | 1;                      // [norm s, a, 1, 0..] padded to trunk0's K; later [next state, reward]
+  SPs = S | 1;                                             // raw state row (odd stride: conflict-free row-per-thread access)
+  OPs = (S + 1) | 1;                                       // [means], then [next state, reward] of the current tile
   NM = (S + 1) <= 16 ? round_up(S + 1, 4) + 4 : 0;         // staged model noise (+4: conflict-free float4 rows); wide states draw in place
-  return (int)((size_t)P.d.slot_bytes * stages + (size_t)TILE_M * (P.d.K0p + P.d.K0m + 16) * 2 +
-               (size_t)TILE_M * (2 * SPs + 2 * OPs + 2 * 4 + 2 * NM) * 4 + sizeof(SmemCtl) + 64);
+  return (int)((size_t)P.d.slot_bytes * stages + (size_t)TILE_M * (P.d.K0p + 2 * P.d.K0m + 16) * 2 +
+               (size_t)TILE_M * (2 * SPs + OPs + 2 * 4 + 2 * NM) * 4 + sizeof(SmemCtl) + 64);
 }
 
 // pack the actor (pack_pol) or one member (pack_mem) into its image

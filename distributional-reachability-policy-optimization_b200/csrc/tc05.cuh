@@ -35,7 +35,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // is out of line (every wait site costs two instructions of the small instruction cache) and as lean as possible: a failed
 // try_wait returns after only ~40 ns, so a waiting warp re-issues the loop body every ~80 cycles and those instructions
 // compete with the working warps of its scheduler (the first profile spent half of all issue slots on wait loops).
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int* err_flag, int code) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int* err_flag, int code) {
   long long t0 = 0;
 #pragma unroll 1
   for (uint32_t it = 0;; ++it) {
