@@ -163,7 +163,7 @@ class SMBPO(Configurable, nn.Module):
         if flags is not None:
             a.init_ready_flags, a.init_rows_per_flag_log2 = _lib.ptr(flags), 17
         if _debug_layer is not None:
-            n_out = 1024 if _debug_layer == 100 else [policy.net[0].weight.shape[0], policy.net[2].weight.shape[0], policy.net[4].weight.shape[0],
+            n_out = 2048 if _debug_layer == 100 else [policy.net[0].weight.shape[0], policy.net[2].weight.shape[0], policy.net[4].weight.shape[0],
                      self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim, self.model_ensemble.hidden_dim,
                      self.model_ensemble.hidden_dim, self.state_dim + 1, self.state_dim + 1][_debug_layer]
             out = torch.zeros((max(B, 8), n_out), device=initial_states.device)
