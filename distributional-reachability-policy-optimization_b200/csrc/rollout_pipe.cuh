@@ -221,6 +221,27 @@ __device__ __forceinline__ void write_input_octets(uint32_t tile_row, int o0, in
   }
 }
 
+// the same, four octets (32 elements) per round: `load(k)` (a global-memory read) of the whole round is issued before the first use, so a
+// wide state costs two or three memory round trips instead of one per octet; `fin(k, x)` turns the loaded value into element k
+template <typename L, typename F>
+__device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n_oct, L load, F fin) {
+#pragma unroll 1
+  for (int o0 = 0; o0 < n_oct; o0 += 4) {
+    float f[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) f[e] = load(8 * o0 + e);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (o0 + q < n_oct) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(fin(8 * (o0 + q) + 2 * j, f[8 * q + 2 * j]), fin(8 * (o0 + q) + 2 * j + 1, f[8 * q + 2 * j + 1]));
+        st_shared_v4(tile_row + 2048u * (o0 + q), pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+}
+
 // debug timing (kDebug build, dump_layer == 100): CTA 0 stamps clock() for its first 4 iterations into dump_out viewed as uint32
 // [(it * 64 + idx) * 8 + k].  idx = slot * 32 + e:  e 0..8 = job (issuer: k 0 counter waits done, 1 first block's weights there, 2 issued);
 // e 10..15 = hidden epilogue i (k 4 wait begin, 5 accumulator full, 6 activation published); e 20 = output group (k 0 head full,
@@ -233,6 +254,39 @@ __device__ __forceinline__ void stamp(const StepParams& p, uint32_t it, int idx,
   }
 }
 
+// ---- CTA-pair (cta_group::2) forms: one tcgen05.mma issued by the leader CTA multiplies BOTH CTAs' 128-row tiles (M = 256) with a weight
+// block of which each CTA holds half the rows in its own ring; completion is committed to the barrier at the same offset in both CTAs.
+__device__ __forceinline__ void mma2_ss_p(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.u32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+               ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 d;\n\tsetp.ne.u32 p, %5, 0;\n\tmov.b64 d, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], d, %4, p;\n\t}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit2_addr(uint32_t addr) {           // arrives on the barrier at this offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(addr), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t cols) {      // the same warp of both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code) { mbar_wait(bar, parity, err_flag, code); }
+// signal to the leader CTA's issuer: an arrival on the barrier in the leader's shared memory (local for the leader's own warps)
+// (default semantics - release at CTA scope - as CUTLASS's ClusterBarrier::arrive(cta_id): a cluster-scope release costs a ~1500-cycle
+// L1 flush per arrival, and what is published here is this CTA's own shared memory / TMEM, consumed by this CTA's own tensor core)
+__device__ __forceinline__ void arrive_leader(uint64_t* bar, uint32_t crank) {
+  if (crank == 0) mbar_arrive(bar);
+  else asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sig_arrive(uint64_t* bar, uint32_t crank) { arrive_leader(bar, crank); }
+
 struct IssueCtx {
   uint32_t ring_a, slot_a, full0, empty0;
   uint32_t ring_par, stage_a; int s, stages;
@@ -240,14 +294,15 @@ struct IssueCtx {
 };
 __device__ __forceinline__ void ring_release_advance(IssueCtx& c) {
   // frees the stage in both CTAs of the pair when the MMAs issued so far retire
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(c.empty0 + 8u * (uint32_t)c.s), "h"((uint16_t)3) : "memory");
   c.stage_a += c.slot_a;
   if (++c.s == c.stages) { c.s = 0; c.ring_par ^= 1u; c.stage_a = c.ring_a; }
 }
 // the current stage's weights have landed (usually known from the look-ahead: no shared-memory round trip on the issue path)
 __device__ __forceinline__ void ring_wait_full(IssueCtx& c, int* err) {
-  if (!c.look) mbar_wait_addr(c.full0 + 8u * (uint32_t)c.s, c.ring_par, err, 3);
+  if (!c.look) mbar_wait_addr(c.full0 + 8u * (uint32_t)c.s, c.ring_par, err, 3);      // (CTA-scope acquire + tcgen05 fence; the peer's half
+                                                                                       // was written by ITS async proxy and is read by ITS tensor core)
   c.look = 0;
   tc_fence_after();
 }
@@ -264,10 +319,10 @@ __device__ __forceinline__ uint32_t mma_block_ss2(uint32_t d, uint32_t a_lo, uin
       "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
       "setp.ne.u32 p, %8, 0;\n\t"
       "mov.b64 da, {%2, %3};\n\tmov.b64 db, {%4, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "setp.eq.u32 p, 1, 1;\n\t"
       "add.u32 ta, %2, 256;\n\tmad.lo.u32 tb, %6, 1, %4;\n\tmov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "selp.u32 %0, 1, 0, q;\n\t}\n"
       : "=r"(ok)
       : "r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(kunits), "r"(idesc), "r"(acc0), "r"(next_full), "r"(next_par)
@@ -282,12 +337,12 @@ __device__ __forceinline__ uint32_t mma_block_ss3(uint32_t d, uint32_t a_lo, uin
       "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
       "setp.ne.u32 p, %8, 0;\n\t"
       "mov.b64 da, {%2, %3};\n\tmov.b64 db, {%4, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "setp.eq.u32 p, 1, 1;\n\t"
       "add.u32 ta, %2, 256;\n\tmad.lo.u32 tb, %6, 1, %4;\n\tmov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "add.u32 ta, %2, 512;\n\tmad.lo.u32 tb, %6, 2, %4;\n\tmov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "selp.u32 %0, 1, 0, q;\n\t}\n"
       : "=r"(ok)
       : "r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(kunits), "r"(idesc), "r"(acc0), "r"(next_full), "r"(next_par)
@@ -302,14 +357,14 @@ __device__ __forceinline__ uint32_t mma_block_ss4(uint32_t d, uint32_t a_lo, uin
       "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
       "setp.ne.u32 p, %8, 0;\n\t"
       "mov.b64 da, {%2, %3};\n\tmov.b64 db, {%4, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "setp.eq.u32 p, 1, 1;\n\t"
       "add.u32 ta, %2, 256;\n\tmad.lo.u32 tb, %6, 1, %4;\n\tmov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "add.u32 ta, %2, 512;\n\tmad.lo.u32 tb, %6, 2, %4;\n\tmov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "add.u32 ta, %2, 768;\n\tmad.lo.u32 tb, %6, 3, %4;\n\tmov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %7, p;\n\t"
       "selp.u32 %0, 1, 0, q;\n\t}\n"
       : "=r"(ok)
       : "r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(kunits), "r"(idesc), "r"(acc0), "r"(next_full), "r"(next_par)
@@ -325,14 +380,14 @@ __device__ __forceinline__ uint32_t mma_block_ts4(uint32_t d, uint32_t a0, uint3
       "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t"
       "setp.ne.u32 p, %8, 0;\n\t"
       "mov.b64 db, {%4, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [%2], db, %7, p;\n\t"
       "setp.eq.u32 p, 1, 1;\n\t"
       "mad.lo.u32 tb, %6, 1, %4;\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%11], db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [%11], db, %7, p;\n\t"
       "mad.lo.u32 tb, %6, 2, %4;\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%12], db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [%12], db, %7, p;\n\t"
       "mad.lo.u32 tb, %6, 3, %4;\n\tmov.b64 db, {tb, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%13], db, %7, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [%13], db, %7, p;\n\t"
       "selp.u32 %0, 1, 0, q;\n\t}\n"
       : "=r"(ok)
       : "r"(d), "r"(a0), "r"(0u), "r"(b_lo), "r"(b_hi), "r"(kunits), "r"(idesc), "r"(acc0), "r"(next_full), "r"(next_par), "r"(a1), "r"(a2), "r"(a3)
@@ -362,7 +417,9 @@ __device__ __forceinline__ void issue_blocks(const StepParams& p, IssueCtx& c, u
   }
 }
 
-template <bool kDebug>
+// kWide: states wider than 15 (O > 16).  A separate instantiation: the wide output path (global / local-memory parking of the means and
+// draws) would otherwise cost the narrow variant instruction-cache space and a larger local frame (measured: 7 % of the step).
+template <bool kDebug, bool kWide>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1) rollout_step_pipe_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,11 +445,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
   auto tile_of = [&](int it, int slot) { return 4 * (cid + it * n_clusters) + 2 * (int)crank + slot; };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], CLUSTER); }
+    // full: the leader's barrier also collects the peer's "my half has landed" relay; empty: one multicast commit of the leader
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&sm->full[s], crank == 0 ? 2 : 1); mbar_init(&sm->empty[s], 1); }
     for (int s = 0; s < N_SLOTS; ++s) {
       mbar_init(&sm->hid_full[s], 1);
       for (int k = 0; k < 3; ++k) mbar_init(&sm->out_full[s][k], 1);
-      for (int k = 0; k < N_CNT; ++k) mbar_init(&sm->sig[s][k], k == C_HID ? 4 * N_GROUPS : 4);
+      for (int k = 0; k < N_CNT; ++k) mbar_init(&sm->sig[s][k], CLUSTER * (k == C_HID ? 4 * N_GROUPS : 4));     // (used in the leader only)
     }
     fence_barrier_init();
   }
@@ -409,7 +467,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(k < 2 ? 1.f : 0.f);
     }
   }
-  if (warp == ISSUER_WARP) tmem_alloc(&sm->tmem_base, 512);
+  if (warp == ISSUER_WARP) tmem_alloc2(&sm->tmem_base, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -431,10 +489,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           const uint32_t kbytes = jb.kstep_units << 4;
           const uint32_t n_reg = jb.n_ks - (jb.ones_ks != 0xFFFFu ? 1u : 0u);
           for (uint32_t ks = 0; ks < jb.n_ks;) {                     // blocks of kb regular k-steps, then the bias k-step on its own
-            const uint32_t nk = ks < n_reg ? min(jb.kb, n_reg - ks) : 1u, bytes = nk * kbytes, half = bytes >> 1;
-            mbar_wait(&sm->empty[s], ph ^ 1, err, 1);              // both CTAs' MMAs on the stage's previous contents are done
-            mbar_expect_tx(&sm->full[s], bytes);
-            bulk_g2s_multicast(ring + (size_t)s * slot_bytes + crank * half, img + (size_t)ks * kbytes + crank * half, half, &sm->full[s], (uint16_t)3);
+            const uint32_t nk = ks < n_reg ? min(jb.kb, n_reg - ks) : 1u, hb = kbytes >> 1;
+            mbar_wait(&sm->empty[s], ph ^ 1, err, 1);              // the pair's MMAs on the stage's previous contents are done
+            mbar_expect_tx(&sm->full[s], nk * hb);
+            // this CTA's half of the rows of each k-step tile (k-step tiles are [N x 16]: the halves are contiguous)
+            for (uint32_t k = 0; k < nk; ++k)
+              bulk_g2s(ring + (size_t)s * slot_bytes + k * hb, img + (size_t)(ks + k) * kbytes + crank * hb, hb, &sm->full[s]);
             if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
             ks += nk;
           }
@@ -444,7 +504,28 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
     // ===================== MMA issuer: one thread alternates the two slots job by job ===================================================
     // A compact program: the job and slot loops are rolled (the whole issuer is a few hundred instructions), only the MMAs of one weight
     // block are issued from straight-line code.  TMEM base = 0 (the CTA owns all 512 columns), checked here.
-    if (elect_one()) {
+    if (crank != 0) {
+      // ---- peer CTA: its MMAs are issued by the leader; relay "my half of the block has landed" to the leader's full barrier ----
+      if (elect_one()) {
+        if (tmem != 0u && atomicCAS(err, 0, 88) == 0) printf("drpo_b200: unexpected TMEM base %u\n", tmem);
+        uint32_t s = 0, ph = 0;
+        for (int it = 0; it <= my_iters; ++it)
+#pragma unroll 1
+          for (int e = 0; e < 2 * N_JOBS; ++e) {
+            const int j = plan.sched[e][1], tit = it - (int)plan.sched[e][2];
+            if (tit < 0 || tit >= my_iters) continue;
+            const JobDev& jb = plan.job[j];
+            const uint32_t n_reg = jb.n_ks - (jb.ones_ks != 0xFFFFu ? 1u : 0u);
+            for (uint32_t ks = 0; ks < jb.n_ks;) {
+              const uint32_t nk = ks < n_reg ? min(jb.kb, n_reg - ks) : 1u;
+              mbar_wait(&sm->full[s], ph, err, 2);
+              arrive_leader(&sm->full[s], 1u);
+              if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+              ks += nk;
+            }
+          }
+      }
+    } else if (elect_one()) {
       if (tmem != 0u && atomicCAS(err, 0, 88) == 0) printf("drpo_b200: unexpected TMEM base %u\n", tmem);
       IssueCtx c;
       c.ring_a = (smem_u32(ring) >> 4) & 0x3FFFu; c.slot_a = slot_bytes >> 4;
@@ -463,15 +544,15 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           if (tit < 0 || tit >= my_iters) continue;
           const uint32_t t = (uint32_t)tit;
           const JobDev& jb = plan.job[j];
-          const uint32_t idesc = jb.idesc, kunits = jb.kstep_units, kb = jb.kb, wait0 = jb.wait0, wait1 = jb.wait1;
+          const uint32_t idesc = jb.idesc, kunits = jb.kstep_units >> 1 /* this CTA's half of a k-step tile */, kb = jb.kb, wait0 = jb.wait0, wait1 = jb.wait1;
           const uint32_t n_reg = jb.n_ks - (jb.ones_ks != 0xFFFFu ? 1u : 0u);
           const uint32_t nfull = jb.nfull;
           const bool ts = jb.a_kind == A_TMEM;
           {
             {
               const uint32_t want0 = ((wait0 >> 8) & 0xFFu) + (wait0 >> 16) * t, want1 = ((wait1 >> 8) & 0xFFu) + (wait1 >> 16) * t;
-              if (wait0 && want0) mbar_wait(&sm->sig[slot][wait0 & 0xFFu], (want0 - 1u) & 1u, err, 20 + (int)(wait0 & 0xFFu));
-              if (wait1 && want1) mbar_wait(&sm->sig[slot][wait1 & 0xFFu], (want1 - 1u) & 1u, err, 20 + (int)(wait1 & 0xFFu));
+              if (wait0 && want0) mbar_wait_cluster(&sm->sig[slot][wait0 & 0xFFu], (want0 - 1u) & 1u, err, 20 + (int)(wait0 & 0xFFu));
+              if (wait1 && want1) mbar_wait_cluster(&sm->sig[slot][wait1 & 0xFFu], (want1 - 1u) & 1u, err, 20 + (int)(wait1 & 0xFFu));
             }
             stamp<kDebug>(p, t, (int)slot * 32 + j, 0);
             const uint32_t d = slot * SLOT_COLS + jb.d_col;
@@ -492,8 +573,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
                 const uint32_t b_lo = c.stage_a | (8u << 16);
                 for (uint32_t k = 0; k < nk; ++k) {
                   const uint32_t acc = (ks + k) != 0 ? 1u : 0u;
-                  if (ts) mma_ts_p(d, a0 + plan.ts_col[ks + k], b_lo + k * kunits, b_hi, idesc, acc);
-                  else mma_ss_p(d, a0 + 256u * (ks + k), a_hi, b_lo + k * kunits, b_hi, idesc, acc);
+                  if (ts) mma2_ts_p(d, a0 + plan.ts_col[ks + k], b_lo + k * kunits, b_hi, idesc, acc);
+                  else mma2_ss_p(d, a0 + 256u * (ks + k), a_hi, b_lo + k * kunits, b_hi, idesc, acc);
                 }
                 ring_release_advance(c);
                 ks += nk; left -= nk;
@@ -501,10 +582,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
             }
             if (jb.ones_ks != 0xFFFFu) {                                     // bias k-step: constant tile of ones x (hi, lo) bias block
               ring_wait_full(c, err);
-              mma_ss_p(d, ones_a, a_hi, c.stage_a | (8u << 16), b_hi, idesc, n_reg != 0 ? 1u : 0u);
+              mma2_ss_p(d, ones_a, a_hi, c.stage_a | (8u << 16), b_hi, idesc, n_reg != 0 ? 1u : 0u);
               ring_release_advance(c);
             }
-            tc_commit_addr(jb.bar == BAR_HID ? hid0 + 8u * slot : out0 + 8u * (3u * slot + (jb.bar - BAR_OUT0)));
+            tc_commit2_addr(jb.bar == BAR_HID ? hid0 + 8u * slot : out0 + 8u * (3u * slot + (jb.bar - BAR_OUT0)));
             stamp<kDebug>(p, t, (int)slot * 32 + j, 2);
           }
         }
@@ -541,6 +622,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           if (e.to_smem) {
             if (e.silu) hidden_chunk<true, true>(src, e.nc, e.n0, e.one, xrow, tdst);
             else hidden_chunk<false, true>(src, e.nc, e.n0, e.one, xrow, tdst);
+            if (lead) stamp<kDebug>(p, (uint32_t)it, slot * 32 + 10 + i, 7);
             fence_proxy_async();                                 // generic-proxy writes of X -> visible to the tensor core
           } else {
             hidden_chunk<true, false>(src, e.nc, e.n0, e.one, xrow, tdst);
@@ -548,7 +630,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->sig[slot][C_HID]);                  // activation visible to the MMAs, accumulator drained
+          if (lane == 0) sig_arrive(&sm->sig[slot][C_HID], crank);                  // activation visible to the MMAs, accumulator drained
           if (lead) stamp<kDebug>(p, (uint32_t)it, slot * 32 + 10 + i, 6);
         }
       }
@@ -564,7 +646,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
     const int sidx = slot * 32 + 20;
     float4 np4 = make_float4(0.f, 0.f, 0.f, 0.f);                          // policy draws of the staged tile
     uint32_t xn[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                     // narrow states: the staged tile's normalised state, packed bf16 pairs
-    const bool narrow = !plan.wide;                                        // S <= 15
+    constexpr bool narrow = !kWide;                                        // S <= 15
 
     auto prologue = [&](int tile, uint32_t it) {
       // ---- policy input [s, 1] -> the slot's xp tile; torch.normal of policy.act keyed by the row's global trajectory id ----
@@ -573,7 +655,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       if (valid && p.ready_flags) wait_rows_ready(p.ready_flags, p.ready_shift, (int)row, (int)row, err);
       const float* ps = p.cur + row * S;
       const int xp_one = plan.xp_one;
-      if (narrow) {                                                       // one pass over the row: raw -> xp, normalised -> registers (the
+      if constexpr (narrow) {                                             // one pass over the row: raw -> xp, normalised -> registers (the
         float sv[16];                                                     // member input is assembled from them when the action arrives)
 #pragma unroll
         for (int k = 0; k < 16; ++k) sv[k] = (k < S && valid) ? __ldg(ps + k) : 0.f;
@@ -588,11 +670,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         st_shared_v4(xprow, pk[0], pk[1], pk[2], pk[3]);
         st_shared_v4(xprow + 2048u, pk[4], pk[5], pk[6], pk[7]);          // K0p = 16
       } else {
-        write_input_octets(xprow, 0, plan.K0p >> 3, [&](int k) { return k < S ? (valid ? __ldg(ps + k) : 0.f) : (k == xp_one ? 1.f : 0.f); });
+        write_input_octets_wide(xprow, plan.K0p >> 3, [&](int k) { return (k < S && valid) ? __ldg(ps + k) : 0.f; },
+                                [&](int k, float x) { return k < S ? x : (k == xp_one ? 1.f : 0.f); });
       }
       fence_proxy_async();                                                // generic-proxy writes of xp -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->sig[slot][C_TILE]);
+      if (lane == 0) sig_arrive(&sm->sig[slot][C_TILE], crank);
       np4 = valid ? noise_get4(p.noise_p, (int64_t)p.ids[row], 0, A) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
 
@@ -633,7 +716,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           const float av = ja == 0 ? act4[0] : (ja == 1 ? act4[1] : (ja == 2 ? act4[2] : (ja == 3 ? act4[3] : 0.f)));     // 0 beyond the A real actions
           return k == xm_one ? 1.f : av;
         };
-        if (narrow) {                                                      // the state part comes from registers (staged by the prologue)
+        if constexpr (narrow) {                                            // the state part comes from registers (staged by the prologue)
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -645,15 +728,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           st_shared_v4(xrow + 2048u, pk[4], pk[5], pk[6], pk[7]);
           write_input_octets(xrow, 2, plan.K0m >> 3, tail);                // (K0m = 32 when S + A + 1 > 16)
         } else {
-          write_input_octets(xrow, 0, plan.K0m >> 3, [&](int k) {
-            if (k < S) return valid ? (__ldg(my_s + k) - sm->norm_mean[k]) * sm->norm_inv[k] : 0.f;
-            return tail(k);
-          });
+          write_input_octets_wide(xrow, plan.K0m >> 3, [&](int k) { return (k < S && valid) ? __ldg(my_s + k) : 0.f; },
+                                  [&](int k, float x) { return k < S ? (valid ? (x - sm->norm_mean[k]) * sm->norm_inv[k] : 0.f) : tail(k); });
         }
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->sig[slot][C_XM]);                    // also: the head accumulator has been read
+        if (lane == 0) sig_arrive(&sm->sig[slot][C_XM], crank);                    // also: the head accumulator has been read
         if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 1);
         if (valid) {                                                     // off the critical path: the actions go to global memory
 #pragma unroll
@@ -663,7 +744,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
       // ---- off the critical path: the slot's next prologue ----
       if (it + 1 < my_iters) prologue(tile_of(it + 1, slot), (uint32_t)it + 1u);
       if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 2);
-      if (!plan.wide) {
+      if constexpr (!kWide) {
         // ---- diff head: means = diffs + [s, 0]                                           src/dynamics.py:118 ----
         float mean[16], ev[16];
 #pragma unroll
@@ -696,7 +777,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           uint32_t r[16]; tmem_ld16(region + plan.v1_col, r); tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->sig[slot][C_OUT]);                   // both head accumulators are in registers
+          if (lane == 0) sig_arrive(&sm->sig[slot][C_OUT], crank);                   // both head accumulators are in registers
           if (kDebug && p.dump_layer == 8 && valid) for (int jj = 0; jj < 16; ++jj) if (jj < O) p.dump_out[row * O + jj] = __uint_as_float(r[jj]);
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
@@ -721,53 +802,66 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         }
       } else {
         // wide states (O > 16): the diff head's accumulator sits in columns the log-var hidden layer overwrites, so the means are
-        // parked in the output arrays (this thread's own row) until the log-var head arrives
+        // parked in the output arrays (this thread's own row) until the log-var head arrives; the Gaussian draws are generated while the
+        // log-var layers run and parked in (L2-resident) local memory
+        float evw[64];
         mbar_wait(&sm->out_full[slot][1], par, err, 7);
         tc_fence_after();
         if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 3);
         for (int c0 = 0; c0 < No; c0 += 16) {
-          uint32_t r[16]; tmem_ld16(region + plan.d1_col + (uint32_t)c0, r); tmem_ld_wait();
+          uint32_t r[16]; tmem_ld16(region + plan.d1_col + (uint32_t)c0, r);
+          float sv[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) sv[jj] = (c0 + jj < S && valid) ? __ldg(my_s + c0 + jj) : 0.f;
+          tmem_ld_wait();
           if (kDebug && p.dump_layer == 7 && valid) for (int jj = 0; jj < 16; ++jj) if (c0 + jj < O) p.dump_out[row * O + c0 + jj] = __uint_as_float(r[jj]);
           if (valid) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
               const int c = c0 + jj;
-              if (c < S) p.next_states[row * S + c] = __uint_as_float(r[jj]) + __ldg(my_s + c);
+              if (c < S) p.next_states[row * S + c] = __uint_as_float(r[jj]) + sv[jj];
               else if (c == S) p.rewards[row] = __uint_as_float(r[jj]);
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->sig[slot][C_D1R]);                     // the log-var hidden layer may overwrite the diff head
+        if (lane == 0) sig_arrive(&sm->sig[slot][C_D1R], crank);                     // the log-var hidden layer may overwrite the diff head
+        {
+          const int64_t pid = valid ? (int64_t)p.ids[row] : 0;
+          for (int cg = 0; 4 * cg < O; ++cg) {
+            const float4 e4 = valid ? noise_get4(p.noise_m, pid, cg, O) : make_float4(0.f, 0.f, 0.f, 0.f);
+            evw[4 * cg] = e4.x; evw[4 * cg + 1] = e4.y; evw[4 * cg + 2] = e4.z; evw[4 * cg + 3] = e4.w;
+          }
+        }
         mbar_wait(&sm->out_full[slot][2], par, err, 7);
         tc_fence_after();
         if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 4);
-        const int64_t pid = valid ? (int64_t)p.ids[row] : 0;
         for (int c0 = 0; c0 < No; c0 += 16) {
-          uint32_t r[16]; tmem_ld16(region + plan.v1_col + (uint32_t)c0, r); tmem_ld_wait();
+          uint32_t r[16]; tmem_ld16(region + plan.v1_col + (uint32_t)c0, r);
+          float mv[16], ev[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int c = c0 + jj;
+            mv[jj] = (c <= S && valid) ? (c < S ? p.next_states[row * S + c] : p.rewards[row]) : 0.f;
+            ev[jj] = c < O ? evw[c] : 0.f;
+          }
+          tmem_ld_wait();
           if (c0 + 16 >= No) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm->sig[slot][C_OUT]);
+            if (lane == 0) sig_arrive(&sm->sig[slot][C_OUT], crank);
           }
           if (kDebug && p.dump_layer == 8 && valid) for (int jj = 0; jj < 16; ++jj) if (c0 + jj < O) p.dump_out[row * O + c0 + jj] = __uint_as_float(r[jj]);
           if (valid) {
 #pragma unroll
-            for (int cg = 0; cg < 4; ++cg) {
-              if (c0 + 4 * cg < O) {
-                const float4 e4 = noise_get4(p.noise_m, pid, (c0 >> 2) + cg, O);
-                const float e[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int c = c0 + 4 * cg + k;
-                  if (c < O) {
-                    const float u = __expf(sm->lv_hi[c] - __uint_as_float(r[4 * cg + k]));
-                    const float sd = sm->lv_s0[c] * sqrt_fast(1.f + __fdividef(sm->lv_E[c], 1.f + u));
-                    float* dst = c < S ? p.next_states + row * S + c : p.rewards + row;
-                    *dst = fmaf(sd, e[k], *dst);
-                  }
-                }
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = c0 + jj;
+              if (c < O) {
+                const float u = __expf(sm->lv_hi[c] - __uint_as_float(r[jj]));
+                const float sd = sm->lv_s0[c] * sqrt_fast(1.f + __fdividef(sm->lv_E[c], 1.f + u));
+                float* dst = c < S ? p.next_states + row * S + c : p.rewards + row;
+                *dst = fmaf(sd, ev[jj], mv[jj]);
               }
             }
           }
@@ -779,7 +873,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                      // no CTA leaves while its peer may still multicast into it or signal its barriers
-  if (warp == ISSUER_WARP) tmem_dealloc(tmem, 512);
+  if (warp == ISSUER_WARP) tmem_dealloc2(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -813,9 +907,10 @@ static int build_plan(const drpo_rollout_args& a, Plan& P, int max_smem, int& st
   // narrow outputs: diff head at Hmp, log-var head at Hmp + No (both survive until the output group reads them);
   // wide outputs  : diff head behind the last packed chunk (overwritten by the log-var hidden layer, which therefore waits for the
   //                 output group), log-var head at 0
-  D.wide = (No > 16 || Hmp + 2 * No > SLOT_COLS) ? 1 : 0;
+  const int Nd1 = std::max(No, 32);                       // the diff head is a TS-mode pair MMA: N must be a multiple of 32
+  D.wide = (No > 16 || Hmp + Nd1 + No > SLOT_COLS) ? 1 : 0;
   D.head_col = 0;
-  if (!D.wide) { D.d1_col = Hmp; D.v1_col = Hmp + No; }
+  if (!D.wide) { D.d1_col = Hmp; D.v1_col = Hmp + Nd1; }
   else {
     {   // behind the packed activation of the last column chunk (chunk starts as in the epilogue records below)
       const int units = Hmp / 16; int n0 = 0, last_n0 = 0, last_nc = 0;
@@ -823,11 +918,11 @@ static int build_plan(const drpo_rollout_args& a, Plan& P, int max_smem, int& st
       D.d1_col = round_up(last_n0 + last_nc / 2, 16);
     }
     D.v1_col = 0;
-    if (D.d1_col + No > SLOT_COLS) { set_error("bf16 rollout: TMEM plan does not fit (model hidden %d, state dim %d)", Hm, S); return DRPO_ERR_UNSUPPORTED; }
+    if (D.d1_col + Nd1 > SLOT_COLS) { set_error("bf16 rollout: TMEM plan does not fit (model hidden %d, state dim %d)", Hm, S); return DRPO_ERR_UNSUPPORTED; }
   }
   const int n_real[N_LAYERS] = {Hp, Hp, 2 * A, Hm, Hm, Hm, Hm, O, O};
   const int k_real[N_LAYERS] = {S, Hp, Hp, S + A, Hm, Hm, Hm, Hm, Hm};
-  const int n_pad[N_LAYERS] = {Hpp, Hpp, 16, Hmp, Hmp, Hmp, Hmp, No, No};
+  const int n_pad[N_LAYERS] = {Hpp, Hpp, 16, Hmp, Hmp, Hmp, Hmp, Nd1, No};
   const int k_pad[N_LAYERS] = {K0p, Hpp, Hpp, K0m, Hmp, Hmp, Hmp, Hmp, Hmp};
   const int job_layer[N_JOBS] = {0, 1, 2, 3, 4, 5, 7, 6, 8};
   D.x_bytes = (uint32_t)(TILE_M * std::max(std::max(Hpp, Hmp), K0m) * 2);
@@ -836,12 +931,12 @@ static int build_plan(const drpo_rollout_args& a, Plan& P, int max_smem, int& st
   const int fixed = (int)(N_SLOTS * (D.x_bytes + D.xp_bytes) + TILE_M * 16 * 2 + sizeof(SmemCtl) + 64);
   max_smem -= 1024;                                                        // the kernel's static shared memory (alignment of the dynamic block)
   uint32_t slot_bytes = 0; int stages = 0;
-  for (uint32_t cand : {20480u, 16384u, 12288u, 8192u}) {
+  for (uint32_t cand : {16384u, 12288u, 8192u}) {
     const int st = std::min<int>(MAX_STAGES, (max_smem - fixed) / (int)cand);
     slot_bytes = cand; stages = st;
     if (st >= 4) break;
   }
-  if (stages < 2 || slot_bytes < (uint32_t)std::max(Hpp, Hmp) * 32u) {
+  if (stages < 2 || slot_bytes < (uint32_t)std::max(Hpp, Hmp) * 16u) {
     set_error("bf16 rollout: needs more shared memory than the device offers (%d B fixed, %d B available)", fixed, max_smem);
     return DRPO_ERR_UNSUPPORTED;
   }
@@ -854,10 +949,10 @@ static int build_plan(const drpo_rollout_args& a, Plan& P, int max_smem, int& st
     const int nks = k_pad[l] / 16 + (ones ? 1 : 0);
     P.n_pad[l] = n_pad[l]; P.n_real[l] = n_real[l]; P.k_real[l] = k_real[l]; P.n_ks[l] = nks; P.ones_ks[l] = ones ? nks - 1 : 0xFFFF;
     P.slot[l] = ones ? 0 : 1; P.job_of[l] = j;
-    J.idesc = make_idesc(n_pad[l]);
+    J.idesc = (make_idesc(n_pad[l]) & ~(0x1Fu << 24)) | ((256u >> 4) << 24);        // M = 256: both CTAs' 128-row tiles
     J.n_ks = (uint32_t)nks; J.ones_ks = ones ? (uint32_t)(nks - 1) : 0xFFFFu;
-    J.kstep_units = (uint32_t)(n_pad[l] * 32) >> 4;
-    J.kb = std::max(1u, std::min(4u, slot_bytes / (uint32_t)(n_pad[l] * 32)));
+    J.kstep_units = (uint32_t)(n_pad[l] * 32) >> 4;                                  // whole k-step tile (both halves) / 16
+    J.kb = std::max(1u, std::min(4u, slot_bytes / (uint32_t)(n_pad[l] * 16)));       // each CTA holds half the rows of a block
     J.nfull = (uint32_t)(nks - (ones ? 1 : 0)) / J.kb;
     uint32_t& off = j < 3 ? off_pol : off_mem;
     J.img_off = off; off += (uint32_t)nks * (uint32_t)n_pad[l] * 32u;

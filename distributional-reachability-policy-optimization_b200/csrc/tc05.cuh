@@ -1,5 +1,5 @@
-// tcgen05 / TMEM / TMA / mbarrier PTX wrappers shared by the fused critic kernels (critic_umma.cu).
-// (umma_rollout.cu keeps its own tuned copies; these live in a separate namespace.)
+// tcgen05 / TMEM / TMA / mbarrier PTX wrappers.
+// Shared by the fused rollout step kernel (rollout_pipe.cuh) and the fused critic kernels (critic_umma.cu).
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -40,18 +40,16 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t p
 #pragma unroll 1
   for (uint32_t it = 0;; ++it) {
     uint32_t ok;
+    // try_wait WITH a suspend-time hint: the hardware parks the warp until the phase completes (or the hint, ~1 ms, expires) and wakes
+    // it ~60 cycles after the arrival.  Without the hint a failed try_wait returns after ~40 ns and the waiting warps poll: the ncu
+    // profile of the two-tile rollout kernel (profiles/r2_rollout.md) showed 56 % of all issued warp instructions were this loop, issued
+    // with scheduler priority over the epilogue warps that were doing the work.
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "@!p mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity), "r"(1000000u) : "memory");
     if (ok) return;
-    // A failed try_wait returns after ~40 ns, so a waiting warp would re-issue this loop every ~80 cycles on the scheduler it
-    // shares with working warps (the profile of an earlier version spent 65% of all issued instructions here).  Short waits
-    // (the pipeline's hand-offs) poll back to back; long ones (output group between its chunks, idle groups at a layer
-    // boundary, the producer) back off with a short sleep.
-    if (it >= 8) __nanosleep(64);
-    if ((it & 63) == 63) {
+    if ((it & 7) == 7) {
       // ~0.5 s of SM clocks without progress is a protocol bug; once one wait of the launch failed the others give up after 1 ms
       if (t0 == 0) t0 = clock64();
       const long long dt = clock64() - t0;

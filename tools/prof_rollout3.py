@@ -28,11 +28,11 @@ for it in (1, 2):
         for s in (0, 1):
             r = st[it, s * 32 + j] - t0
             print(f"  {name} s{s}: {r[0]:8d} {r[1]:8d} {r[2]:8d} | {st[it, s * 32 + j][3]:6d}")
-    print(" hidden epilogue / slot: wait_begin acc_full published")
+    print(" hidden epilogue / slot: wait_begin acc_full chunk_done published")
     for i, name in enumerate(hid):
         for s in (0, 1):
             r = st[it, s * 32 + 10 + i] - t0
-            print(f"  {name} s{s}: {r[4]:8d} {r[5]:8d} {r[6]:8d}")
+            print(f"  {name} s{s}: {r[4]:8d} {r[5]:8d} {r[7]:8d} {r[6]:8d}")
     for s in (0, 1):
         r = st[it, s * 32 + 20] - t0
         print(f" output group s{s}: head_full {r[0]} xm_published {r[1]} next_prologue_done {r[2]} diff_full {r[3]} lvar_full {r[4]} stores_done {r[5]}")
