@@ -50,6 +50,29 @@ def flops_per_critic_sample(S, A, C):
     return 2 * (8 * Q + 2 * P + 5 * T + 9 * H)
 
 
+def flops_per_multiplier_sample(S, A, C):
+    """Dense multiply-adds x 2 of SSAC.update_multiplier (src/ssac.py:529-578) per sample: two policy forwards, two constraint-critic
+    forwards (trunk + both heads), the lambda net forward and its backward (dX of the hidden layer, both dW, head)."""
+    P = 256 * S + 65536 + 512 * A
+    QC = (S + A) * 256 + 65536 + 2 * (65536 + 256 * C)
+    L = (S + 1) * 256 + 65536 + 256
+    return 2 * (2 * P + 2 * QC + 2 * L + 65536)
+
+
+def flops_per_actor_sample(S, A, C):
+    """Dense multiply-adds x 2 of SSAC.update_actor_and_alpha (src/ssac.py:458-527) per sample: two policy forwards, Q_k forward,
+    three constraint-critic forwards, the lambda net forward; dX chains through Q_k and (twice) the constraint critic down to the
+    action columns; head + hidden dX and both dW of the two policies."""
+    P = 256 * S + 65536 + 512 * A
+    Q = (S + A) * 256 + 65536 + 256
+    QC = (S + A) * 256 + 65536 + 2 * (65536 + 256 * C)
+    L = (S + 1) * 256 + 65536 + 256
+    dQ = 256 + 65536 + 256 * A
+    dQC = 2 * (256 * C + 65536) + 65536 + 256 * A
+    dP = 2 * 512 * A + 65536 + 65536 + 256 * S
+    return 2 * (2 * P + Q + 3 * QC + L + dQ + 2 * dQC + 2 * dP)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -514,9 +537,17 @@ def bench_critic(args, device, world, rank, pk):
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         k = max(n // 2, 1)
-        res[name] = {"metric": f"ssac_{name}_updates_per_s", "value": k / (float(ms2) * 1e-3), "unit": "updates/s", "global_batch": Bg,
+        ups2 = k / (float(ms2) * 1e-3)
+        fl2 = (flops_per_actor_sample if name == "actor" else flops_per_multiplier_sample)(S, A, C)
+        ach2 = fl2 * Bg * ups2 / 1e12 / world
+        res[name] = {"metric": f"ssac_{name}_updates_per_s", "value": ups2, "unit": "updates/s", "global_batch": Bg,
                      "ms_per_update": float(ms2) / k, "gpu_launches": int(lib.drpo_launch_count() - l0),
-                     "dtype": "f32" if cprec == "fp32" else "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer"}
+                     "dtype": {"bf16": "bf16 (fused tcgen05 forward/loss/dX kernel + tcgen05 dW kernel), fp32 accumulate/optimizer",
+                               "tf32": "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer", "fp32": "f32"}[cprec],
+                     "roofline": {"bound": "tensor", "achieved": round(ach2, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                                  "frac": round(ach2 / pk["tensor_sustained"], 5), "traffic": None,
+                                  "kernel": "solver_fused_kernel ; achieved = whole update incl. dW, reductions, clip/Adam",
+                                  "algorithmic_flops_per_sample": fl2}}
     if world == 1 and not args.skip_cpu:
         res["actor"]["cpu_baseline"] = cpu_actor_baseline(args.cpu_critic_batch)
     return res

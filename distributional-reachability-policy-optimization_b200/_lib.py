@@ -186,6 +186,7 @@ SYMBOLS = [
     ("drpo_critic_step", C.c_int, [C.POINTER(CriticArgs)]),
     ("drpo_debug_critic_rows", C.c_int, [C.c_void_p]),
     ("drpo_debug_critic_prof", C.c_int, [C.c_void_p]),
+    ("drpo_debug_solver_rows", C.c_int, [C.c_void_p]),
     ("drpo_debug_critic_dw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("drpo_multiplier_workspace_bytes", C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("drpo_multiplier_step", C.c_int, [C.POINTER(MultiplierArgs)]),

@@ -1,4 +1,5 @@
-// Interface between the C-ABI translation unit and the fused tcgen05 critic step (critic_umma.cu).
+// Interface between the C-ABI translation unit and the fused tcgen05 SSAC update steps (critic_umma.cu: critic step;
+// solver_umma.cu: multiplier and actor steps).
 #pragma once
 #include "../../include/drpo_b200.h"
 namespace drpo {
@@ -12,5 +13,13 @@ void critic_set_prof(long long* p);     // profiling aid: per-op clock stamps [2
 // tests: dW[256, 8*b_octets] of one (dH, H) operand pair in the octet layout
 int critic_debug_dw(const void* a_oct, const void* b_oct, int b_octets, int64_t rows_padded, int ksplit, float* partial, float* out,
                     int* err_flag, void* stream);
+// DRPO_PREC_BF16 multiplier / actor steps (solver_umma.cu).  mode: 0 = multiplier step, 1 = actor step
+int64_t solver_ws_bytes(int mode, int64_t B, int S, int A, int C);
+// phase 1 of drpo_multiplier_step: fills args.grads and args.losses[0]
+int multiplier_phase1(const drpo_multiplier_args& a, int* err_flag);
+// phase 1 of drpo_actor_step: fills args.grads_actor, args.grads_safe and args.losses[0..2], [5]
+int actor_phase1(const drpo_actor_args& a, int* err_flag);
+// tests: per-row intermediates [B,16] written by the next multiplier_phase1 / actor_phase1 (NULL = off)
+void solver_set_debug_rows(float* p);
 }  // namespace cu
 }  // namespace drpo

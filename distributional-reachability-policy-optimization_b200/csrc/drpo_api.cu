@@ -447,8 +447,14 @@ int drpo_critic_step(const drpo_critic_args* a) {
   return rc;
 }
 
+static bool solver_dims_fused(int state_dim, int action_dim, int con_dim, int hidden) {
+  return hidden == 256 && state_dim + action_dim <= 64 && state_dim + 1 <= 64 && (action_dim == 1 || action_dim == 2) &&
+         (con_dim == 1 || con_dim == 2 || con_dim == 4);
+}
 int64_t drpo_multiplier_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
-  return mult_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+  const int64_t a = mult_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+  const int64_t b = solver_dims_fused(state_dim, action_dim, con_dim, hidden) ? cu::solver_ws_bytes(0, batch, state_dim, action_dim, con_dim) + 4096 : 0;
+  return a > b ? a : b;
 }
 
 int drpo_multiplier_step(const drpo_multiplier_args* a) {
@@ -464,14 +470,30 @@ int drpo_multiplier_step(const drpo_multiplier_args* a) {
   DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_multiplier_step: bad phases");
   DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
                  "drpo_multiplier_step: unknown precision %d", a->precision);
-  g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;          // both tensor modes: TF32 tensor-op GEMMs
+  if (a->precision == DRPO_PREC_BF16) {
+    // fused tcgen05 path (solver_umma.cu): phase 1 = pack + fused forward/loss/dX kernel + dW kernel + gradient assembly; phase 2 shared
+    drpo_multiplier_args b = *a;
+    if (a->phases & 1) {
+      DRPO_CHECK_ARG(a->workspace_bytes >= 4096, "drpo_multiplier_step: workspace too small");
+      int* err_flag = (int*)a->workspace;
+      b.workspace = (char*)a->workspace + 4096; b.workspace_bytes = a->workspace_bytes - 4096;
+      DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)a->stream));
+      if ((rc = cu::multiplier_phase1(b, err_flag))) return rc;
+      if ((rc = publish_status(err_flag, 1, a->losses + DRPO_LOSS_ERR_SLOT, a->stream))) return rc;
+    }
+    if (a->phases & 2) { b = *a; b.phases = 2; return multiplier_step_fp32(b); }
+    return DRPO_OK;
+  }
+  g_gemm_mode = a->precision == DRPO_PREC_TF32 ? 1 : 0;          // library tensor-core mode: TF32 tensor-op GEMMs (cuBLAS)
   rc = multiplier_step_fp32(*a);
   g_gemm_mode = 0;
   return rc;
 }
 
 int64_t drpo_actor_workspace_bytes(int64_t batch, int32_t state_dim, int32_t action_dim, int32_t con_dim, int32_t hidden) {
-  return actor_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+  const int64_t a = actor_ws_bytes(batch, state_dim, action_dim, con_dim, hidden);
+  const int64_t b = solver_dims_fused(state_dim, action_dim, con_dim, hidden) ? cu::solver_ws_bytes(1, batch, state_dim, action_dim, con_dim) + 4096 : 0;
+  return a > b ? a : b;
 }
 
 int drpo_actor_step(const drpo_actor_args* a) {
@@ -495,7 +517,21 @@ int drpo_actor_step(const drpo_actor_args* a) {
   DRPO_CHECK_ARG((a->phases & ~3) == 0 && a->phases != 0, "drpo_actor_step: bad phases");
   DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
                  "drpo_actor_step: unknown precision %d", a->precision);
-  g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;
+  if (a->precision == DRPO_PREC_BF16) {
+    // fused tcgen05 path (solver_umma.cu); phase 2 (clips, three Adam steps) is shared with the fp32 path
+    drpo_actor_args b = *a;
+    if (a->phases & 1) {
+      DRPO_CHECK_ARG(a->workspace_bytes >= 4096, "drpo_actor_step: workspace too small");
+      int* err_flag = (int*)a->workspace;
+      b.workspace = (char*)a->workspace + 4096; b.workspace_bytes = a->workspace_bytes - 4096;
+      DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)a->stream));
+      if ((rc = cu::actor_phase1(b, err_flag))) return rc;
+      if ((rc = publish_status(err_flag, 1, a->losses + DRPO_LOSS_ERR_SLOT, a->stream))) return rc;
+    }
+    if (a->phases & 2) { b = *a; b.phases = 2; return actor_step_fp32(b); }
+    return DRPO_OK;
+  }
+  g_gemm_mode = a->precision == DRPO_PREC_TF32 ? 1 : 0;
   rc = actor_step_fp32(*a);
   g_gemm_mode = 0;
   return rc;
@@ -529,6 +565,7 @@ int drpo_ensemble_train_step(const drpo_ensemble_train_args* a) {
 }
 
 int drpo_debug_critic_rows(float* rows) { cu::critic_set_debug_rows(rows); return DRPO_OK; }
+int drpo_debug_solver_rows(float* rows) { cu::solver_set_debug_rows(rows); return DRPO_OK; }
 int drpo_debug_critic_prof(int64_t* stamps) { cu::critic_set_prof((long long*)stamps); return DRPO_OK; }
 
 int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets, int64_t rows_padded, int32_t ksplit, float* partial,

@@ -294,6 +294,11 @@ int drpo_debug_critic_rows(float* rows);
 int drpo_debug_critic_prof(int64_t* stamps);
 int drpo_debug_critic_dw(const void* a_oct, const void* b_oct, int32_t b_octets, int64_t rows_padded, int32_t ksplit,
                          float* partial, float* out, void* stream);
+/* Debug aid of the DRPO_PREC_BF16 multiplier / actor steps (tests): per-row intermediates [batch,16] of the next phase-1 calls.
+ * multiplier step: a[0], a[A-1], Qc_ub(obs,a), penalty, a_safe[0], safe_Qc, lambda-net output, lambda, dL/d(output).
+ * actor step: a_eval[0], safe_Qc, lambda, a[0], log-prob, Q_k, Qc_ub(obs,a), dQ-path dL/da[0], total dL/da[0], dL/dmu[0],
+ * dL/d(raw log-std)[0], a_safe'[0], Qc_ub(obs,a_safe'), dL/da_safe'[0], dL/dmu_safe[0], dL/d(raw log-std)_safe[0]. */
+int drpo_debug_solver_rows(float* rows);
 
 /* ------------------------------------------------------------------------------------------------------------
  * SSAC.update_multiplier (src/ssac.py:529-578) in DRPO mode (mlp_multiplier): actor rsample, two Qc passes with
@@ -342,7 +347,7 @@ typedef struct drpo_actor_args {
    * Multi-GPU callers all-reduce the two gradient arenas and losses[0..2], losses[5] between the phases. */
   int32_t phases;
   float* losses;   /* device [DRPO_LOSSES_LEN]: actor loss, alpha loss, safe-actor loss, actor grad norm, -, d alpha_loss/d log_alpha, safe grad norm, -, ..., [15] watchdog flag */
-  int32_t precision;                       /* DRPO_PREC_FP32, or DRPO_PREC_TF32 / DRPO_PREC_BF16 = TF32 tensor-op GEMMs */
+  int32_t precision;                       /* DRPO_PREC_FP32; DRPO_PREC_BF16 = fused tcgen05 kernel (hidden 256, S+A <= 64); DRPO_PREC_TF32 = library TF32 GEMMs */
   void* workspace; int64_t workspace_bytes; void* stream;
 } drpo_actor_args;
 
