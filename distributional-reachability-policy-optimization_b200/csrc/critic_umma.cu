@@ -68,12 +68,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
   // lock step, coupled by the weight ring: each CTA fetches half of every chunk and multicasts it to both
   const uint32_t crank = cluster_ctarank();
   const int n_clusters = (int)gridDim.x / CLUSTER, cid = (int)blockIdx.x / CLUSTER;
-  const int my_tiles = (p.n_tiles / CLUSTER - cid + n_clusters - 1) / n_clusters;
+  const int my_jobs = sched_my_jobs(p.sch, p.n_tiles, cid, n_clusters);
 
   if (warp == PRODUCER) {
-    fused_producer(p, sm, ring, my_tiles, crank, err);
+    fused_producer(p, sm, ring, my_jobs, cid, n_clusters, crank, err);
   } else if (warp == ISSUER) {
-    fused_issuer(p, sm, ring, xs0, xs1, ones, tmem, my_tiles, lane, err, p.prof);
+    fused_issuer(p, sm, ring, xs0, xs1, ones, tmem, my_jobs, cid, n_clusters, lane, err, p.prof);
   } else {
     // ---- epilogue groups ----------------------------------------------------------------------------------------------------
     Epi e;
@@ -87,8 +87,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 #pragma unroll
     for (int c = 0; c < C; ++c) { sc_m[c] = 0.f; sc_l[c] = 0.f; }
 
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = CLUSTER * (cid + t * n_clusters) + (int)crank;
+    for (int t = 0; t < my_jobs; ++t) {
+      const int job = cid + t * n_clusters, chain = sched_chain(p.sch, job), n_chain = p.sch.n[chain];
+      const int tile = CLUSTER * sched_pair(p.sch, job) + (int)crank;
       e.grow = (int64_t)tile * TILE + e.row;
       e.valid = e.grow < p.B;
       const int64_t gr = e.valid ? e.grow : 0;
@@ -128,8 +129,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 #pragma unroll
       for (int c = 0; c < C; ++c) nqc[c] = 0.f;
 #pragma unroll 1
-      for (int o = 0; o < MAX_OPS; ++o) {
-        const EOp d = p.eop[o];
+      for (int oi = 0; oi < n_chain; ++oi) {
+        const EOp d = p.eop[p.sch.order[chain][oi]];
         const uint32_t region = d.out_region == 0 ? 0u : (d.out_region == 1 ? TM_R0 : TM_R1);
         if (!d.backward) epi_forward(e, region, p.sv[d.save], d.hw_off, d.no, hpart, d.wait_all != 0);
         else epi_backward(e, p.sv[d.hsave], d.bias_slot, p.sv[d.save], region, d.wait_all != 0);
@@ -171,6 +172,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
             }
             fence_proxy_async();
           }
+          if (p.dbg && e.g == 0 && e.valid) {
+            float* dd = p.dbg + gr * 16;
+            if (first) { dd[0] = an[0]; dd[1] = an[A - 1]; dd[2] = lp; } else { dd[3] = an[0]; dd[4] = an[A - 1]; }
+          }
           if (first) {
             logp = lp;
 #pragma unroll
@@ -208,10 +213,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
             const float ee = fminf(fmaxf(e.valid ? p.n_qc.get(gr, c) : 0.f, -2.f), 2.f);
             nqc[c] = fmaf(ee, sd, om[c]);
           }
-          if (p.dbg && e.g == 0 && e.valid) {
-            float* dd = p.dbg + gr * 16;
-            dd[0] = a1[0]; dd[1] = a1[A - 1]; dd[2] = logp; dd[3] = a2[0]; dd[4] = a2[A - 1]; dd[7] = nqc[0];
-          }
+          if (p.dbg && e.g == 0 && e.valid) p.dbg[gr * 16 + 7] = nqc[0];
 #pragma unroll
           for (int j = 0; j < MAXO; ++j) hpart[j] = 0.f;
         } else if (d.post == POST_Q0 || d.post == POST_Q1) {
@@ -273,7 +275,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 #pragma unroll
           for (int j = 0; j < MAXO; ++j) hpart[j] = 0.f;
         }
-        if (o != MAX_OPS - 1) epi_op_done(e);          // the arrival for the next tile's first op follows its staging
+        if (oi != n_chain - 1) epi_op_done(e);          // the arrival for the next tile's first op follows its staging
       }
     }
     // ---- per-CTA results ---------------------------------------------------------------------------------------------------
@@ -469,6 +471,27 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
     DRPO_LAUNCH(gather_ctab_kernel, ct.n, 256, 0, st, ct, ctab);
   }
   fp.n_ops = n_ops; fp.wimg = img; fp.ctab = ctab; fp.ctab_floats = ctab_off;
+  {
+    // The update is two chains that never exchange a value: {actor, target Q1, target Q2, Q1, Q2} (ops 0-5, 12-17) and
+    // {safe actor, target Qc, Qc} (ops 6-11, 18-23), 12 ops each.  Dealing (tile pair, chain) jobs to the CTA pairs instead of
+    // whole tile pairs halves the step of a small shard (8 192 rows: 32 tile pairs -> 64 jobs on 74 CTA pairs) and shortens the
+    // tail of a large one (65 536 rows: 4 rounds of 24 ops -> 7 rounds of 12).  Taken whenever it lowers the number of rounds.
+    const int n_pairs = pl.n_tiles / CLUSTER, mc = 148 / CLUSTER;
+    bool split = (2 * n_pairs + mc - 1) / mc < 2 * ((n_pairs + mc - 1) / mc);
+    if (const char* ev = getenv("DRPO_CRITIC_SPLIT")) split = ev[0] == '1';
+    fp.sch.split = split ? 1 : 0;
+    if (!split) {
+      fp.sch.n[0] = (uint8_t)n_ops;
+      for (int i = 0; i < n_ops; ++i) fp.sch.order[0][i] = (uint8_t)i;
+    } else {
+      fp.sch.n[0] = fp.sch.n[1] = 12;
+      for (int i = 0; i < 6; ++i) {
+        fp.sch.order[0][i] = (uint8_t)i; fp.sch.order[0][6 + i] = (uint8_t)(12 + i);
+        fp.sch.order[1][i] = (uint8_t)(6 + i); fp.sch.order[1][6 + i] = (uint8_t)(18 + i);
+      }
+      pl.grid = std::min(2 * n_pairs, mc) * CLUSTER;
+    }
+  }
   const drpo_batch& b = a.batch;
   fp.obs = b.obs; fp.act = b.act; fp.next_obs = b.next_obs; fp.rew = b.rew; fp.cv = b.cv; fp.done = b.done;
   fp.n_actor = make_noise(a.eps_actor, A, a.seed, TAG_CRITIC_ACTOR, a.noise_step, a.row_id_offset);

@@ -35,6 +35,7 @@ struct SolverParams {
   FOp op[S_MAX_OPS];
   EOp eop[S_MAX_OPS];
   int n_ops;
+  JobSched sch;
   const uint8_t* wimg;
   const float* ctab; int ctab_floats;
   int hw_lam2;                             // multiplier: head weights of the lambda net (backward)
@@ -137,12 +138,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
   const uint32_t tmem = sm->tmem_base;
   const uint32_t crank = cluster_ctarank();
   const int n_clusters = (int)gridDim.x / CLUSTER, cid = (int)blockIdx.x / CLUSTER;
-  const int my_tiles = (p.n_tiles / CLUSTER - cid + n_clusters - 1) / n_clusters;
+  const int my_jobs = sched_my_jobs(p.sch, p.n_tiles, cid, n_clusters);
 
   if (warp == PRODUCER) {
-    fused_producer(p, sm, ring, my_tiles, crank, err);
+    fused_producer(p, sm, ring, my_jobs, cid, n_clusters, crank, err);
   } else if (warp == ISSUER) {
-    fused_issuer(p, sm, ring, xs0, xs1, ones, tmem, my_tiles, lane, err, (long long*)nullptr);
+    fused_issuer(p, sm, ring, xs0, xs1, ones, tmem, my_jobs, cid, n_clusters, lane, err, (long long*)nullptr);
   } else {
     Epi e;
     e.sm = sm; e.ctab = ctab; e.gacc = gacc; e.hp = hp; e.g = warp >> 2; e.lane = lane; e.row = (warp & 3) * 32 + lane;
@@ -154,8 +155,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 #pragma unroll
     for (int j = 0; j < 2 * A; ++j) { sc0[j] = 0.f; sc1[j] = 0.f; }
 
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = CLUSTER * (cid + t * n_clusters) + (int)crank;
+    for (int t = 0; t < my_jobs; ++t) {
+      const int tile = CLUSTER * (cid + t * n_clusters) + (int)crank;      // (no independent chains in these updates: sch.split = 0)
       e.grow = (int64_t)tile * TILE + e.row;
       e.valid = e.grow < p.B;
       const int64_t gr = e.valid ? e.grow : 0;
@@ -598,7 +599,9 @@ static int solver_run(int mode, Builder& b, SolverParams& fp, SPlan& pl, const S
     DRPO_LAUNCH(pack_images_kernel, grid, 256, 0, st, b.pt, reinterpret_cast<__nv_bfloat16*>(w.img));
     DRPO_LAUNCH(gather_ctab_kernel, b.ct.n, 256, 0, st, b.ct, w.ctab);
   }
-  fp.n_ops = b.n_ops; fp.wimg = w.img; fp.ctab = w.ctab; fp.ctab_floats = b.ctab_off;
+  fp.n_ops = b.n_ops; fp.sch.split = 0; fp.sch.n[0] = (uint8_t)b.n_ops;
+  for (int i = 0; i < b.n_ops; ++i) fp.sch.order[0][i] = (uint8_t)i;
+  fp.wimg = w.img; fp.ctab = w.ctab; fp.ctab_floats = b.ctab_off;
   fp.sv[0] = nullptr;
   for (int i = 0; i < pl.n_sv; ++i) fp.sv[1 + i] = w.sv[i];
   fp.gacc_out = w.gacc_out; fp.nv = pl.nv; fp.loss_part = w.loss_part; fp.err_flag = err_flag; fp.dbg = g_solver_dbg;

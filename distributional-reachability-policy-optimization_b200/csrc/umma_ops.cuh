@@ -49,10 +49,23 @@ struct EOp {
 };
 constexpr uint8_t NO_SLOT = 255;           // EOp::bias_slot of a backward op through a frozen net: no column sums
 
+// Order in which a CTA pair walks the op tables.  split = 0: every tile pair runs order[0] (all ops).  split = 1: the update has two
+// chains of ops that do not depend on each other (critic step: actor -> target Q's -> Q losses | safe actor -> target Qc -> Qc
+// loss); job j of the grid is chain (j & 1) of tile pair (j >> 1), so small batches spread over twice as many SMs and a large
+// batch is dealt in half-size pieces (shorter tail).
+struct JobSched { uint8_t order[2][32]; uint8_t n[2]; uint8_t split; uint8_t pad; };
+__device__ __forceinline__ int sched_chain(const JobSched& s, int job) { return s.split ? (job & 1) : 0; }
+__device__ __forceinline__ int sched_pair(const JobSched& s, int job) { return s.split ? (job >> 1) : job; }
+__device__ __forceinline__ int sched_my_jobs(const JobSched& s, int n_tiles, int cid, int n_clusters) {
+  const int jobs = (n_tiles / 2) * (s.split ? 2 : 1);
+  return (jobs - cid + n_clusters - 1) / n_clusters;
+}
+
 struct FusedParams {
   FOp op[MAX_OPS];
   EOp eop[MAX_OPS];
   int n_ops;
+  JobSched sch;
   const uint8_t* wimg;
   const float* ctab; int ctab_floats;
   int hw_q[2], hw_cm, hw_cl;               // head weights needed again by the backward steps (offsets into ctab)
@@ -404,14 +417,16 @@ __device__ __forceinline__ void head_combine(Epi& e, const float (&hpart)[MAXO],
 // the two single-warp roles every fused SSAC kernel shares (P = its parameter block: op[], n_ops, wimg, stages)
 // ---------------------------------------------------------------------------------------------------------------
 template <class P>
-__device__ __forceinline__ void fused_producer(const P& p, FusedSmem* sm, uint8_t* ring, int my_tiles, uint32_t crank, int* err) {
+__device__ __forceinline__ void fused_producer(const P& p, FusedSmem* sm, uint8_t* ring, int my_jobs, int cid, int n_clusters, uint32_t crank,
+                                               int* err) {
   const int stages = p.stages;
   // ---- TMA producer: (tile, op, chunk, part) weight blocks through the ring ---------------------------------------------
   if (elect_one()) {
     uint32_t s = 0, ph = 0;
-    for (int t = 0; t < my_tiles; ++t)
-      for (int o = 0; o < p.n_ops; ++o) {
-        const FOp op = p.op[o];
+    for (int t = 0; t < my_jobs; ++t) {
+      const int chain = sched_chain(p.sch, cid + t * n_clusters);
+      for (int oi = 0; oi < p.sch.n[chain]; ++oi) {
+        const FOp op = p.op[p.sch.order[chain][oi]];
         const uint32_t bytes = 64u * (op.kp + (op.bias ? KBIAS : 0)) * 2u;
         for (int c = 0; c < NGROUPS; ++c)
           for (int part = 0; part < op.parts; ++part) {
@@ -423,12 +438,13 @@ __device__ __forceinline__ void fused_producer(const P& p, FusedSmem* sm, uint8_
             if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
           }
       }
+    }
   }
 }
 
 template <class P>
 __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t* ring, uint8_t* xs0, uint8_t* xs1, uint8_t* ones, uint32_t tmem,
-                                             int my_tiles, int lane, int* err, long long* prof) {
+                                             int my_jobs, int cid, int n_clusters, int lane, int* err, long long* prof) {
   const int stages = p.stages;
   // ---- MMA issuer ---------------------------------------------------------------------------------------------------------
   // The tensor pipe accepts only ~4 MMAs ahead of execution, so every barrier wait between two chunks is a bubble in the
@@ -439,8 +455,10 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
   const uint32_t ones_lo = (uint32_t)ones_d, ones_hi = (uint32_t)(ones_d >> 32);
   const int round = stages >= 4 ? 4 : 2;
   const uint32_t idesc = make_idesc(64);
-  for (int t = 0; t < my_tiles; ++t)
-    for (int o = 0; o < p.n_ops; ++o, ++it) {
+  for (int t = 0; t < my_jobs; ++t) {
+    const int chain = sched_chain(p.sch, cid + t * n_clusters);
+    for (int oi = 0; oi < p.sch.n[chain]; ++oi, ++it) {
+      const int o = p.sch.order[chain][oi];
       const FOp op = p.op[o];
       const int nk = op.kp >> 4;
       const int pshift = op.parts - 1;                              // parts is 1 or 2
@@ -460,7 +478,7 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
           if (stamp) prof[o * 32 + 9] = clock64();
           // the previous op's activations / post step; an `early` op does not read them: its MMAs go first and the phase is
           // observed right after (every phase is observed, in order, before the next one of the same barrier can complete)
-          if (!op.early) mbar_wait(&sm->act_ready[it & 1], (it >> 1) & 1, err, 2);
+          if (!op.early || oi == 0) mbar_wait(&sm->act_ready[it & 1], (it >> 1) & 1, err, 2);      // (a job's first op always waits for the staging)
           if (stamp) prof[o * 32] = clock64();
         }
         tc_fence_after();
@@ -497,9 +515,10 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
         __syncwarp();
         stage = sw; phase = pw;
       }
-      if (op.early) mbar_wait(&sm->act_ready[it & 1], (it >> 1) & 1, err, 6);
+      if (op.early && oi != 0) mbar_wait(&sm->act_ready[it & 1], (it >> 1) & 1, err, 6);
       if (stamp) prof[o * 32 + 1] = clock64();
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -107,6 +107,10 @@ def test_actor_bf16_step_vs_oracle(S, A, C, B):
         # the action gradient went through two frozen critics in bf16 and is summed over the batch with cancellation: the bulk
         # within 2e-2 of the tensor's scale (the per-row rounding errors average out with the batch size: <= 15 % outliers at
         # 130 rows, <= 10 % at 1000, <= 5 % at 4096, <= 1 % at the 64k batch of the full-size test below), every entry within 2e-1
+        if want.numel() <= 8 and B < 512:
+            # the 2A-entry head bias: a fraction of outliers means nothing for 4 numbers; 130 rows average little: 5e-2 each
+            assert_close(views[k], want, 5e-2, f"grad {k}")
+            continue
         assert_close(views[k], want, 2e-2, f"grad {k}", max_outlier_frac=1.5e-1 if B < 512 else (1e-1 if B < 2048 else 5e-2))
         assert_close(views[k], want, 2e-1, f"grad {k} (outlier bound)")
     sd = solver.state_dict()
