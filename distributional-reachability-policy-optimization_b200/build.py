@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdrpo_sm100.so")
-SOURCES = ["drpo_api.cu", "umma_rollout.cu", "critic_umma.cu", "solver_umma.cu"]
+SOURCES = ["drpo_api.cu", "umma_rollout.cu", "critic_umma.cu", "solver_umma.cu", "ens_umma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

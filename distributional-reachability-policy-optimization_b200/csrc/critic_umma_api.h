@@ -21,5 +21,12 @@ int multiplier_phase1(const drpo_multiplier_args& a, int* err_flag);
 int actor_phase1(const drpo_actor_args& a, int* err_flag);
 // tests: per-row intermediates [B,16] written by the next multiplier_phase1 / actor_phase1 (NULL = off)
 void solver_set_debug_rows(float* p);
+// DRPO_PREC_BF16 ensemble forward / sample outside the rollout (ens_umma.cu): members m0..m1-1 on `batch` rows; noise == NULL:
+// means / log_vars [m1-m0, batch, S+1]; noise != NULL (one member): next_states [batch,S], rewards [batch]
+bool ens_bf16_supported(const drpo_ensemble& e);
+int64_t ens_bf16_ws_bytes(const drpo_ensemble& e);
+int ens_bf16_run(const drpo_ensemble& e, int m0, int m1, int per_member_inputs, const float* states, const float* actions, int64_t batch,
+                 float* means, float* log_vars, const drpo_noise* noise, float* next_states, float* rewards, void* workspace,
+                 int64_t workspace_bytes, void* stream, int* err_flag);
 }  // namespace cu
 }  // namespace drpo

@@ -133,7 +133,19 @@ static int check_ens(const drpo_ensemble* e) {
 
 int64_t drpo_ensemble_workspace_bytes(const drpo_ensemble* ens, int64_t batch) {
   if (!ens || batch < 0) return -1;
-  return ens_scratch_floats(*ens, batch) * 4 + 16 * 256;
+  return ens_scratch_floats(*ens, batch) * 4 + 16 * 256 + (cu::ens_bf16_supported(*ens) ? cu::ens_bf16_ws_bytes(*ens) : 0);
+}
+// DRPO_PREC_BF16 of the standalone ensemble entry points: the fused tcgen05 member chain of ens_umma.cu
+static int ens_bf16_call(const drpo_ensemble* ens, int m0, int m1, int per_member, const float* states, const float* actions, int64_t batch,
+                         float* means, float* log_vars, const drpo_noise* noise, float* next_states, float* rewards, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  DRPO_CHECK_ARG(workspace && workspace_bytes >= 4096, "ensemble forward (bf16): workspace too small");
+  int* err_flag = (int*)workspace;
+  DRPO_CUDA_OK(cudaMemsetAsync(err_flag, 0, 16, (cudaStream_t)stream));
+  int rc = cu::ens_bf16_run(*ens, m0, m1, per_member, states, actions, batch, means, log_vars, noise, next_states, rewards,
+                            (char*)workspace + 4096, workspace_bytes - 4096, stream, err_flag);
+  if (rc) return rc;
+  return publish_status(err_flag, 1, nullptr, stream);
 }
 
 int drpo_ensemble_forward(const drpo_ensemble* ens, int32_t member, int32_t per_member_inputs, const float* states,
@@ -142,8 +154,11 @@ int drpo_ensemble_forward(const drpo_ensemble* ens, int32_t member, int32_t per_
   int rc = check_ens(ens); if (rc) return rc;
   DRPO_CHECK_ARG(member >= -1 && member < ens->ensemble_size, "member %d out of range", member);
   DRPO_CHECK_ARG(batch >= 0 && (batch == 0 || (states && actions && means && log_vars)), "drpo_ensemble_forward: bad arguments");
-  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_ensemble_forward: only DRPO_PREC_FP32 here (the bf16 path is fused into drpo_rollout)");
+  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32 || precision == DRPO_PREC_BF16, "drpo_ensemble_forward: DRPO_PREC_FP32 or DRPO_PREC_BF16");
   if (batch == 0) return DRPO_OK;
+  if (precision == DRPO_PREC_BF16)
+    return ens_bf16_call(ens, member < 0 ? 0 : member, member < 0 ? ens->ensemble_size : member + 1, per_member_inputs && member < 0, states, actions,
+                         batch, means, log_vars, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
   Arena ar(workspace, workspace_bytes);
   EnsScratch w = ens_scratch(ar, *ens, batch);
   if (!ar.ok()) { set_error("drpo_ensemble_forward: workspace too small"); return DRPO_ERR_WORKSPACE; }
@@ -166,8 +181,11 @@ int drpo_ensemble_sample(const drpo_ensemble* ens, int32_t member, const float* 
   int rc = check_ens(ens); if (rc) return rc;
   DRPO_CHECK_ARG(member >= 0 && member < ens->ensemble_size, "member %d out of range", member);
   DRPO_CHECK_ARG(batch >= 0 && (batch == 0 || (states && actions && noise && next_states && rewards)), "drpo_ensemble_sample: bad arguments");
-  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32, "drpo_ensemble_sample: only DRPO_PREC_FP32 here");
+  DRPO_CHECK_ARG(precision == DRPO_PREC_FP32 || precision == DRPO_PREC_BF16, "drpo_ensemble_sample: DRPO_PREC_FP32 or DRPO_PREC_BF16");
   if (batch == 0) return DRPO_OK;
+  if (precision == DRPO_PREC_BF16)
+    return ens_bf16_call(ens, member, member + 1, 0, states, actions, batch, nullptr, nullptr, noise, next_states, rewards, workspace,
+                         workspace_bytes, stream);
   Arena ar(workspace, workspace_bytes);
   EnsScratch w = ens_scratch(ar, *ens, batch);
   if (!ar.ok()) { set_error("drpo_ensemble_sample: workspace too small"); return DRPO_ERR_WORKSPACE; }

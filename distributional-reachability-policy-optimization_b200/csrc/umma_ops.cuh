@@ -33,7 +33,9 @@ enum ASrc { A_XS0 = 0, A_XS1 = 1, A_R0 = 2, A_R1 = 3 };
 
 // bias: the chunks carry a bias K block.  early: the op reads only shared-memory inputs that were complete before the previous op
 // (its A operand is [s,a] staged at the tile start), so its MMAs need not wait for the previous op's epilogues and post step
-struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t bias; uint8_t early; uint8_t pad[3]; };
+// nchunks: 64-column output chunks the op computes (0 = all four); a narrow output layer (ensemble heads) sets 1 and the issuer
+// completes the other accumulators' barriers without MMAs
+struct FOp { uint32_t w_off[2]; uint16_t kp; uint8_t a_src[2]; uint8_t parts; uint8_t bias; uint8_t early; uint8_t nchunks; uint8_t pad[2]; };
 // epilogue side of an op
 enum Post { POST_NONE = 0, POST_POLICY0, POST_POLICY1, POST_QT0, POST_QT1, POST_KEEP, POST_QCT, POST_Q0, POST_Q1, POST_QC };
 struct EOp {
@@ -109,7 +111,7 @@ struct FusedSmem {
 //   [n/8][k/8][8 rows][8 elems];  transposed images hold W^T (the backward op's B operand)
 // ---------------------------------------------------------------------------------------------------------------
 struct PackEntry { const float* W; const float* bias; int n_real, k_real, kp, transposed; int64_t dst; };
-struct PackTable { PackEntry e[28]; int n; };
+struct PackTable { PackEntry e[48]; int n; };
 // Forward images (bias != NULL) carry a 16-wide extra K block per chunk: k = kp holds bf16(b), k = kp+1 holds bf16(b - bf16(b));
 // the issuer multiplies it with a constant tile of ones, so the accumulator already contains the fp32-accurate bias.
 static __global__ void pack_images_kernel(PackTable t, __nv_bfloat16* __restrict__ img) {
@@ -237,11 +239,15 @@ __device__ __forceinline__ void epi_forward(Epi& e, uint32_t out_region, __nv_bf
   tmem_ld_wait();
   epi_free_acc(e);
   if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 17 + 4 * e.g] = clock64();
-  if (act) {                               // tanh layer: apply it in place (tanh.approx, error far below the bf16 rounding that follows)
+  if (act) {                               // tanh (1) / SiLU (2) layer: applied in place (tanh.approx, error far below the bf16 rounding that follows)
 #pragma unroll
     for (int half = 0; half < 2; ++half)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) raw[half][j] = __float_as_uint(tanh_fast(__uint_as_float(raw[half][j])));
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(raw[half][j]);
+        const float hx = 0.5f * x;
+        raw[half][j] = __float_as_uint(act == 1 ? tanh_fast(x) : fmaf(hx, tanh_fast(hx), hx));      // x*sigmoid(x) = h + h*tanh(h), h = x/2
+      }
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -428,7 +434,8 @@ __device__ __forceinline__ void fused_producer(const P& p, FusedSmem* sm, uint8_
       for (int oi = 0; oi < p.sch.n[chain]; ++oi) {
         const FOp op = p.op[p.sch.order[chain][oi]];
         const uint32_t bytes = 64u * (op.kp + (op.bias ? KBIAS : 0)) * 2u;
-        for (int c = 0; c < NGROUPS; ++c)
+        const int nch = op.nchunks ? op.nchunks : NGROUPS;
+        for (int c = 0; c < nch; ++c)
           for (int part = 0; part < op.parts; ++part) {
             mbar_wait(&sm->empty[s], ph ^ 1, err, 1);   // both CTAs' MMAs on the stage's previous contents are done (multicast commits)
             mbar_expect_tx(&sm->full[s], bytes);
@@ -464,11 +471,13 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
       const int pshift = op.parts - 1;                              // parts is 1 or 2
       const bool stamp = prof && blockIdx.x == 0 && lane == 0 && t == 1;
       const uint32_t sbo = (uint32_t)(op.kp + (op.bias ? KBIAS : 0)) * 16;
-      for (int i0 = 0; i0 < (NGROUPS << pshift); i0 += round) {
+      const int total = (op.nchunks ? op.nchunks : NGROUPS) << pshift;
+      for (int i0 = 0; i0 < total; i0 += round) {
+        const int nr = min(round, total - i0);
         // (the first round's weights and the accumulators become available while the previous op is still in its epilogue:
         // these waits are off the critical path; the last one - the previous op's activations - is the real dependency)
         uint32_t sw = stage, pw = phase;
-        for (int r = 0; r < round; ++r) {
+        for (int r = 0; r < nr; ++r) {
           mbar_wait(&sm->full[sw], pw, err, 4);
           if (++sw == (uint32_t)stages) { sw = 0; pw ^= 1; }
         }
@@ -486,7 +495,7 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
         if (elect_one()) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            if (r < round) {
+            if (r < nr) {
               const int i = i0 + r, c = i >> pshift, part = i & pshift;
               uint32_t s = stage + r; if (s >= (uint32_t)stages) s -= stages;
               // B: chunk image [64 cols][kp] K-major: LBO = 128 B (next K octet), SBO = kp*16 B (next 8 columns)
@@ -511,6 +520,9 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
               if (part == pshift) tc_commit(&sm->acc_full[c]);
             }
           }
+          // a narrow op: the accumulators it does not use complete their phase too (their epilogue groups only pass the barriers)
+          if (op.nchunks && i0 + nr >= total)
+            for (int c = op.nchunks; c < NGROUPS; ++c) tc_commit(&sm->acc_full[c]);
         }
         __syncwarp();
         stage = sw; phase = pw;

@@ -96,6 +96,9 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         self.optimizer = FusedAdam(self._arena, self.learning_rate, weight_decay=1e-4)
         self._fit_losses = torch.zeros(1 + E, device=device)
         self.precision = _lib.PREC_FP32
+        # precision of the standalone forward entry points (_forward1 / _forward_all / means / sample / elite_samples):
+        # PREC_FP32, or PREC_BF16 = the fused tcgen05 member chain (csrc/ens_umma.cu; hidden <= 256, state_dim + action_dim <= 64)
+        self.forward_precision = _lib.PREC_FP32
         self.elite_inds = torch.randint(high=E, size=(self.num_elites,)).tolist()      # src/dynamics.py:105-106
         self._ws = _lib.Workspace()
         self.noise_seed = 0x5EEDD12A
@@ -172,7 +175,7 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         ens = self.as_struct()
         ws = self._workspace(lib, ens, B, states.device)
         _lib.check(lib.drpo_ensemble_forward(ens, member, int(per_member), _lib.ptr(states), _lib.ptr(actions), B,
-                                             _lib.ptr(means), _lib.ptr(log_vars), _lib.PREC_FP32, _lib.ptr(ws), ws.numel(),
+                                             _lib.ptr(means), _lib.ptr(log_vars), self.forward_precision, _lib.ptr(ws), ws.numel(),
                                              _lib.stream_ptr()), "drpo_ensemble_forward")
         return means, log_vars
 
@@ -200,7 +203,7 @@ class BatchedGaussianEnsemble(Configurable, nn.Module):
         ens = self.as_struct()
         ws = self._workspace(lib, ens, B, states.device)
         _lib.check(lib.drpo_ensemble_sample(ens, index, _lib.ptr(states), _lib.ptr(actions), B, noise, _lib.ptr(next_states),
-                                            _lib.ptr(rewards), _lib.PREC_FP32, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                                            _lib.ptr(rewards), self.forward_precision, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "drpo_ensemble_sample")
         return next_states, rewards
 

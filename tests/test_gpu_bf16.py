@@ -349,3 +349,56 @@ def test_bf16_injected_rollout_teacher_forced_every_step(tag, S, A, C, B):
         for k, want in (("actions", act), ("next_states", nxt), ("rewards", rew)):
             assert_close(st[k], want, 2e-2, f"{tag} step {t} {k} (teacher-forced)")
         ids = ids[~st["dones"]]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# standalone ensemble entry points at DRPO_PREC_BF16 (csrc/ens_umma.cu): the fused tcgen05 member chain outside the rollout
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,S,A", [("point_robot", 11, 2), ("cartpole", 4, 1), ("quadrotor", 12, 2)])
+def test_ensemble_entry_points_bf16_vs_golden(golden, tag, S, A):
+    """_forward1 / sample / means / elite_samples / _forward_all against the reference's own outputs (golden ensemble.npz) within
+    the 2e-2 of the bf16 GEMM path (relative to each tensor's scale)."""
+    import drpo_b200
+    from drpo_b200 import _lib
+    from tests.util import make_ensemble
+    g = golden("ensemble")
+    w = O.make_ensemble_weights(int(g[f"{tag}.seed"]), S, A)
+    ens = make_ensemble(w, S, A)
+    ens.forward_precision = drpo_b200.PREC_BF16
+    s, a, eps = to_dev(g[f"{tag}.states"]), to_dev(g[f"{tag}.actions"]), to_dev(g[f"{tag}.eps"])
+    m, lv = ens._forward1(s, a, int(g[f"{tag}.member"]))
+    assert_close(m, g[f"{tag}.means"], 2e-2, "means"); assert_close(lv, g[f"{tag}.log_vars"], 2e-2, "log_vars")
+    ens._elite_inds = [int(g[f"{tag}.member"])]
+    ns, r = ens.sample(s, a, eps=eps)
+    assert_close(ns, g[f"{tag}.next_states"], 2e-2, "next_states"); assert_close(r, g[f"{tag}.rewards"], 2e-2, "rewards")
+    ms, mr = ens.means(s, a)
+    assert_close(ms, g[f"{tag}.means_all_s"], 2e-2, "means()"); assert_close(mr, g[f"{tag}.means_all_r"], 2e-2, "means() r")
+    ens._elite_inds = [6, 0, 2, 5, 1]
+    es, er = ens.elite_samples(s, a, eps=to_dev(g[f"{tag}.eps_elite"]))
+    assert_close(es, g[f"{tag}.elite_s"], 2e-2, "elite_samples"); assert_close(er, g[f"{tag}.elite_r"], 2e-2, "elite r")
+    sE = s.repeat(7, 1, 1) + torch.arange(7, device=s.device).view(7, 1, 1) * 0.01
+    aE = a.repeat(7, 1, 1)
+    mE, lvE = ens._forward_all(sE, aE)
+    om, olv = O.ensemble_forward_all(w, sE.cpu(), aE.cpu())
+    assert_close(mE, om, 2e-2, "_forward_all means"); assert_close(lvE, olv, 2e-2, "_forward_all log_vars")
+    torch.cuda.synchronize()
+    _lib.check_kernel_status("ensemble bf16")
+
+
+def test_ensemble_bf16_ragged_and_wide():
+    """Batch sizes that are not tile multiples (incl. 1 and 0), the 60-dim safetygym state, and a batch of several waves."""
+    import drpo_b200
+    from drpo_b200 import _lib
+    from tests.util import make_ensemble
+    g = torch.Generator().manual_seed(1)
+    for S, A, sizes in ((12, 2, (0, 1, 63, 257, 1000)), (60, 2, (130, 40000))):
+        w = O.make_ensemble_weights(7, S, A)
+        ens = make_ensemble(w, S, A)
+        ens.forward_precision = drpo_b200.PREC_BF16
+        for B in sizes:
+            s, a = torch.randn(B, S, generator=g), torch.rand(B, A, generator=g) * 2 - 1
+            m, lv = ens._forward1(to_dev(s), to_dev(a), 2)
+            om, olv = O.ensemble_forward1(w, s, a, 2)
+            assert_close(m, om, 2e-2, f"means S={S} B={B}"); assert_close(lv, olv, 2e-2, f"lv S={S} B={B}")
+        torch.cuda.synchronize()
+        _lib.check_kernel_status("ensemble bf16 ragged")
