@@ -129,6 +129,16 @@ class ClockSampler:
             # measured to cost ~1 ms per rollout step): one sample early in the region, then one every 100 ms (~1 % of the region)
             self._stop.wait(float(os.environ.get("DRPO_BENCH_CLOCK_INTERVAL", "0.1")))
 
+    def sample_now(self):
+        """One synchronous sample from the launching thread: called after the timed region's launches are queued and before the
+        closing synchronisation, i.e. while the GPU is still executing them - guarantees a sample for regions shorter than the
+        sampler thread's first wait (the strong-scaled shards at N = 8 run ~10 ms)."""
+        try:
+            if self.nvml is not None:
+                self.rows.append(self._sample_nvml())
+        except Exception:
+            pass
+
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
@@ -228,6 +238,7 @@ def measure_rollout(args, lib, workload, B_global, scaling, device, rank, world,
             view = step_device()
             total += view.step_counts[-1]
         ev1.record()
+        clocks.sample_now()
         barrier()
     launches = lib.drpo_launch_count() - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
