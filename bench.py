@@ -27,13 +27,15 @@ import torch  # noqa: E402
 HORIZON = 10
 DEFAULT_B0 = {"quadrotor": 1_000_000, "cartpole-move": 100_000, "safetygym-point-synthetic": 400_000, "point-robot": 100_000}
 CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
-# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_umma_kernel launch at the bench workload (1 M rows), from the
-# `ncu --set full` capture of the final round-1 kernel (profiles/r1_ncu_full_rollout_step_1M_final_raw.csv: 52.9 MB read + 17.2 MB
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_pipe_kernel launch at the bench workload (1 M rows), from the
+# `ncu --set full` capture of the shipped round-2 kernel (profiles/r2_ncu_full_rollout_step_1M_raw.csv: 52.6 MB read + 19.7 MB
 # written - 48 MB of states in; most of the 60 MB of outputs is still in L2 when the kernel ends); null when no capture exists
-TRAFFIC_BYTES_PER_LAUNCH = {("quadrotor", 1_000_000): 70104064}
+TRAFFIC_BYTES_PER_LAUNCH = {("quadrotor", 1_000_000): 52561152 + 19717632}
 # the same for one critic_fused_kernel launch at B = 65 536, tracking dims (profiles/r1_ncu_full_critic_fused_64k_raw.csv:
 # 44.2 MB read + 378.2 MB written: the saved bf16 activations the dW kernel consumes)
 CRITIC_TRAFFIC_BYTES_PER_LAUNCH = {("tracking", 65536): 422400000}
+# dram__bytes_read.sum + dram__bytes_write.sum of one solver_fused_kernel launch (ncu --set full, profiles/r2_ncu_full_solver_actor_64k_raw.csv)
+SOLVER_TRAFFIC_BYTES_PER_LAUNCH = {("actor", "tracking", 65536): 81275136 + 396089088}
 
 
 def flops_per_transition(S, A):
@@ -556,7 +558,8 @@ def bench_critic(args, device, world, rank, pk):
                      "dtype": {"bf16": "bf16 (fused tcgen05 forward/loss/dX kernel + tcgen05 dW kernel), fp32 accumulate/optimizer",
                                "tf32": "tf32 tensor-op GEMMs (cuBLAS), fp32 elementwise/optimizer", "fp32": "f32"}[cprec],
                      "roofline": {"bound": "tensor", "achieved": round(ach2, 3), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                                  "frac": round(ach2 / pk["tensor_sustained"], 5), "traffic": None,
+                                  "frac": round(ach2 / pk["tensor_sustained"], 5),
+                                  "traffic": SOLVER_TRAFFIC_BYTES_PER_LAUNCH.get((name, CRITIC_WORKLOAD, B)) if cprec == "bf16" else None,
                                   "kernel": "solver_fused_kernel ; achieved = whole update incl. dW, reductions, clip/Adam",
                                   "algorithmic_flops_per_sample": fl2}}
     if world == 1 and not args.skip_cpu:
