@@ -165,3 +165,62 @@ def test_solver_bf16_full_size_matches_fp32_path():
     assert_close(b[0], f[0], 2e-2, "actor losses"); assert_close(b[2], f[2], 2e-2, "multiplier loss")
     assert_close(b[1], f[1], 2e-2, "actor gradient arenas", max_outlier_frac=1e-2)
     assert_close(b[3], f[3], 2e-2, "multiplier gradient arena", max_outlier_frac=1e-2)
+
+
+def _philox(lib, B, cols, seed, tag, step):
+    from drpo_b200 import _lib
+    out = torch.empty(B, cols, device=dev())
+    _lib.check(lib.drpo_philox_normal(out.data_ptr(), B, cols, None, seed, tag, step, None), "drpo_philox_normal")
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("S,A,C,B", [(51, 2, 1, 4096), (12, 2, 2, 1000)])
+def test_ssac_steps_bf16_philox_mode_vs_oracle(S, A, C, B):
+    """The configuration bench.py times: bf16 fused kernels drawing their noise IN the kernel (Philox keyed by seed / stream tag /
+    optimiser step / global row id).  The oracle is fed the same stream exported by drpo_philox_normal (tags: critic actor 3, safe
+    actor 4, Qc 5; multiplier 6; actor step 7 / 8), so a mis-keyed or wrong-variance draw inside a fused kernel shows up as a loss
+    mismatch."""
+    import drpo_b200
+    from drpo_b200 import _lib
+    lib = _lib.load()
+    w = O.make_ssac_weights(81, S, A, C)
+    solver = make_ssac(w, S, A, C, B)
+    solver.precision = drpo_b200.PREC_BF16
+    wo = {k: v.clone() for k, v in w.items()}
+    g = torch.Generator().manual_seed(82)
+    obs = torch.randn(B, S, generator=g); act = torch.rand(B, A, generator=g) * 2 - 1
+    nobs = obs + 0.1 * torch.randn(B, S, generator=g); rew = torch.randn(B, generator=g)
+    done = torch.rand(B, generator=g) < 0.1; viol = torch.rand(B, generator=g) < 0.1
+    cv = (torch.randn(B, generator=g) - 0.5) if C == 1 else (torch.randn(B, C, generator=g) - 0.5)
+    batch = [obs, act, nobs, rew, done, viol, cv]
+    seed, hp = solver.noise_seed, O.SSACHyper()
+    # critic step (first update: optimiser step 1)
+    eq = _philox(lib, B, C, seed, 5, 1)
+    noise = (_philox(lib, B, A, seed, 3, 1), _philox(lib, B, A, seed, 4, 1), eq[:, 0] if C == 1 else eq)
+    lq, lc, _ = O.critic_update(wo, batch, noise, hp, 0.0, O.AdamState(), 3e-4)
+    glq, glc = solver.update_critic(*[to_dev(b) for b in batch])
+    assert_close(glq, lq, 2e-2, "loss_q (philox)"); assert_close(glc, lc, 2e-2, "loss_c (philox)")
+    # actor step on fresh copies of the weights (the critic step above moved both sides by one Adam step of different rounding)
+    w2 = O.make_ssac_weights(83, S, A, C)
+    s2 = make_ssac(w2, S, A, C, B); s2.precision = drpo_b200.PREC_BF16
+    wo2 = {k: v.clone() for k, v in w2.items()}
+    na = (_philox(lib, B, A, s2.noise_seed, 7, 1), _philox(lib, B, A, s2.noise_seed, 8, 1))
+    la = torch.tensor(0.0)
+    al, aux = O.actor_update(wo2, obs, na, hp, la, 1, C, -float(A), {k: O.AdamState() for k in ("actor", "alpha", "safe")},
+                             dict(actor=8e-5, alpha=8e-5, safe=8e-5))
+    got = s2.update_actor_and_alpha(to_dev(obs), q_index=1)
+    assert_close(got, torch.stack(al), 2e-2, "actor losses (philox)")
+    assert_close(s2._actor_losses[3], aux["grad_norm_actor"], 3e-2, "actor grad norm (philox)")
+    # multiplier step (its stream: seed + 1, tag 6, step 1)
+    w3 = O.make_ssac_weights(84, S, A, C)
+    s3 = make_ssac(w3, S, A, C, B); s3.precision = drpo_b200.PREC_BF16
+    wo3 = {k: v.clone() for k, v in w3.items()}
+    lm, auxm = O.multiplier_update(wo3, obs, _philox(lib, B, A, s3.noise_seed + 1, 6, 1), hp, C, O.AdamState(), 3e-4)
+    glm = s3.update_multiplier(to_dev(obs))
+    if bool((auxm["safe_qc"].abs() > 2e-2 * auxm["safe_qc"].abs().max()).all()):
+        assert_close(glm, lm, 2e-2, "multiplier loss (philox)")
+    else:                                                     # a row within rounding of the safe / unsafe switch changes its loss branch
+        assert_close(glm, lm, 1e-1, "multiplier loss (philox, rows at the switch)")
+    torch.cuda.synchronize()
+    _lib.check_kernel_status("philox-mode SSAC steps")
