@@ -221,15 +221,71 @@ __device__ __forceinline__ void write_input_octets(uint32_t tile_row, int o0, in
   }
 }
 
-// the same, four octets (32 elements) per round: `load(k)` (a global-memory read) of the whole round is issued before the first use, so a
-// wide state costs two or three memory round trips instead of one per octet; `fin(k, x)` turns the loaded value into element k
-template <typename L, typename F>
-__device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n_oct, L load, F fin) {
+// four consecutive elements k0 .. k0+3 (k0 a multiple of 4) of one fp32 row of S elements: one 16-byte load when the row is 16-byte
+// aligned (vec: S % 4 == 0) and the group lies inside it - each thread reads its OWN row, so a scalar load is 32 sectors per warp
+// instruction and the instruction count is what the load/store unit pays for; zeros beyond the row or when the row is not valid
+// (kLdg: read-only data of this launch through the non-coherent path; false for rows this very thread stored earlier in the kernel)
+template <bool kLdg>
+__device__ __forceinline__ void load_row4(const float* row, int k0, int S, bool valid, bool vec, float (&f)[4]) {
+  if (!valid || k0 >= S) { f[0] = f[1] = f[2] = f[3] = 0.f; return; }
+  if (vec && k0 + 4 <= S) {
+    const float4 v = kLdg ? __ldg(reinterpret_cast<const float4*>(row + k0)) : *reinterpret_cast<const float4*>(row + k0);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f[e] = k0 + e < S ? (kLdg ? __ldg(row + k0 + e) : row[k0 + e]) : 0.f;
+  }
+}
+__device__ __forceinline__ void store_row4(float* row, int k0, int S, bool vec, const float (&f)[4]) {      // elements k0..k0+3 that lie inside the row
+  if (k0 >= S) return;
+  if (vec && k0 + 4 <= S) *reinterpret_cast<float4*>(row + k0) = make_float4(f[0], f[1], f[2], f[3]);
+  else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (k0 + e < S) row[k0 + e] = f[e];
+  }
+}
+
+// the same, four octets (32 elements) per round: the global-memory reads of the whole round (the thread's own state row `row`, S
+// elements, zeros behind it) are issued before the first use, so a wide state costs two or three memory round trips instead of one
+// per octet; `fin(k, x)` turns the loaded value into element k
+// `keep` (a thread-local array of 64 floats, i.e. lane-interleaved local memory: every later access is one coalesced wavefront)
+// receives the raw row, so that the tile's later passes over its state do not go back to global memory with 32-sector accesses
+template <typename F>
+__device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n_oct, const float* row, int S, bool valid, bool vec, F fin, float* keep) {
 #pragma unroll 1
   for (int o0 = 0; o0 < n_oct; o0 += 4) {
     float f[32];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) f[e] = load(8 * o0 + e);
+    for (int e4 = 0; e4 < 8; ++e4) {
+      float v[4];
+      load_row4<true>(row, 8 * o0 + 4 * e4, S, valid, vec, v);
+      f[4 * e4] = v[0]; f[4 * e4 + 1] = v[1]; f[4 * e4 + 2] = v[2]; f[4 * e4 + 3] = v[3];
+    }
+    if (8 * o0 < 64) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) keep[8 * o0 + e] = f[e];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (o0 + q < n_oct) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(fin(8 * (o0 + q) + 2 * j, f[8 * q + 2 * j]), fin(8 * (o0 + q) + 2 * j + 1, f[8 * q + 2 * j + 1]));
+        st_shared_v4(tile_row + 2048u * (o0 + q), pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+}
+
+// the same from the thread-local copy of the row (`loc`, 64 floats, zeros behind the S real elements).  The copy lives in L2 (the
+// output groups' local arrays exceed the small L1 left beside 227 KB of shared memory), so a round's 32 loads are issued together
+template <typename F>
+__device__ __forceinline__ void write_input_octets_local(uint32_t tile_row, int n_oct, const float* loc, F fin) {
+#pragma unroll 1
+  for (int o0 = 0; o0 < n_oct; o0 += 4) {
+    float f[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) f[e] = 8 * o0 + e < 64 ? loc[8 * o0 + e] : 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (o0 + q < n_oct) {
@@ -647,6 +703,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
     float4 np4 = make_float4(0.f, 0.f, 0.f, 0.f);                          // policy draws of the staged tile
     uint32_t xn[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                     // narrow states: the staged tile's normalised state, packed bf16 pairs
     constexpr bool narrow = !kWide;                                        // S <= 15
+    // wide states: the raw state row of the tile in flight and of the staged next tile (filled by the prologue, read again by the
+    // member-input and diff-head passes) in thread-local memory
+    float srow[kWide ? 2 : 1][kWide ? 64 : 1];
 
     auto prologue = [&](int tile, uint32_t it) {
       // ---- policy input [s, 1] -> the slot's xp tile; torch.normal of policy.act keyed by the row's global trajectory id ----
@@ -670,8 +729,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         st_shared_v4(xprow, pk[0], pk[1], pk[2], pk[3]);
         st_shared_v4(xprow + 2048u, pk[4], pk[5], pk[6], pk[7]);          // K0p = 16
       } else {
-        write_input_octets_wide(xprow, plan.K0p >> 3, [&](int k) { return (k < S && valid) ? __ldg(ps + k) : 0.f; },
-                                [&](int k, float x) { return k < S ? x : (k == xp_one ? 1.f : 0.f); });
+        write_input_octets_wide(xprow, plan.K0p >> 3, ps, S, valid, (S & 3) == 0,
+                                [&](int k, float x) { return k < S ? x : (k == xp_one ? 1.f : 0.f); }, srow[it & 1u]);
       }
       fence_proxy_async();                                                // generic-proxy writes of xp -> visible to the tensor core
       __syncwarp();
@@ -728,8 +787,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           st_shared_v4(xrow + 2048u, pk[4], pk[5], pk[6], pk[7]);
           write_input_octets(xrow, 2, plan.K0m >> 3, tail);                // (K0m = 32 when S + A + 1 > 16)
         } else {
-          write_input_octets_wide(xrow, plan.K0m >> 3, [&](int k) { return (k < S && valid) ? __ldg(my_s + k) : 0.f; },
-                                  [&](int k, float x) { return k < S ? (valid ? (x - sm->norm_mean[k]) * sm->norm_inv[k] : 0.f) : tail(k); });
+          write_input_octets_local(xrow, plan.K0m >> 3, srow[it & 1],
+                                   [&](int k, float x) { return k < S ? (valid ? (x - sm->norm_mean[k]) * sm->norm_inv[k] : 0.f) : tail(k); });
         }
         fence_proxy_async();
         tc_fence_before();
@@ -802,9 +861,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         }
       } else {
         // wide states (O > 16): the diff head's accumulator sits in columns the log-var hidden layer overwrites, so the means are
-        // parked in the output arrays (this thread's own row) until the log-var head arrives; the Gaussian draws are generated while the
-        // log-var layers run and parked in (L2-resident) local memory
-        float evw[64];
+        // parked until the log-var head arrives; the Gaussian draws are generated while the log-var layers run.  Both are parked in
+        // thread-local memory (lane-interleaved: every access is one coalesced wavefront; a thread's own 240-byte row in global
+        // memory costs 32 sectors per warp instruction) and the state row comes from the copy the prologue kept: the only
+        // global-memory traffic of the tile's output is ONE pass of 16-byte stores.
+        float evw[64], mvw[64];
+        const bool vec = (S & 3) == 0;                                     // 16-byte aligned rows: one vector store per four columns
+        float* my_ns = p.next_states + row * S;
+        const float* my_row = srow[it & 1];
         mbar_wait(&sm->out_full[slot][1], par, err, 7);
         tc_fence_after();
         if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 3);
@@ -812,17 +876,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           uint32_t r[16]; tmem_ld16(region + plan.d1_col + (uint32_t)c0, r);
           float sv[16];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) sv[jj] = (c0 + jj < S && valid) ? __ldg(my_s + c0 + jj) : 0.f;
+          for (int jj = 0; jj < 16; ++jj) sv[jj] = c0 + jj < S ? my_row[c0 + jj] : 0.f;
           tmem_ld_wait();
           if (kDebug && p.dump_layer == 7 && valid) for (int jj = 0; jj < 16; ++jj) if (c0 + jj < O) p.dump_out[row * O + c0 + jj] = __uint_as_float(r[jj]);
-          if (valid) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int c = c0 + jj;
-              if (c < S) p.next_states[row * S + c] = __uint_as_float(r[jj]) + sv[jj];
-              else if (c == S) p.rewards[row] = __uint_as_float(r[jj]);
-            }
-          }
+          for (int jj = 0; jj < 16; ++jj) mvw[c0 + jj] = __uint_as_float(r[jj]) + sv[jj];       // means = diffs + [s, 0]      src/dynamics.py:118
         }
         tc_fence_before();
         __syncwarp();
@@ -841,11 +899,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           uint32_t r[16]; tmem_ld16(region + plan.v1_col + (uint32_t)c0, r);
           float mv[16], ev[16];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int c = c0 + jj;
-            mv[jj] = (c <= S && valid) ? (c < S ? p.next_states[row * S + c] : p.rewards[row]) : 0.f;
-            ev[jj] = c < O ? evw[c] : 0.f;
-          }
+          for (int jj = 0; jj < 16; ++jj) { mv[jj] = mvw[c0 + jj]; ev[jj] = c0 + jj < O ? evw[c0 + jj] : 0.f; }
           tmem_ld_wait();
           if (c0 + 16 >= No) {
             tc_fence_before();
@@ -855,14 +909,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           if (kDebug && p.dump_layer == 8 && valid) for (int jj = 0; jj < 16; ++jj) if (c0 + jj < O) p.dump_out[row * O + c0 + jj] = __uint_as_float(r[jj]);
           if (valid) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int c = c0 + jj;
-              if (c < O) {
+            for (int g4 = 0; g4 < 4; ++g4) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int jj = 4 * g4 + e, c = min(c0 + jj, O - 1);
                 const float u = __expf(sm->lv_hi[c] - __uint_as_float(r[jj]));
                 const float sd = sm->lv_s0[c] * sqrt_fast(1.f + __fdividef(sm->lv_E[c], 1.f + u));
-                float* dst = c < S ? p.next_states + row * S + c : p.rewards + row;
-                *dst = fmaf(sd, ev[jj], mv[jj]);
+                v[e] = fmaf(sd, ev[jj], mv[jj]);
+                if (c0 + jj == S) p.rewards[row] = v[e];
               }
+              store_row4(my_ns, c0 + 4 * g4, S, vec, v);
             }
           }
         }

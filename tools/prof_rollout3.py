@@ -5,14 +5,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import drpo_b200
 from drpo_b200 import synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 2 * 4
-S, A, C = 12, 2, 2
+wl = sys.argv[2] if len(sys.argv) > 2 else "quadrotor"
+env_name, S, A, C = synthetic.WORKLOADS[wl]
 dev = torch.device("cuda:0")
 cfg = drpo_b200.SMBPO.Config(); cfg.rollout_batch_size, cfg.horizon, cfg.buffer_max = B, 1, B * 2
-alg = drpo_b200.SMBPO(cfg, drpo_b200.device_env("quadrotor"), device=dev)
+alg = drpo_b200.SMBPO(cfg, drpo_b200.device_env(env_name), device=dev)
 alg.model_ensemble.load_state_dict(synthetic.make_ensemble_weights(1, S, A)); alg.model_ensemble._elite_inds = [0, 1, 2, 3, 4]
 alg.solver.load_state_dict(synthetic.make_ssac_weights(2, S, A, C), strict=False)
 alg.rollout_precision = drpo_b200.PREC_BF16
-init = synthetic.make_start_states("quadrotor", B, 3).to(dev)
+init = synthetic.make_start_states(wl, B, 3).to(dev)
 for _ in range(2):
     out = alg.rollout(alg.actor, initial_states=init, member_idx=[0], _debug_layer=100)
 torch.cuda.synchronize()
