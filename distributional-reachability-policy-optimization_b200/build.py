@@ -22,7 +22,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "drpo_b200.h"))
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
@@ -30,8 +30,18 @@ def build(force=False, verbose=False):
             cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
         objs.append(o)
+    if jobs:                                   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            for r in ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs):
+                if verbose and (r.stdout or r.stderr):
+                    sys.stdout.write(r.stdout); sys.stderr.write(r.stderr)
+                if r.returncode != 0:
+                    if not verbose:
+                        sys.stderr.write(r.stderr)
+                    raise subprocess.CalledProcessError(r.returncode, r.args)
     if force or not _newer(OUT, objs):
         cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcuda", "-lcublas", "-lcublasLt"]
         if verbose:
