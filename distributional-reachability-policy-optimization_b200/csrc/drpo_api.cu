@@ -576,7 +576,7 @@ int drpo_ensemble_train_step(const drpo_ensemble_train_args* a) {
   }
   DRPO_CHECK_ARG(a->precision == DRPO_PREC_FP32 || a->precision == DRPO_PREC_BF16 || a->precision == DRPO_PREC_TF32,
                  "drpo_ensemble_train_step: unknown precision %d", a->precision);
-  g_gemm_mode = a->precision != DRPO_PREC_FP32 ? 1 : 0;
+  g_gemm_mode = a->precision == DRPO_PREC_TF32 ? 1 : 0;          // library GEMMs only on explicit request; DRPO_PREC_BF16 = the fp32 kernels here
   rc = ensemble_train_step(*a);
   g_gemm_mode = 0;
   return rc;

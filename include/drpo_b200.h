@@ -371,7 +371,7 @@ typedef struct drpo_ensemble_train_args {
   drpo_adam adam;
   int32_t phases;
   float* losses;               /* device [1 + ensemble_size]: compute_loss, then every member's NLL */
-  int32_t precision;           /* DRPO_PREC_FP32, or DRPO_PREC_TF32 / DRPO_PREC_BF16 = TF32 tensor-op GEMMs */
+  int32_t precision;           /* DRPO_PREC_FP32 (also what DRPO_PREC_BF16 runs here: no fused kernel for the training iteration); DRPO_PREC_TF32 = library TF32 GEMMs */
   void* workspace; int64_t workspace_bytes; void* stream;
 } drpo_ensemble_train_args;
 
