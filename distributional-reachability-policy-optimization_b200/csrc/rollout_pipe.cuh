@@ -874,14 +874,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 3);
         for (int c0 = 0; c0 < No; c0 += 16) {
           uint32_t r[16]; tmem_ld16(region + plan.d1_col + (uint32_t)c0, r);
-          float sv[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) sv[jj] = c0 + jj < S ? my_row[c0 + jj] : 0.f;
           tmem_ld_wait();
           if (kDebug && p.dump_layer == 7 && valid) for (int jj = 0; jj < 16; ++jj) if (c0 + jj < O) p.dump_out[row * O + c0 + jj] = __uint_as_float(r[jj]);
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) mvw[c0 + jj] = __uint_as_float(r[jj]) + sv[jj];       // means = diffs + [s, 0]      src/dynamics.py:118
-        }
+          for (int jj = 0; jj < 16; ++jj) mvw[c0 + jj] = __uint_as_float(r[jj]);       // (the state is added in the last pass: this one is on the
+        }                                                                            // critical path of the log-var hidden layer)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) sig_arrive(&sm->sig[slot][C_D1R], crank);                     // the log-var hidden layer may overwrite the diff head
@@ -895,11 +892,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         mbar_wait(&sm->out_full[slot][2], par, err, 7);
         tc_fence_after();
         if (t == 0) stamp<kDebug>(p, (uint32_t)it, sidx, 4);
+        // first pass: drain the log-var head's accumulator (std * eps replaces eps in the local array) so that the slot's next tile
+        // may start (C_OUT) before the sums and the global stores of the second pass
         for (int c0 = 0; c0 < No; c0 += 16) {
           uint32_t r[16]; tmem_ld16(region + plan.v1_col + (uint32_t)c0, r);
-          float mv[16], ev[16];
+          float ev[16];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) { mv[jj] = mvw[c0 + jj]; ev[jj] = c0 + jj < O ? evw[c0 + jj] : 0.f; }
+          for (int jj = 0; jj < 16; ++jj) ev[jj] = c0 + jj < O ? evw[c0 + jj] : 0.f;
           tmem_ld_wait();
           if (c0 + 16 >= No) {
             tc_fence_before();
@@ -907,18 +906,24 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
             if (lane == 0) sig_arrive(&sm->sig[slot][C_OUT], crank);
           }
           if (kDebug && p.dump_layer == 8 && valid) for (int jj = 0; jj < 16; ++jj) if (c0 + jj < O) p.dump_out[row * O + c0 + jj] = __uint_as_float(r[jj]);
-          if (valid) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int c = min(c0 + jj, O - 1);
+            const float u = __expf(sm->lv_hi[c] - __uint_as_float(r[jj]));
+            evw[c0 + jj] = sm->lv_s0[c] * sqrt_fast(1.f + __fdividef(sm->lv_E[c], 1.f + u)) * ev[jj];
+          }
+        }
+        if (valid) {
+          for (int c0 = 0; c0 < No; c0 += 16) {
+            float o16[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)                               // means = diffs + [s, 0] (src/dynamics.py:118), + std * eps (:201-203)
+              o16[jj] = (mvw[c0 + jj] + (c0 + jj < S ? my_row[c0 + jj] : 0.f)) + evw[c0 + jj];
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-              float v[4];
+              const float v[4] = {o16[4 * g4], o16[4 * g4 + 1], o16[4 * g4 + 2], o16[4 * g4 + 3]};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int jj = 4 * g4 + e, c = min(c0 + jj, O - 1);
-                const float u = __expf(sm->lv_hi[c] - __uint_as_float(r[jj]));
-                const float sd = sm->lv_s0[c] * sqrt_fast(1.f + __fdividef(sm->lv_E[c], 1.f + u));
-                v[e] = fmaf(sd, ev[jj], mv[jj]);
-                if (c0 + jj == S) p.rewards[row] = v[e];
-              }
+              for (int e = 0; e < 4; ++e) if (c0 + 4 * g4 + e == S) p.rewards[row] = v[e];
               store_row4(my_ns, c0 + 4 * g4, S, vec, v);
             }
           }
