@@ -132,7 +132,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
       for (int oi = 0; oi < n_chain; ++oi) {
         const EOp d = p.eop[p.sch.order[chain][oi]];
         const uint32_t region = d.out_region == 0 ? 0u : (d.out_region == 1 ? TM_R0 : TM_R1);
-        if (!d.backward) epi_forward(e, region, p.sv[d.save], d.hw_off, d.no, hpart, d.wait_all != 0);
+        if (!d.backward) epi_forward_halfwise(e, region, p.sv[d.save], d.hw_off, d.no, hpart, d.wait_all != 0);
         else epi_backward(e, p.sv[d.hsave], d.bias_slot, p.sv[d.save], region, d.wait_all != 0);
         if (d.post == POST_POLICY0 || d.post == POST_POLICY1) {
           // squashed-Gaussian sample of the next action (+ log-prob)                       src/ssac.py:286-288, 340-341

@@ -40,7 +40,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
   uint8_t* ring = smem;
   uint8_t* xs0 = ring + (size_t)stages * CHUNK_BYTES;
   uint8_t* ones = xs0 + TILE * p.Kx * 2;
-  FusedSmem* sm = reinterpret_cast<FusedSmem*>(ones + TILE * KBIAS * 2);
+  float* obuf = reinterpret_cast<float*>(ones + TILE * KBIAS * 2);          // [128 rows][S + 1]: the tile's output rows, staged for coalesced stores
+  FusedSmem* sm = reinterpret_cast<FusedSmem*>(obuf + TILE * 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int PRODUCER = EPI_THREADS / 32, ISSUER = PRODUCER + 1;
   int* err = p.err_flag;
@@ -105,41 +106,47 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 #pragma unroll 1
       for (int oi = 0; oi < ENS_OPS; ++oi) {
         if (oi != 3 && oi != 5) {
-          epi_forward(e, oi == 1 ? TM_R1 : TM_R0, nullptr, 0, 0, hpart, false, 2);
+          epi_forward_halfwise(e, oi == 1 ? TM_R1 : TM_R0, nullptr, 0, 0, hpart, false, 2);
         } else {
           // output layer: columns 0..S of accumulator 0 hold [next_state - state, reward] (oi == 3) or the raw log-variance (oi == 5)
           epi_wait_acc(e);
-          uint32_t raw[2][32];
-          if (e.g == 0) {
-            tmem_ld32(e.tm + TM_ACC, raw[0]);
-            tmem_ld32(e.tm + TM_ACC + 32, raw[1]);
-            tmem_ld_wait();
-          }
-          epi_free_acc(e);
-          ++e.it;
-          if (e.g == 0 && e.valid) {
-            if (!p.sample) {
-              float* out = (oi == 3 ? p.means : p.log_vars) + slot * p.slot_stride_out + e.grow * O;
+          float* orow = obuf + e.row * O;
+          // The thread's row goes to shared memory first and the 128 rows leave as ONE contiguous block ([B, S+1] row-major: a tile's
+          // rows are adjacent) instead of 4-byte pieces at a 4(S+1)-byte stride per thread.  32 columns at a time (register budget).
 #pragma unroll
-              for (int c = 0; c < 64; ++c) {
-                if (c < O) {
-                  const float v = __uint_as_float(raw[c >> 5][c & 31]);
-                  out[c] = oi == 3 ? __fadd_rn(v, c < S ? st[c] : 0.f) : soft_clamp(v, p.min_lv[c], p.max_lv[c]);
-                }
-              }
-            } else {
-              // samples = means + sqrt(exp(log_vars)) * eps                           src/dynamics.py:201-203
-              float* ns = p.next_states + e.grow * S;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t raw[32];
+            if (e.g == 0 && 32 * half < O) {
+              tmem_ld32(e.tm + TM_ACC + 32 * half, raw);
+              tmem_ld_wait();
+            }
+            if (half == 1) { epi_free_acc(e); ++e.it; }
+            if (e.g == 0 && 32 * half < O) {
 #pragma unroll
-              for (int c = 0; c < 64; ++c) {
+              for (int j = 0; j < 32; ++j) {
+                const int c = 32 * half + j;
                 if (c < O) {
-                  const float v = __uint_as_float(raw[c >> 5][c & 31]);
-                  float* dst = c < S ? ns + c : p.rewards + e.grow;
-                  if (oi == 3) *dst = __fadd_rn(v, c < S ? st[c] : 0.f);
-                  else *dst = fmaf(sqrtf(expf(soft_clamp(v, p.min_lv[c], p.max_lv[c]))), p.noise.get(e.grow, c), *dst);
+                  const float v = __uint_as_float(raw[j]);
+                  if (oi == 3) orow[c] = __fadd_rn(v, (c < S && e.valid) ? st[c] : 0.f);                  // means = diffs + [s, 0]   src/dynamics.py:118
+                  else if (!p.sample) orow[c] = soft_clamp(v, p.min_lv[c], p.max_lv[c]);                // soft-clamped log-variance     :119-121
+                  else orow[c] = fmaf(sqrtf(expf(soft_clamp(v, p.min_lv[c], p.max_lv[c]))), e.valid ? p.noise.get(e.grow, c) : 0.f, orow[c]);   // :201-203
                 }
               }
             }
+          }
+          if (e.g == 0) {
+            named_bar_sync(2, TILE);
+            const int64_t row0 = (int64_t)tile * TILE;
+            const int rows = (int)max((int64_t)0, min((int64_t)TILE, p.B - row0));
+            if (!p.sample) {
+              float* dst = (oi == 3 ? p.means : p.log_vars) + slot * p.slot_stride_out + row0 * O;
+              for (int i = e.row; i < rows * O; i += TILE) dst[i] = obuf[i];
+            } else if (oi == 5) {
+              float* dst = p.next_states + row0 * S;
+              for (int i = e.row; i < rows * S; i += TILE) { const int r = i / S; dst[i] = obuf[r * O + (i - r * S)]; }
+              if (e.valid) p.rewards[e.grow] = orow[S];
+            }
+            if (!p.sample || oi == 5) named_bar_sync(2, TILE);                                         // (sample mode keeps the means until the log-var head)
           }
         }
         if (oi != ENS_OPS - 1) epi_op_done(e);
@@ -186,7 +193,7 @@ int ens_bf16_run(const drpo_ensemble& e, int m0, int m1, int per_member_inputs, 
   EnsParams fp; memset(&fp, 0, sizeof(fp));
   const int64_t Bpad = (batch + CLUSTER * TILE - 1) / (CLUSTER * TILE) * (CLUSTER * TILE);
   fp.B = batch; fp.Bpad = Bpad; fp.S = S; fp.A = A; fp.Kx = Kx; fp.n_tiles = (int)(Bpad / TILE);
-  const size_t fixed = (size_t)TILE * Kx * 2 + TILE * KBIAS * 2 + sizeof(FusedSmem);
+  const size_t fixed = (size_t)TILE * Kx * 2 + TILE * KBIAS * 2 + (size_t)TILE * 64 * sizeof(float) + sizeof(FusedSmem);
   int stages = (int)((232448 - 1024 - fixed) / CHUNK_BYTES);
   if (stages > 6) stages = 6;
   fp.stages = stages;

@@ -188,7 +188,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
       for (int o = 0; o < p.n_ops; ++o) {
         const EOp d = p.eop[o];
         const uint32_t region = d.out_region == 0 ? 0u : (d.out_region == 1 ? TM_R0 : TM_R1);
-        if (!d.backward) epi_forward(e, region, p.sv[d.save], d.hw_off, d.no, hpart, d.wait_all != 0, d.act);
+        if (!d.backward) epi_forward_halfwise(e, region, p.sv[d.save], d.hw_off, d.no, hpart, d.wait_all != 0, d.act);
         else epi_backward(e, p.sv[d.hsave], d.bias_slot, p.sv[d.save], region, d.wait_all != 0, d.act, d.hw_off, d.no, hpart);
         float* dbg = (p.dbg && e.g == 0 && e.valid) ? p.dbg + gr * 16 : nullptr;
 

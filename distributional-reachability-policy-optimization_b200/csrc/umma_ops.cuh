@@ -145,13 +145,16 @@ static __global__ void gather_ctab_kernel(CopyTable t, float* __restrict__ out) 
 __device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
-// column sums over the 32 rows of a warp: v[j] = this row's value of column j; returns the sum of column `lane`
-__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
+// column sums over the 32 rows of a warp: f(j) = this row's value of column j (j is a compile-time constant at every call site,
+// so the 32 values need not exist at the same time as an array); returns the sum of column `lane`
+template <class F>
+__device__ __forceinline__ float colsum32_f(int lane, F f) {
   float w[16];
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float keep = b4 ? v[i + 16] : v[i], send = b4 ? v[i] : v[i + 16];
+    const float lo = f(i), hi = f(i + 16);
+    const float keep = b4 ? hi : lo, send = b4 ? lo : hi;
     w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
   }
 #pragma unroll
@@ -171,6 +174,9 @@ __device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
   }
   const float keep = b0 ? w[1] : w[0], send = b0 ? w[0] : w[1];
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
+  return colsum32_f(lane, [&](int j) { return v[j]; });
 }
 
 // per-thread view of the fused kernel's epilogue state
@@ -220,6 +226,11 @@ __device__ __forceinline__ void save_octets(const Epi& e, __nv_bfloat16* base, i
 }
 __device__ __forceinline__ void add_colsum(const Epi& e, int slot, int half, const float (&v)[32]) {
   const float s = colsum32(v, e.lane);
+  atomicAdd(&e.gacc[slot * HID + e.g * 64 + half * 32 + e.lane], s);
+}
+template <class F>
+__device__ __forceinline__ void add_colsum_f(const Epi& e, int slot, int half, F f) {
+  const float s = colsum32_f(e.lane, f);
   atomicAdd(&e.gacc[slot * HID + e.g * 64 + half * 32 + e.lane], s);
 }
 
@@ -284,6 +295,62 @@ __device__ __forceinline__ void epi_forward(Epi& e, uint32_t out_region, __nv_bf
     }
   }
   if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 18 + 4 * e.g] = clock64();
+  ++e.it;
+}
+
+// The same epilogue, 32 accumulator columns at a time: half the live registers.  With 18 warps per CTA the register file gives 96
+// registers per thread; epi_forward's 64-register accumulator block plus an activation's temporaries exceed that, and ptxas moves the
+// whole block through local memory (ncu source page of the SiLU ensemble kernel: 58 STL.64 + as many LDL.64 per thread and layer,
+// 0.8 G L2 sectors per launch - the epilogue was waiting on L2 round trips of its own spills).  Costs a second tcgen05.ld round trip
+// and frees the accumulator ~200 cycles later.
+__device__ __forceinline__ void epi_forward_halfwise(Epi& e, uint32_t out_region, __nv_bfloat16* save, int hw_off, int no,
+                                                     float (&hpart)[MAXO], bool wait_all, int act = 0) {
+  epi_wait_acc(e);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t raw[32];
+    tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
+    tmem_ld_wait();
+    if (half == 1) epi_free_acc(e);
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(raw[j]);
+        const float hx = 0.5f * x;
+        raw[j] = __float_as_uint(act == 1 ? tanh_fast(x) : fmaf(hx, tanh_fast(hx), hx));
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < no) {
+        const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
+        float acc = hpart[o];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = w4[j];
+          const float h0 = __uint_as_float(raw[4 * j]), h1 = __uint_as_float(raw[4 * j + 1]);
+          const float h2 = __uint_as_float(raw[4 * j + 2]), h3 = __uint_as_float(raw[4 * j + 3]);
+          acc = fmaf(act ? h0 : fmaxf(h0, 0.f), w.x, acc);
+          acc = fmaf(act ? h1 : fmaxf(h1, 0.f), w.y, acc);
+          acc = fmaf(act ? h2 : fmaxf(h2, 0.f), w.z, acc);
+          acc = fmaf(act ? h3 : fmaxf(h3, 0.f), w.w, acc);
+        }
+        hpart[o] = acc;
+      }
+    }
+    if (out_region || save) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        pk[j] = act ? pack_bf16(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]))
+                    : pack_bf16_relu(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+      if (save) save_octets(e, save, half, pk);
+      if (out_region) {
+        if (wait_all && half == 0) epi_wait_all_mma(e);
+        tmem_st16(e.tm + out_region + e.g * 32 + half * 16, pk);
+      }
+    }
+  }
   ++e.it;
 }
 
@@ -370,9 +437,9 @@ __device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const
       tmem_ld16(e.tm + region + e.g * 32 + half * 16, hp16);
       tmem_ld_wait();
     }
-    float h[32];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { h[2 * j] = bf_lo(hp16[j]); h[2 * j + 1] = bf_hi(hp16[j]); }
+    // (h stays packed: 16 registers instead of 32, unpacked where it is used; the products d[o] * h feeding the weight-gradient
+    // column sums are formed inside the butterfly - the register file gives 96 registers per thread and spills go to L2)
+    auto hval = [&](int j) { return (j & 1) ? bf_hi(hp16[j >> 1]) : bf_lo(hp16[j >> 1]); };
     float dh[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) dh[j] = 0.f;
@@ -380,10 +447,8 @@ __device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const
     for (int o = 0; o < MAXO; ++o) {
       if (o < no) {
         if (w_slot0 >= 0) {
-          float t[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) t[j] = d[o] * h[j];
-          add_colsum(e, w_slot0 + o, half, t);
+          const float dd = d[o];
+          add_colsum_f(e, w_slot0 + o, half, [&](int j) { return dd * hval(j); });
         }
         const float4* w4 = reinterpret_cast<const float4*>(e.ctab + hw_off + o * HID + e.g * 64 + half * 32);
 #pragma unroll
@@ -395,7 +460,7 @@ __device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const
       }
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) dh[j] = act ? dh[j] * (1.f - h[j] * h[j]) : (h[j] > 0.f ? dh[j] : 0.f);
+    for (int j = 0; j < 32; ++j) { const float hj = hval(j); dh[j] = act ? dh[j] * (1.f - hj * hj) : (hj > 0.f ? dh[j] : 0.f); }
     if (bias_slot != NO_SLOT) add_colsum(e, bias_slot, half, dh);
     uint32_t pk[16];
 #pragma unroll
