@@ -47,8 +47,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], CLUSTER); }
-    for (int g = 0; g < NGROUPS; ++g) { mbar_init(&sm->acc_full[g], 1); mbar_init(&sm->acc_free[g], 128); }
-    mbar_init(&sm->act_ready[0], EPI_THREADS); mbar_init(&sm->act_ready[1], EPI_THREADS);
+    for (int g = 0; g < NGROUPS; ++g) { mbar_init(&sm->acc_full[g], 1); mbar_init(&sm->acc_free[g], 4); }
+    mbar_init(&sm->act_ready[0], EPI_THREADS / 32); mbar_init(&sm->act_ready[1], EPI_THREADS / 32);
     fence_barrier_init();
   }
   if (warp == ISSUER) tmem_alloc(&sm->tmem_base, 512);

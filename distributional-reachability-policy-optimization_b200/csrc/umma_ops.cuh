@@ -200,9 +200,12 @@ __device__ __forceinline__ void epi_wait_acc(Epi& e) {
   tc_fence_after();
   if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 16 + 4 * e.g] = clock64();
 }
+// (one arrival per WARP on the epilogue -> issuer barriers: every lane fences, the warp converges, lane 0 arrives - 16 + 16 arrivals
+// per op instead of 512 + 512 serialised shared-memory atomics on the hand-off path)
 __device__ __forceinline__ void epi_free_acc(Epi& e) {
   tc_fence_before();
-  mbar_arrive(&e.sm->acc_free[e.g]);
+  __syncwarp();
+  if (e.lane == 0) mbar_arrive(&e.sm->acc_free[e.g]);
 }
 // all of this op's MMAs (every chunk) have completed: the op's A regions may be overwritten
 __device__ __forceinline__ void epi_wait_all_mma(Epi& e) {
@@ -212,8 +215,9 @@ __device__ __forceinline__ void epi_wait_all_mma(Epi& e) {
 __device__ __forceinline__ void epi_op_done(Epi& e) {      // this thread's TMEM / shared writes for the next op are complete
   tmem_st_wait();
   tc_fence_before();
-  mbar_arrive(&e.sm->act_ready[e.arr & 1]);      // arrival number k enables op k; even / odd ops use separate barriers so that an
-  ++e.arr;                                       // issuer that observes op k's phase late can never be two phases behind
+  __syncwarp();
+  if (e.lane == 0) mbar_arrive(&e.sm->act_ready[e.arr & 1]);      // arrival number k enables op k; even / odd ops use separate barriers so
+  ++e.arr;                                                        // that an issuer that observes op k's phase late can never be two phases behind
 }
 // 16-byte panels of 32 packed columns -> global octet layout
 __device__ __forceinline__ void save_octets(const Epi& e, __nv_bfloat16* base, int half, const uint32_t (&pk)[16]) {
@@ -312,6 +316,7 @@ __device__ __forceinline__ void epi_forward_halfwise(Epi& e, uint32_t out_region
     tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
     tmem_ld_wait();
     if (half == 1) epi_free_acc(e);
+    if (half == 0 && e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 17 + 4 * e.g] = clock64();
     if (act) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -351,6 +356,7 @@ __device__ __forceinline__ void epi_forward_halfwise(Epi& e, uint32_t out_region
       }
     }
   }
+  if (e.prof && e.it >= MAX_OPS && e.it < 2 * MAX_OPS) e.prof[(e.it - MAX_OPS) * 32 + 18 + 4 * e.g] = clock64();
   ++e.it;
 }
 
