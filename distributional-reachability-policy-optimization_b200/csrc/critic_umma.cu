@@ -15,9 +15,10 @@
 //       layout as MN-major UMMA operands (K = batch rows), 256 x N fp32 accumulated in TMEM, one partial per CTA.
 //   critic_grad_reduce_kernel   sums the split-K partials / per-CTA column sums into the gradient arena.
 //
-// Octet layout of a saved [rows, F] bf16 matrix: element (r, f) at ((f / 8) * rows_padded + r) * 8 + f % 8, i.e. one
-// [rows, 8] panel per 8 features.  The fused kernel's threads (one per row) write 16-byte vectors that are contiguous across
-// a warp, and a 64-row slab of one panel is a contiguous 1 KB block = 8 no-swizzle MN-major core matrices.
+// Slab-octet layout of a saved [rows, F] bf16 matrix (umma_ops.cuh: oct_index): per 64-row slab one [64 rows][8] panel per 8 features,
+// the slab's panels contiguous.  The fused kernel's threads (one per row) write 16-byte vectors that are contiguous across a warp,
+// one panel of a slab is a contiguous 1 KB block = 8 no-swizzle MN-major core matrices, and a whole slab (all panels) is what one
+// stage of the dW kernel consumes: one bulk copy per operand.
 #include "critic_umma_api.h"
 #include "umma_ops.cuh"
 
@@ -110,7 +111,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
         *reinterpret_cast<uint4*>(xs0 + j * 2048 + e.row * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
         const uint4 v1 = make_uint4(w1[0], w1[1], w1[2], w1[3]);
         *reinterpret_cast<uint4*>(xs1 + j * 2048 + e.row * 16) = v1;
-        *reinterpret_cast<uint4*>(p.x_sa + ((int64_t)j * p.Bpad + e.grow) * 8) = v1;
+        *reinterpret_cast<uint4*>(p.x_sa + oct_index(e.grow, j, p.Kx >> 3)) = v1;
       }
       const float rew = e.valid ? p.rew[gr] : 0.f;
       const float dn = (e.valid && p.done[gr]) ? 1.f : 0.f;

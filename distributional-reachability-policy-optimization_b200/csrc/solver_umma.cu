@@ -172,7 +172,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
         }
         const uint4 v = make_uint4(w0[0], w0[1], w0[2], w0[3]);
         *reinterpret_cast<uint4*>(xs0 + j * 2048 + e.row * 16) = v;
-        if (MODE == MODE_ACTOR) *reinterpret_cast<uint4*>(p.x_obs + ((int64_t)j * p.Bpad + e.grow) * 8) = v;
+        if (MODE == MODE_ACTOR) *reinterpret_cast<uint4*>(p.x_obs + oct_index(e.grow, j, p.Kx >> 3)) = v;
       }
       fence_proxy_async();
       epi_op_done(e);
@@ -247,7 +247,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
               }
               const uint4 vv = make_uint4(w0[0], w0[1], w0[2], w0[3]);
               *reinterpret_cast<uint4*>(xs1 + j * 2048 + e.row * 16) = vv;
-              if (MODE == MODE_MULT) *reinterpret_cast<uint4*>(p.x_aug + ((int64_t)j * p.Bpad + e.grow) * 8) = vv;
+              if (MODE == MODE_MULT) *reinterpret_cast<uint4*>(p.x_aug + oct_index(e.grow, j, p.Kx >> 3)) = vv;
             }
             fence_proxy_async();
             if (dbg) dbg[MODE == MODE_MULT ? 5 : 1] = qc;

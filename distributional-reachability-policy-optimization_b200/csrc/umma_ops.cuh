@@ -23,6 +23,13 @@ constexpr int TILE = 128;                  // batch rows per tile = TMEM lanes
 constexpr int NGROUPS = 4;                 // epilogue groups = 64-column slabs = accumulators
 constexpr int EPI_THREADS = NGROUPS * 128;
 constexpr int F_THREADS = EPI_THREADS + 64;   // + warp 16 TMA producer, warp 17 MMA issuer (owns the TMEM allocation)
+constexpr int OCT_ROWS = 64;                // rows per slab of a saved octet array = batch rows (K) per stage of the dW kernel
+// Saved [rows, F] bf16 matrix, slab-octet layout: element (r, f) at (((r / 64) * (F / 8) + f / 8) * 64 + r % 64) * 8 + f % 8, i.e. per
+// 64-row slab one [64 rows][8] panel per 8 features, the slab's F/8 panels contiguous.  A warp of the fused kernel (32 rows, one
+// 16-byte vector each) writes 512 contiguous bytes per panel; a dW stage (one slab of dH and of H) is ONE contiguous block per operand
+// - one bulk copy instead of F/8 copies of 1 KB, whose per-request cost held the dW kernel at 3.5 TB/s - and already in the order
+// of the MN-major UMMA core matrices ([panel][64 rows][8]).
+__host__ __device__ inline int64_t oct_index(int64_t row, int oct, int n_oct) { return ((((row >> 6) * n_oct + oct) << 6) + (row & 63)) * 8; }
 constexpr int MAX_OPS = 24;
 constexpr int MAXO = 4;                    // widest CUDA-core head: 2*action_dim <= 4, con_dim <= 4
 constexpr int KBIAS = 16;                  // extra K block of every forward weight chunk: bias (hi, lo) against a constant-ones A tile
@@ -225,7 +232,7 @@ __device__ __forceinline__ void save_octets(const Epi& e, __nv_bfloat16* base, i
   for (int o = 0; o < 4; ++o) {
     const int oct = e.g * 8 + half * 4 + o;
     uint4 v = make_uint4(pk[4 * o], pk[4 * o + 1], pk[4 * o + 2], pk[4 * o + 3]);
-    *reinterpret_cast<uint4*>(base + ((int64_t)oct * e.Bpad + e.grow) * 8) = v;
+    *reinterpret_cast<uint4*>(base + oct_index(e.grow, oct, HID / 8)) = v;
   }
 }
 __device__ __forceinline__ void add_colsum(const Epi& e, int slot, int half, const float (&v)[32]) {
@@ -373,7 +380,7 @@ __device__ __forceinline__ void epi_backward(Epi& e, const __nv_bfloat16* hsave,
     uint4 hv[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o)
-      hv[o] = *reinterpret_cast<const uint4*>(hsave + ((int64_t)(e.g * 8 + half * 4 + o) * e.Bpad + e.grow) * 8);
+      hv[o] = *reinterpret_cast<const uint4*>(hsave + oct_index(e.grow, e.g * 8 + half * 4 + o, HID / 8));
     uint32_t raw[32];
     tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
     tmem_ld_wait();
@@ -436,7 +443,7 @@ __device__ __forceinline__ void epi_head_backward(Epi& e, uint32_t region, const
     if (hglobal) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(hglobal + ((int64_t)(e.g * 8 + half * 4 + o) * e.Bpad + e.grow) * 8);
+        const uint4 hv = *reinterpret_cast<const uint4*>(hglobal + oct_index(e.grow, e.g * 8 + half * 4 + o, HID / 8));
         hp16[4 * o] = hv.x; hp16[4 * o + 1] = hv.y; hp16[4 * o + 2] = hv.z; hp16[4 * o + 3] = hv.w;
       }
     } else {
@@ -641,17 +648,17 @@ static __global__ void __launch_bounds__(DW_THREADS, 1) critic_dw_kernel(const _
   const uint32_t tmem = sm->tmem_base;
 
   if (warp == 0) {
-    // producer: every lane copies its share of the 32 + b_octets panels of each stage (1 KB each)
+    // producer: a stage = one 64-row slab of dH (32 panels, 32 KB contiguous) and of H (b_octets panels, contiguous): two bulk copies
     const uint32_t bytes = (32 + job.b_octets) * DW_PANEL;
-    for (int sl = slab0, n = 0; sl < slab1; ++sl, ++n) {
-      const uint32_t s = n % DW_STAGES, ph = (n / DW_STAGES) & 1;
-      mbar_wait(&sm->empty[s], ph ^ 1, err, 21);
-      if (lane == 0) mbar_expect_tx(&sm->full[s], bytes);
-      __syncwarp();
-      uint8_t* dst = smem + s * DW_STAGE_BYTES;
-      const int64_t row0 = (int64_t)sl * DW_ROWS;
-      bulk_g2s(dst + lane * DW_PANEL, job.a + ((int64_t)lane * p.Bpad + row0) * 8, DW_PANEL, &sm->full[s]);
-      if (lane < job.b_octets) bulk_g2s(dst + (32 + lane) * DW_PANEL, job.b + ((int64_t)lane * p.Bpad + row0) * 8, DW_PANEL, &sm->full[s]);
+    if (lane == 0) {
+      for (int sl = slab0, n = 0; sl < slab1; ++sl, ++n) {
+        const uint32_t s = n % DW_STAGES, ph = (n / DW_STAGES) & 1;
+        mbar_wait(&sm->empty[s], ph ^ 1, err, 21);
+        mbar_expect_tx(&sm->full[s], bytes);
+        uint8_t* dst = smem + s * DW_STAGE_BYTES;
+        bulk_g2s(dst, job.a + (int64_t)sl * 32 * (OCT_ROWS * 8), 32 * DW_PANEL, &sm->full[s]);
+        bulk_g2s(dst + 32 * DW_PANEL, job.b + (int64_t)sl * job.b_octets * (OCT_ROWS * 8), job.b_octets * DW_PANEL, &sm->full[s]);
+      }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(N, 1, 1);

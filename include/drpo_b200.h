@@ -287,7 +287,7 @@ int drpo_critic_step(const drpo_critic_args* args);
 /* Debug aids of the DRPO_PREC_BF16 critic step (tests): `rows` != NULL makes the next phase-1 calls write per-row
  * intermediates [batch,16] = a1[2], log-prob, a2[2], Q1', Q2', Qc' sample, Q1, Q2, Qc mean, Qc raw log-std, dL/dQ1, dL/dQ2,
  * dL/dmean, dL/dlogstd (first constraint).  drpo_debug_critic_dw runs the split-K weight-gradient kernel on one operand
- * pair given in the octet layout ([features/8][rows_padded][8] bf16): out[256, 8*b_octets] = dH^T H. */
+ * pair given in the slab-octet layout ([rows_padded/64][features/8][64][8] bf16): out[256, 8*b_octets] = dH^T H. */
 int drpo_debug_critic_rows(float* rows);
 /* profiling aid: device int64 [24][32] clock stamps per dense op (issuer: operands ready, MMAs issued, per-chunk waits; last epilogue group:
  * accumulator full, epilogue done) of CTA 0's second tile */

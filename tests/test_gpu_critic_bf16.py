@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _octets(x):
-    """[rows, F] -> the kernels' octet layout [F/8][rows][8] (bf16)."""
+    """[rows, F] -> the kernels' slab-octet layout [rows/64][F/8][64][8] (bf16): per 64-row slab one [64, 8] panel per 8 features."""
     rows, F = x.shape
-    return x.view(rows, F // 8, 8).permute(1, 0, 2).contiguous()
+    assert rows % 64 == 0
+    return x.view(rows // 64, 64, F // 8, 8).permute(0, 2, 1, 3).contiguous()
 
 
 @pytest.mark.parametrize("rows,n_in,ksplit", [(128, 256, 1), (1024, 256, 3), (4096, 64, 7), (640, 16, 2)])
