@@ -260,6 +260,11 @@ def ptr(t):
 
 
 def stream_ptr():
+    # the raw cudaStream_t of torch's current stream; the C accessor costs ~0.3 us where torch.cuda.current_stream().cuda_stream
+    # builds a Stream object (~15 us per call - a tenth of a data-parallel update step's host time)
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if get is not None:
+        return get(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -359,6 +359,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         self._ws = _lib.Workspace()
         self.noise_seed = 0xD2B0
         self.precision = _lib.PREC_FP32
+        self._ws_need = {}
         self.data_parallel = False          # set True under torchrun: gradients are all-reduced between backward and Adam
         self._dp_synced = False             # replicas are made identical (rank 0's state) at the first data-parallel step
         self._dp_rng = random.Random(0xD2B0)  # critic pick of the actor step under data parallelism: identical on every rank
@@ -587,7 +588,10 @@ class SSAC(Configurable, BasePolicy, nn.Module):
         a.discount, a.tau, a.grad_norm, a.qc_td_bound = self.discount, self.tau, self.grad_norm, self.qc_td_bound
         a.adam = opt.as_struct()
         a.losses, a.precision = _lib.ptr(self._losses), self.precision
-        ws = self._ws.get(lib.drpo_critic_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim), obs.device)
+        need = self._ws_need.get(B)
+        if need is None:                                    # (host time matters at the strong-scaled shard sizes: one C query per batch size)
+            need = self._ws_need[B] = lib.drpo_critic_workspace_bytes(B, self.state_dim, self.action_dim, self.con_dim, self.hidden_dim)
+        ws = self._ws.get(need, obs.device)
         a.workspace, a.workspace_bytes, a.stream = _lib.ptr(ws), ws.numel(), _lib.stream_ptr()
         if phases is not None:
             a.phases = phases
@@ -603,8 +607,7 @@ class SSAC(Configurable, BasePolicy, nn.Module):
             a.phases = 2
             _lib.check(lib.drpo_critic_step(a), "drpo_critic_step(optimizer)")
         self.critic_lr_scheduler.step()
-        out = self._losses[:2].clone()
-        return out[0], out[1]
+        return self._losses[:2].clone().unbind(0)           # (two 0-dim loss tensors, one copy kernel)
 
     def update_multiplier(self, obs, eps=None):
         """SSAC.update_multiplier (src/ssac.py:570-578)."""
