@@ -402,3 +402,38 @@ def test_ensemble_bf16_ragged_and_wide():
             assert_close(m, om, 2e-2, f"means S={S} B={B}"); assert_close(lv, olv, 2e-2, f"lv S={S} B={B}")
         torch.cuda.synchronize()
         _lib.check_kernel_status("ensemble bf16 ragged")
+
+
+def test_ensemble_bf16_many_members_and_philox_sample():
+    """Two paths of csrc/ens_umma.cu the golden vectors do not reach, held to this library's fp32 kernels (which the tests above pin to
+    the reference): an ensemble of more than 8 members (several (tile pair, member) launches share one weight-image buffer) and
+    sample() drawing its noise in the kernel (same Philox seed / tag / step in both precisions)."""
+    import drpo_b200
+    from drpo_b200 import _lib
+    S, A, E, B = 12, 2, 10, 777
+    cfg = drpo_b200.BatchedGaussianEnsemble.Config()
+    cfg.ensemble_size, cfg.num_elites = E, 5
+    torch.manual_seed(5)
+    ens = drpo_b200.BatchedGaussianEnsemble(cfg, S, A, device=dev())
+    with torch.no_grad():
+        for p in ens.parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.12)
+            elif p.numel() not in (S + 1,):
+                p.normal_(0.0, 0.05)
+    g = torch.Generator().manual_seed(6)
+    s, a = to_dev(torch.randn(B, S, generator=g)), to_dev(torch.rand(B, A, generator=g) * 2 - 1)
+    ens.state_normalizer.fit(s)
+    out = {}
+    for name, prec in (("fp32", drpo_b200.PREC_FP32), ("bf16", drpo_b200.PREC_BF16)):
+        ens.forward_precision = prec
+        ms, mr = ens.means(s, a)                               # all E members, shared inputs
+        ens._elite_inds = [9]
+        ens._noise_step = 41
+        ns, r = ens.sample(s, a)                               # member 9, in-kernel Philox (step 42 in both runs)
+        out[name] = (ms.clone(), mr.clone(), ns.clone(), r.clone())
+    torch.cuda.synchronize()
+    _lib.check_kernel_status("ensemble bf16 (10 members, philox sample)")
+    assert out["fp32"][0].shape == (E, B, S)
+    for i, what in enumerate(("means() states", "means() rewards", "sample() next_states", "sample() rewards")):
+        assert_close(out["bf16"][i], out["fp32"][i], 2e-2, what)
