@@ -250,8 +250,11 @@ __device__ __forceinline__ void store_row4(float* row, int k0, int S, bool vec, 
 // per octet; `fin(k, x)` turns the loaded value into element k
 // `keep` (a thread-local array of 64 floats, i.e. lane-interleaved local memory: every later access is one coalesced wavefront)
 // receives the raw row, so that the tile's later passes over its state do not go back to global memory with 32-sector accesses
-template <typename F>
-__device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n_oct, const float* row, int S, bool valid, bool vec, F fin, float* keep) {
+// `keepn` (32 words) receives nrm(k, x) of the same elements as packed bf16 pairs: the member input's state part, ready to be copied
+// when the action arrives (that copy is on the tile's critical path, the prologue is not)
+template <typename F, typename G>
+__device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n_oct, const float* row, int S, bool valid, bool vec, F fin, float* keep,
+                                                        uint32_t* keepn, G nrm) {
 #pragma unroll 1
   for (int o0 = 0; o0 < n_oct; o0 += 4) {
     float f[32];
@@ -264,6 +267,8 @@ __device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n
     if (8 * o0 < 64) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) keep[8 * o0 + e] = f[e];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) keepn[4 * o0 + e] = pack_bf16(nrm(8 * o0 + 2 * e, f[2 * e]), nrm(8 * o0 + 2 * e + 1, f[2 * e + 1]));
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -277,25 +282,30 @@ __device__ __forceinline__ void write_input_octets_wide(uint32_t tile_row, int n
   }
 }
 
-// the same from the thread-local copy of the row (`loc`, 64 floats, zeros behind the S real elements).  The copy lives in L2 (the
-// output groups' local arrays exceed the small L1 left beside 227 KB of shared memory), so a round's 32 loads are issued together
+// the member input from the thread-local packed copy of the normalised state (`locn`, 32 words = 64 bf16, written by the prologue):
+// octets that lie inside the state are copied, the others take `tail(k)` (actions, the bias slot, zeros) behind the state.  The copy
+// lives in L2 (the output groups' local arrays exceed the small L1 left beside 227 KB of shared memory): all loads are issued first.
 template <typename F>
-__device__ __forceinline__ void write_input_octets_local(uint32_t tile_row, int n_oct, const float* loc, F fin) {
-#pragma unroll 1
-  for (int o0 = 0; o0 < n_oct; o0 += 4) {
-    float f[32];
+__device__ __forceinline__ void write_input_octets_packed(uint32_t tile_row, int n_oct, const uint32_t* locn, int S, F tail) {
+  uint32_t w[32];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) f[e] = 8 * o0 + e < 64 ? loc[8 * o0 + e] : 0.f;
+  for (int e = 0; e < 32; ++e) w[e] = locn[e];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (o0 + q < n_oct) {
-        uint32_t pk[4];
+  for (int o = 0; o < 8; ++o) {
+    if (o < n_oct) {
+      uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(fin(8 * (o0 + q) + 2 * j, f[8 * q + 2 * j]), fin(8 * (o0 + q) + 2 * j + 1, f[8 * q + 2 * j + 1]));
-        st_shared_v4(tile_row + 2048u * (o0 + q), pk[0], pk[1], pk[2], pk[3]);
+      for (int j = 0; j < 4; ++j) {
+        const int k0 = 8 * o + 2 * j;
+        if (k0 + 1 < S) pk[j] = w[4 * o + j];
+        else pk[j] = pack_bf16(k0 < S ? __uint_as_float(w[4 * o + j] << 16) : tail(k0), tail(k0 + 1));
       }
+      st_shared_v4(tile_row + 2048u * o, pk[0], pk[1], pk[2], pk[3]);
     }
   }
+  for (int o = 8; o < n_oct; ++o)                        // (K0m > 64 only when S + A + 1 > 64)
+    st_shared_v4(tile_row + 2048u * o, pack_bf16(tail(8 * o), tail(8 * o + 1)), pack_bf16(tail(8 * o + 2), tail(8 * o + 3)),
+                 pack_bf16(tail(8 * o + 4), tail(8 * o + 5)), pack_bf16(tail(8 * o + 6), tail(8 * o + 7)));
 }
 
 // debug timing (kDebug build, dump_layer == 100): CTA 0 stamps clock() for its first 4 iterations into dump_out viewed as uint32
@@ -706,6 +716,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
     // wide states: the raw state row of the tile in flight and of the staged next tile (filled by the prologue, read again by the
     // member-input and diff-head passes) in thread-local memory
     float srow[kWide ? 2 : 1][kWide ? 64 : 1];
+    uint32_t nrow[kWide ? 2 : 1][kWide ? 32 : 1];                        // the same rows normalised, packed bf16 pairs (the member input's state part)
 
     auto prologue = [&](int tile, uint32_t it) {
       // ---- policy input [s, 1] -> the slot's xp tile; torch.normal of policy.act keyed by the row's global trajectory id ----
@@ -730,7 +741,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
         st_shared_v4(xprow + 2048u, pk[4], pk[5], pk[6], pk[7]);          // K0p = 16
       } else {
         write_input_octets_wide(xprow, plan.K0p >> 3, ps, S, valid, (S & 3) == 0,
-                                [&](int k, float x) { return k < S ? x : (k == xp_one ? 1.f : 0.f); }, srow[it & 1u]);
+                                [&](int k, float x) { return k < S ? x : (k == xp_one ? 1.f : 0.f); }, srow[it & 1u], nrow[it & 1u],
+                                [&](int k, float x) { return (k < S && valid) ? (x - sm->norm_mean[k]) * sm->norm_inv[k] : 0.f; });
       }
       fence_proxy_async();                                                // generic-proxy writes of xp -> visible to the tensor core
       __syncwarp();
@@ -787,8 +799,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1
           st_shared_v4(xrow + 2048u, pk[4], pk[5], pk[6], pk[7]);
           write_input_octets(xrow, 2, plan.K0m >> 3, tail);                // (K0m = 32 when S + A + 1 > 16)
         } else {
-          write_input_octets_local(xrow, plan.K0m >> 3, srow[it & 1],
-                                   [&](int k, float x) { return k < S ? (valid ? (x - sm->norm_mean[k]) * sm->norm_inv[k] : 0.f) : tail(k); });
+          write_input_octets_packed(xrow, plan.K0m >> 3, nrow[it & 1], S, tail);
         }
         fence_proxy_async();
         tc_fence_before();
