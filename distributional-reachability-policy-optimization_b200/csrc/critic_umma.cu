@@ -467,9 +467,8 @@ int critic_phase1(const drpo_critic_args& a, int* err_flag) {
     return DRPO_ERR_ARG;
   }
   {
-    dim3 grid(64, pt.n);
-    DRPO_LAUNCH(pack_images_kernel, grid, 256, 0, st, pt, reinterpret_cast<__nv_bfloat16*>(img));
-    DRPO_LAUNCH(gather_ctab_kernel, ct.n, 256, 0, st, ct, ctab);
+    dim3 grid(64, pt.n + ct.n);
+    DRPO_LAUNCH(pack_gather_kernel, grid, 256, 0, st, pt, reinterpret_cast<__nv_bfloat16*>(img), ct, ctab);
   }
   fp.n_ops = n_ops; fp.wimg = img; fp.ctab = ctab; fp.ctab_floats = ctab_off;
   {

@@ -595,9 +595,8 @@ static int solver_run(int mode, Builder& b, SolverParams& fp, SPlan& pl, const S
     return DRPO_ERR_ARG;
   }
   {
-    dim3 grid(64, b.pt.n);
-    DRPO_LAUNCH(pack_images_kernel, grid, 256, 0, st, b.pt, reinterpret_cast<__nv_bfloat16*>(w.img));
-    DRPO_LAUNCH(gather_ctab_kernel, b.ct.n, 256, 0, st, b.ct, w.ctab);
+    dim3 grid(64, b.pt.n + b.ct.n);
+    DRPO_LAUNCH(pack_gather_kernel, grid, 256, 0, st, b.pt, reinterpret_cast<__nv_bfloat16*>(w.img), b.ct, w.ctab);
   }
   fp.n_ops = b.n_ops; fp.sch.split = 0; fp.sch.n[0] = (uint8_t)b.n_ops;
   for (int i = 0; i < b.n_ops; ++i) fp.sch.order[0][i] = (uint8_t)i;
