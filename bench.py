@@ -30,7 +30,9 @@ CRITIC_WORKLOAD, CRITIC_B = "tracking", 65536
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_step_pipe_kernel launch at the bench workload (1 M rows), from the
 # `ncu --set full` capture of the shipped round-2 kernel (profiles/r2_ncu_full_rollout_step_1M_raw.csv: 52.6 MB read + 19.7 MB
 # written - 48 MB of states in; most of the 60 MB of outputs is still in L2 when the kernel ends); null when no capture exists
-TRAFFIC_BYTES_PER_LAUNCH = {("quadrotor", 1_000_000): 52561152 + 19717632}
+TRAFFIC_BYTES_PER_LAUNCH = {("quadrotor", 1_000_000): 52561152 + 19717632,
+                            # profiles/r2_ncu_full_rollout_step_safetygym400k_raw.csv / ..._cartpole100k_raw.csv (the 100 k-row launch stays in L2)
+                            ("safetygym-point-synthetic", 400_000): 124049408 + 218478080, ("cartpole-move", 100_000): 2475776}
 # the same for one critic_fused_kernel launch at B = 65 536, tracking dims (profiles/r2_ncu_full_critic_fused_64k_final_raw.csv:
 # 36.0 MB read + 366.6 MB written: the saved bf16 activations the dW kernel consumes)
 CRITIC_TRAFFIC_BYTES_PER_LAUNCH = {("tracking", 65536): 36007424 + 366628608}
