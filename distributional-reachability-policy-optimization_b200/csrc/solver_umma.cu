@@ -150,10 +150,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
     e.tm = tmem + ((uint32_t)((warp & 3) * 32) << 16); e.it = 0; e.arr = 0; e.err = err; e.Bpad = p.Bpad; e.prof = nullptr;
     const int S = p.S;
     const float alpha = MODE == MODE_ACTOR ? expf(*p.log_alpha) : 0.f;
-    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-    float sc0[2 * A], sc1[2 * A];                     // last-layer bias gradients (multiplier: sc0[0]; actor: actor / safe actor)
-#pragma unroll
-    for (int j = 0; j < 2 * A; ++j) { sc0[j] = 0.f; sc1[j] = 0.f; }
+    // Loss sums and last-layer bias gradients go straight to shared memory (warp sum + one atomic per warp at the few sites that
+    // produce them) instead of living in registers across the op loop: at 96 registers per thread every loop-carried value is a
+    // spill to L2 around each epilogue.  lacc = three doubles in the unused tail of the scalar slot of the column-sum accumulators.
+    const int scal = MODE == MODE_MULT ? MSLOT_SCAL : aslot_scal(A);
+    float* scacc = gacc + scal * HID;                 // [0..2A): first trained net's head bias gradient, [4..4+2A): the safe actor's
+    double* lacc = reinterpret_cast<double*>(scacc + 16);
+    auto add_loss = [&](int k, double v) { v = warp_sum_d(v); if (lane == 0) atomicAdd(&lacc[k], v); };
+    auto add_scal = [&](int k, float v) { v = warp_sum(v); if (lane == 0) atomicAdd(&scacc[k], v); };
 
     for (int t = 0; t < my_jobs; ++t) {
       const int tile = CLUSTER * (cid + t * n_clusters) + (int)crank;      // (no independent chains in these updates: sch.split = 0)
@@ -253,9 +257,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
             if (dbg) dbg[MODE == MODE_MULT ? 5 : 1] = qc;
           } else {
             // backward through both heads of the frozen constraint critic (m1 stashed in R0, l1 in R1)
-            if (e.g == 0 && e.valid) {
-              if (d.post == SP_QCUB_GRAD1) l0 += (double)(lam * qc); else l1 += (double)qc;
-            }
+            if (e.g == 0) add_loss(d.post == SP_QCUB_GRAD1 ? 0 : 1, !e.valid ? 0.0 : (d.post == SP_QCUB_GRAD1 ? (double)(lam * qc) : (double)qc));
             if (dbg) dbg[d.post == SP_QCUB_GRAD1 ? 6 : 12] = qc;
 #pragma unroll 1
             for (int hd = 0; hd < 2; ++hd) {
@@ -279,9 +281,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
           const float tgt = unsafe ? (p.ub - p.lam_eps) : 0.f;
           const float dlam = unsafe ? 2.f * (lu - tgt) * p.inv_bg : -0.5f * penalty * p.inv_bg;
           float dr[MAXO] = {e.valid ? dlam * (1.f - th * th) : 0.f, 0.f, 0.f, 0.f};
-          if (e.g == 0 && e.valid) {
-            l0 += (double)(ls * penalty); l1 += (double)((lu - tgt) * (lu - tgt));
-            sc0[0] += dr[0];
+          if (e.g == 0) {
+            add_loss(0, e.valid ? (double)(ls * penalty) : 0.0); add_loss(1, e.valid ? (double)((lu - tgt) * (lu - tgt)) : 0.0);
+            add_scal(0, dr[0]);
             if (dbg) { dbg[6] = out[0]; dbg[7] = lm; dbg[8] = dr[0]; }
           }
           epi_head_backward(e, TM_R1, dr, 1, p.hw_lam2, MSLOT_W2, MSLOT_B1, p.sv[MS_DH2], 1);
@@ -297,7 +299,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
           tmem_st_wait();
           float out[MAXO];
           head_combine(e, hpart, d.hb_off, out);
-          if (e.g == 0 && e.valid) l0 += (double)(alpha * logp - out[0]);
+          if (e.g == 0) add_loss(0, e.valid ? (double)(alpha * logp - out[0]) : 0.0);
           if (dbg) dbg[5] = out[0];
           float dq[MAXO] = {e.valid ? -p.inv_bg : 0.f, 0.f, 0.f, 0.f};
           epi_head_backward(e, TM_R1, dq, 1, p.hw_q2, -1, NO_SLOT, nullptr);
@@ -325,10 +327,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
             dpo[A + j] = e.valid ? (dx * psd[j] * peps[j] - wl) * 10.f * psg[j] * (1.f - psg[j]) : 0.f;
             if (dbg && j == 0) { dbg[perf ? 8 : 13] = dat; dbg[perf ? 9 : 14] = dpo[0]; dbg[perf ? 10 : 15] = dpo[A]; }
           }
-          if (e.g == 0 && e.valid) {
-            if (perf) l2 += (double)(logp + p.target_entropy);
+          if (e.g == 0) {
+            if (perf) add_loss(2, e.valid ? (double)(logp + p.target_entropy) : 0.0);
 #pragma unroll
-            for (int j = 0; j < 2 * A; ++j) { if (perf) sc0[j] += dpo[j]; else sc1[j] += dpo[j]; }
+            for (int j = 0; j < 2 * A; ++j) add_scal((perf ? 0 : 4) + j, dpo[j]);
           }
           const int n = perf ? 0 : 1;
           epi_head_backward(e, TM_R0, dpo, 2 * A, perf ? p.hw_actor2 : p.hw_safe2, aslot_w2(n, A), aslot_b1(n, A),
@@ -348,21 +350,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
       }
     }
     // ---- per-CTA results ---------------------------------------------------------------------------------------------------
-    if (e.g == 0) {
-      const int scal = MODE == MODE_MULT ? MSLOT_SCAL : aslot_scal(A);
-#pragma unroll
-      for (int j = 0; j < 2 * A; ++j) {
-        float v = warp_sum(sc0[j]); if (lane == 0) atomicAdd(&gacc[scal * HID + j], v);
-        v = warp_sum(sc1[j]); if (lane == 0) atomicAdd(&gacc[scal * HID + 4 + j], v);
-      }
-      l0 = warp_sum_d(l0); l1 = warp_sum_d(l1); l2 = warp_sum_d(l2);
-      double* lsm = reinterpret_cast<double*>(hp);
-      if (lane == 0) { lsm[3 * (warp & 3)] = l0; lsm[3 * (warp & 3) + 1] = l1; lsm[3 * (warp & 3) + 2] = l2; }
-    }
     named_bar_sync(1, EPI_THREADS);
     if (threadIdx.x == 0) {
-      const double* lsm = reinterpret_cast<const double*>(hp);
-      for (int k = 0; k < 3; ++k) p.loss_part[4 * blockIdx.x + k] = lsm[k] + lsm[3 + k] + lsm[6 + k] + lsm[9 + k];
+      for (int k = 0; k < 3; ++k) p.loss_part[4 * blockIdx.x + k] = lacc[k];
       p.loss_part[4 * blockIdx.x + 3] = 0.0;
     }
     for (int i = threadIdx.x; i < p.nv * HID; i += EPI_THREADS) p.gacc_out[(int64_t)blockIdx.x * p.nv * HID + i] = gacc[i];
