@@ -83,10 +83,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
     e.prof = (blockIdx.x == 0 && (threadIdx.x & 127) == 0) ? p.prof : nullptr;          // first thread of every group
     const int S = p.S, D = p.D;
     const float alpha = expf(*p.log_alpha);
-    double loss_q = 0.0, loss_c = 0.0;
-    float sc_q0 = 0.f, sc_q1 = 0.f, sc_m[C], sc_l[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) { sc_m[c] = 0.f; sc_l[c] = 0.f; }
+    // Loss sums and head-bias gradients go straight to shared memory (warp sum + one atomic per warp at the two sites that produce
+    // them) instead of living in registers across the op loop: at 96 registers per thread a loop-carried value is a spill to L2.
+    // lacc = two doubles in the unused tail of the scalar slot of the column-sum accumulators.
+    float* scacc = gacc + SLOT_SCAL * HID;
+    double* lacc = reinterpret_cast<double*>(scacc + 16);
+    auto add_loss = [&](int k, double v) { v = warp_sum_d(v); if (lane == 0) atomicAdd(&lacc[k], v); };
+    auto add_scal = [&](int k, float v) { v = warp_sum(v); if (lane == 0) atomicAdd(&scacc[k], v); };
 
     for (int t = 0; t < my_jobs; ++t) {
       const int job = cid + t * n_clusters, chain = sched_chain(p.sch, job), n_chain = p.sch.n[chain];
@@ -225,10 +228,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
           head_combine(e, hpart, d.hb_off, oq);
           const float err_q = oq[0] - q_target;
           float dq[MAXO] = {e.valid ? err_q * p.inv_bg : 0.f, 0.f, 0.f, 0.f};
-          if (e.g == 0 && e.valid) {
-            loss_q += 0.5 * (double)err_q * err_q;
-            if (i == 0) sc_q0 += dq[0]; else sc_q1 += dq[0];
-            if (p.dbg) { p.dbg[gr * 16 + 8 + i] = oq[0]; p.dbg[gr * 16 + 12 + i] = dq[0]; }
+          if (e.g == 0) {
+            add_loss(0, e.valid ? 0.5 * (double)err_q * err_q : 0.0);
+            add_scal(i, dq[0]);
+            if (p.dbg && e.valid) { p.dbg[gr * 16 + 8 + i] = oq[0]; p.dbg[gr * 16 + 12 + i] = dq[0]; }
           }
           epi_head_backward(e, TM_R1, dq, 1, p.hw_q[i], slot_q_w2(i), slot_q_b1(i), p.sv[SV_Q_DH2 + i]);
           hpart[0] = 0.f;
@@ -241,6 +244,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
           named_bar_sync(1, EPI_THREADS);
           head_combine(e, hpart, d.hb_off, ol);
           float dmean[MAXO] = {0.f, 0.f, 0.f, 0.f}, dls[MAXO] = {0.f, 0.f, 0.f, 0.f};
+          double lc = 0.0;
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const float h = cvr[c], mu = om[c];
@@ -255,11 +259,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
             if (e.valid) {
               dmean[c] = du / var * p.inv_bgc;
               dls[c] = (1.f - db * db / var) * p.inv_bgc * dsoftplus(y1 + 4.f) * dsoftplus(4.f - x);
-              if (e.g == 0) {
-                loss_c += (double)(du * du / (2.f * var) + db * db / (2.f * var) + logf(sd));
-                sc_m[c] += dmean[c]; sc_l[c] += dls[c];
-              }
+              lc += (double)(du * du / (2.f * var) + db * db / (2.f * var) + logf(sd));
             }
+          }
+          if (e.g == 0) {
+            add_loss(1, lc);
+#pragma unroll
+            for (int c = 0; c < C; ++c) { add_scal(2 + c, dmean[c]); add_scal(2 + C + c, dls[c]); }
           }
           if (p.dbg && e.g == 0 && e.valid) {
             float* dd = p.dbg + gr * 16;
@@ -280,25 +286,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
       }
     }
     // ---- per-CTA results ---------------------------------------------------------------------------------------------------
-    if (e.g == 0) {
-      float v;
-      v = warp_sum(sc_q0); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 0], v);
-      v = warp_sum(sc_q1); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 1], v);
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        v = warp_sum(sc_m[c]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 2 + c], v);
-        v = warp_sum(sc_l[c]); if (lane == 0) atomicAdd(&gacc[SLOT_SCAL * HID + 2 + C + c], v);
-      }
-      loss_q = warp_sum_d(loss_q); loss_c = warp_sum_d(loss_c);
-      double* lsm = reinterpret_cast<double*>(hp);                       // hp is idle now
-      if (lane == 0) { lsm[2 * (warp & 3)] = loss_q; lsm[2 * (warp & 3) + 1] = loss_c; }
-    }
     named_bar_sync(1, EPI_THREADS);
-    if (threadIdx.x == 0) {
-      const double* lsm = reinterpret_cast<const double*>(hp);
-      p.loss_part[2 * blockIdx.x] = lsm[0] + lsm[2] + lsm[4] + lsm[6];
-      p.loss_part[2 * blockIdx.x + 1] = lsm[1] + lsm[3] + lsm[5] + lsm[7];
-    }
+    if (threadIdx.x == 0) { p.loss_part[2 * blockIdx.x] = lacc[0]; p.loss_part[2 * blockIdx.x + 1] = lacc[1]; }
     for (int i = threadIdx.x; i < p.nv * HID; i += EPI_THREADS) p.gacc_out[(int64_t)blockIdx.x * p.nv * HID + i] = gacc[i];
   }
   tc_fence_before();
