@@ -92,7 +92,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
     auto add_scal = [&](int k, float v) { v = warp_sum(v); if (lane == 0) atomicAdd(&scacc[k], v); };
 
     for (int t = 0; t < my_jobs; ++t) {
-      const int job = cid + t * n_clusters, chain = sched_chain(p.sch, job), n_chain = p.sch.n[chain];
+      const int job = cid + t * n_clusters, chain = sched_chain(p.sch, job, n_clusters), n_chain = p.sch.n[chain];
       const int tile = CLUSTER * sched_pair(p.sch, job) + (int)crank;
       e.grow = (int64_t)tile * TILE + e.row;
       e.valid = e.grow < p.B;

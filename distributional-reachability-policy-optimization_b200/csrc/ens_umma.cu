@@ -14,7 +14,7 @@ namespace cu {
 
 constexpr int ENS_MAX_MEMBERS = 8, ENS_OPS = 6;
 struct EnsSched { uint8_t order[ENS_MAX_MEMBERS][8]; uint8_t n[ENS_MAX_MEMBERS]; int members; };
-__device__ __forceinline__ int sched_chain(const EnsSched& s, int job) { return job % s.members; }
+__device__ __forceinline__ int sched_chain(const EnsSched& s, int job, int /*n_clusters*/) { return job % s.members; }
 __device__ __forceinline__ int sched_pair(const EnsSched& s, int job) { return job / s.members; }
 __device__ __forceinline__ int sched_my_jobs(const EnsSched& s, int n_tiles, int cid, int n_clusters) {
   return ((n_tiles / 2) * s.members - cid + n_clusters - 1) / n_clusters;
@@ -78,7 +78,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
     const int S = p.S, A = p.A, D = S + A, O = S + 1;
     float hpart[MAXO] = {0.f, 0.f, 0.f, 0.f};
     for (int t = 0; t < my_jobs; ++t) {
-      const int job = cid + t * n_clusters, slot = sched_chain(p.sch, job);
+      const int job = cid + t * n_clusters, slot = sched_chain(p.sch, job, n_clusters);
       const int tile = CLUSTER * sched_pair(p.sch, job) + (int)crank;
       e.grow = (int64_t)tile * TILE + e.row;
       e.valid = e.grow < p.B;

@@ -63,7 +63,14 @@ constexpr uint8_t NO_SLOT = 255;           // EOp::bias_slot of a backward op th
 // loss); job j of the grid is chain (j & 1) of tile pair (j >> 1), so small batches spread over twice as many SMs and a large
 // batch is dealt in half-size pieces (shorter tail).
 struct JobSched { uint8_t order[2][32]; uint8_t n[2]; uint8_t split; uint8_t pad; };
-__device__ __forceinline__ int sched_chain(const JobSched& s, int job) { return s.split ? (job & 1) : 0; }
+// The two chains are not equally long (critic: 79 k vs 89 k cycles), and with an even number of CTA pairs job parity = CTA-pair parity:
+// the chain of a tile pair's two jobs is swapped every `n_clusters / 2` tile pairs, so a CTA pair alternates chains round by round
+// instead of running the long one every time.
+__device__ __forceinline__ int sched_chain(const JobSched& s, int job, int n_clusters) {
+  if (!s.split) return 0;
+  const int half = n_clusters > 1 ? (n_clusters >> 1) : 1;
+  return (job & 1) ^ (((job >> 1) / half) & 1);
+}
 __device__ __forceinline__ int sched_pair(const JobSched& s, int job) { return s.split ? (job >> 1) : job; }
 __device__ __forceinline__ int sched_my_jobs(const JobSched& s, int n_tiles, int cid, int n_clusters) {
   const int jobs = (n_tiles / 2) * (s.split ? 2 : 1);
@@ -530,7 +537,7 @@ __device__ __forceinline__ void fused_producer(const P& p, FusedSmem* sm, uint8_
   if (elect_one()) {
     uint32_t s = 0, ph = 0;
     for (int t = 0; t < my_jobs; ++t) {
-      const int chain = sched_chain(p.sch, cid + t * n_clusters);
+      const int chain = sched_chain(p.sch, cid + t * n_clusters, n_clusters);
       for (int oi = 0; oi < p.sch.n[chain]; ++oi) {
         const FOp op = p.op[p.sch.order[chain][oi]];
         const uint32_t bytes = 64u * (op.kp + (op.bias ? KBIAS : 0)) * 2u;
@@ -563,7 +570,7 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
   const int round = stages >= 4 ? 4 : 2;
   const uint32_t idesc = make_idesc(64);
   for (int t = 0; t < my_jobs; ++t) {
-    const int chain = sched_chain(p.sch, cid + t * n_clusters);
+    const int chain = sched_chain(p.sch, cid + t * n_clusters, n_clusters);
     for (int oi = 0; oi < p.sch.n[chain]; ++oi, ++it) {
       const int o = p.sch.order[chain][oi];
       const FOp op = p.op[o];
