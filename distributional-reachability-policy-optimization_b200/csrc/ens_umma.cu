@@ -189,6 +189,7 @@ int ens_bf16_run(const drpo_ensemble& e, int m0, int m1, int per_member_inputs, 
                  int64_t workspace_bytes, void* stream, int* err_flag) {
   cudaStream_t st = (cudaStream_t)stream;
   const int S = e.state_dim, A = e.action_dim, O = S + 1, Kx = round_up(S + A, 16);
+  const int Kh = round_up(e.hidden, 16);                     // K of the hidden-input layers: 208 for the reference's 200 (13 k-steps, not 16)
   DRPO_CHECK_ARG(ens_bf16_supported(e), "ensemble forward (bf16): needs hidden <= 256 and state_dim + action_dim <= 64");
   EnsParams fp; memset(&fp, 0, sizeof(fp));
   const int64_t Bpad = (batch + CLUSTER * TILE - 1) / (CLUSTER * TILE) * (CLUSTER * TILE);
@@ -210,7 +211,7 @@ int ens_bf16_run(const drpo_ensemble& e, int m0, int m1, int per_member_inputs, 
       for (int l = 0; l < ENS_OPS; ++l) {
         PackEntry& pe = pt.e[pt.n++];
         pe.W = n.l[l].w; pe.bias = n.l[l].b; pe.transposed = 0; pe.n_real = n.l[l].out_dim; pe.k_real = n.l[l].in_dim;
-        pe.kp = l == 0 ? Kx : HID; pe.dst = img_off / 2;
+        pe.kp = l == 0 ? Kx : Kh; pe.dst = img_off / 2;
         FOp& op = fp.op[s * ENS_OPS + l];
         op.w_off[0] = (uint32_t)img_off; op.kp = (uint16_t)pe.kp; op.parts = 1; op.bias = 1; op.early = 0;
         op.a_src[0] = (uint8_t)(l == 0 ? A_XS0 : (l == 1 || l == 3 || l == 5 ? A_R0 : A_R1));

@@ -620,7 +620,8 @@ __device__ __forceinline__ void fused_issuer(const P& p, FusedSmem* sm, uint8_t*
               } else {
                 const uint32_t a_tmem = tmem + (src == A_R0 ? TM_R0 : TM_R1);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) mma_ts_p(d_tmem, a_tmem + k * 8, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
+                for (int k = 0; k < 16; ++k)                       // (nk < 16: a hidden width below 256, e.g. the ensemble's 200 -> 13 k-steps)
+                  if (k < nk) mma_ts_p(d_tmem, a_tmem + k * 8, b_lo + k * 16, b_hi, idesc, (part | k) != 0);
               }
               if (op.bias) mma_ss_p(d_tmem, ones_lo, ones_hi, b_lo + nk * 16, b_hi, idesc, 1u);      // + bias (ones x bias block)
               tc_commit_multicast(&sm->empty[s], (uint16_t)3);      // frees the stage in both CTAs of the pair
