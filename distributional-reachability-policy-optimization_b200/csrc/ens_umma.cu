@@ -30,7 +30,7 @@ struct EnsParams {
   const float *norm_mean, *norm_std, *min_lv, *max_lv;
   float *means, *log_vars; int64_t slot_stride_out;                          // forward mode
   int sample; NoiseView noise; float *next_states, *rewards;                 // sample mode (one member)
-  int64_t B, Bpad; int S, A, Kx, n_tiles;
+  int64_t B, Bpad; int S, A, Kx, Kh, n_tiles;               // Kh: padded hidden width = K of the hidden-input layers
   int* err_flag;
 };
 
@@ -106,7 +106,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(F_THREADS, 1) 
 #pragma unroll 1
       for (int oi = 0; oi < ENS_OPS; ++oi) {
         if (oi != 3 && oi != 5) {
-          epi_forward_halfwise(e, oi == 1 ? TM_R1 : TM_R0, nullptr, 0, 0, hpart, false, 2);
+          epi_forward_halfwise(e, oi == 1 ? TM_R1 : TM_R0, nullptr, 0, 0, hpart, false, 2, p.Kh);
         } else {
           // output layer: columns 0..S of accumulator 0 hold [next_state - state, reward] (oi == 3) or the raw log-variance (oi == 5)
           epi_wait_acc(e);
@@ -193,7 +193,7 @@ int ens_bf16_run(const drpo_ensemble& e, int m0, int m1, int per_member_inputs, 
   DRPO_CHECK_ARG(ens_bf16_supported(e), "ensemble forward (bf16): needs hidden <= 256 and state_dim + action_dim <= 64");
   EnsParams fp; memset(&fp, 0, sizeof(fp));
   const int64_t Bpad = (batch + CLUSTER * TILE - 1) / (CLUSTER * TILE) * (CLUSTER * TILE);
-  fp.B = batch; fp.Bpad = Bpad; fp.S = S; fp.A = A; fp.Kx = Kx; fp.n_tiles = (int)(Bpad / TILE);
+  fp.B = batch; fp.Bpad = Bpad; fp.S = S; fp.A = A; fp.Kx = Kx; fp.Kh = Kh; fp.n_tiles = (int)(Bpad / TILE);
   const size_t fixed = (size_t)TILE * Kx * 2 + TILE * KBIAS * 2 + (size_t)TILE * 64 * sizeof(float) + sizeof(FusedSmem);
   int stages = (int)((232448 - 1024 - fixed) / CHUNK_BYTES);
   if (stages > 6) stages = 6;

@@ -343,11 +343,17 @@ __device__ __forceinline__ void epi_forward(Epi& e, uint32_t out_region, __nv_bf
 // whole block through local memory (ncu source page of the SiLU ensemble kernel: 58 STL.64 + as many LDL.64 per thread and layer,
 // 0.8 G L2 sectors per launch - the epilogue was waiting on L2 round trips of its own spills).  Costs a second tcgen05.ld round trip
 // and frees the accumulator ~200 cycles later.
+// n_cols: columns of the layer the NEXT op reads (its K); 32-column pieces beyond it are neither loaded nor stored (the ensemble's
+// hidden width 200 -> K = 208: the last group, whose accumulator completes last, skips its second half)
 __device__ __forceinline__ void epi_forward_halfwise(Epi& e, uint32_t out_region, __nv_bfloat16* save, int hw_off, int no,
-                                                     float (&hpart)[MAXO], bool wait_all, int act = 0) {
+                                                     float (&hpart)[MAXO], bool wait_all, int act = 0, int n_cols = HID) {
   epi_wait_acc(e);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
+    if (e.g * 64 + half * 32 >= n_cols) {                    // (warp-uniform)
+      if (half == 1) epi_free_acc(e);
+      continue;
+    }
     uint32_t raw[32];
     tmem_ld32(e.tm + TM_ACC + e.g * 64 + half * 32, raw);
     tmem_ld_wait();
